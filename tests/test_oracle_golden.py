@@ -1,0 +1,91 @@
+"""Pin the CPU oracle (oracle/ngsdist_oracle.c) against the reference's outputs.
+
+The goldens in tests/golden/*.dist were written by the unmodified reference binary
+(tests/golden/make_golden.py); the oracle must reproduce every file byte for byte after the
+reference's own "%.10f" formatting (ngsDist.cpp:282-287, gen_func.cpp:479-496).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from util import format_dist, golden_text, load_bin, manifest, parse_flags, read_text_input
+
+MAN = manifest()
+
+
+def test_taus_known_answers():
+    # GSL's own test-suite value for gsl_rng_taus and the App. G vectors
+    t = oracle.Taus(1)
+    for _ in range(9999):
+        t.get()
+    assert t.get() == 2733957125
+    t = oracle.Taus(0)  # seed 0 maps to 1
+    assert [t.get() for _ in range(5)] == [802792108, 4084684829, 2342628799, 320516809, 984487517]
+    t = oracle.Taus(12345)
+    assert [t.get() for _ in range(5)] == [604716153, 3670082527, 2361899765, 2078690716, 1650372189]
+    t = oracle.Taus(12345)
+    assert list(t.boot_map(10, 1)) == [1, 8, 5, 4, 3, 6, 1, 9, 3, 1]
+
+
+def test_survey_appendix_g_vectors():
+    raw = np.array([[(0.7, 0.2, 0.1), (0.1, 0.3, 0.6), (0.25, 0.5, 0.25)],
+                    [(0.05, 0.05, 0.9), (1 / 3, 1 / 3, 1 / 3), (0.6, 0.3, 0.1)],
+                    [(0.4, 0.4, 0.2), (0.8, 0.1, 0.1), (0.0, 0.5, 0.5)],
+                    [(0.9, 0.05, 0.05), (0.2, 0.2, 0.6), (0.1, 0.8, 0.1)]])
+    rows = [
+        (dict(indep=True, evol_model=0), "0.5466666667 0.5212500000 0.4862500000"),
+        (dict(indep=False, evol_model=0), "0.6875626874 0.6246339598 0.5623311575"),
+        (dict(indep=True, evol_model=0, pairwise_del=True), "0.5650000000 0.5212500000 0.4983333333"),
+        (dict(indep=True, evol_model=2, avg_nuc_dist=True), "1.0397207708 1.0523261096 0.9682381360"),
+        (dict(call_geno=True, evol_model=0), "0.6250000000 0.6250000000 0.5000000000"),
+        (dict(call_geno=True, evol_model=1, pairwise_del=True), "1.0986122887 0.9808292530 0.6931471806"),
+    ]
+    for kw, want in rows:
+        d = oracle.run_job(raw, **kw)[0]["dist"]
+        assert "%.10f %.10f %.10f" % (d[0, 1], d[0, 2], d[1, 2]) == want, kw
+    reps = oracle.run_job(raw, indep=True, evol_model=0, n_boot_rep=3, boot_block_size=1, seed=12345)
+    d = reps[3]["dist"]
+    assert "%.10f %.10f %.10f" % (d[0, 1], d[0, 2], d[1, 2]) == "0.5354166667 0.5137500000 0.4875000000"
+
+
+@pytest.mark.parametrize("case", MAN["binary"], ids=lambda c: c["name"])
+def test_oracle_reproduces_reference_binary_input(case):
+    kw, _ = parse_flags(case["flags"])
+    raw = load_bin(case["input"], case["n_ind"], case["n_sites"])
+    res = oracle.run_job(raw, kind=0, **kw)
+    assert format_dist([r["dist"] for r in res]) == golden_text(case["name"])
+
+
+@pytest.mark.parametrize("case", MAN["text"], ids=lambda c: c["name"])
+def test_oracle_reproduces_reference_text_input(case):
+    kw, probs = parse_flags(case["flags"])
+    data = read_text_input(case["input"], case["n_ind"], case["n_sites"], probs)
+    if probs:
+        res = oracle.run_job(data, kind=1, **kw)
+    else:
+        P = oracle.frontend_geno(data)
+        n_sites = P.shape[1]
+        rng = oracle.Taus(kw["seed"])
+        res = []
+        args = dict(score=oracle.score_matrix(kw["avg_nuc_dist"]), indep=True, pairwise_del=kw["pairwise_del"],
+                    tot_sites=kw["tot_sites"], evol_model=kw["evol_model"])
+        for rep in range(kw["n_boot_rep"] + 1):
+            if rep == 0:
+                res.append(oracle.distances(P, **args))
+            else:
+                n_sites -= n_sites % kw["boot_block_size"]
+                sm = rng.boot_map(n_sites // kw["boot_block_size"], kw["boot_block_size"])
+                res.append(oracle.distances(P, site_map=sm, **args))
+    assert format_dist([r["dist"] for r in res]) == golden_text(case["name"])
+
+
+def test_synth_generator_is_deterministic_and_marks_missing():
+    a = oracle.synth_raw(20251018, 0.1, 11, 200)
+    b = oracle.synth_raw(20251018, 0.1, 11, 200)
+    assert np.array_equal(a, b)
+    miss = (a == 1.0 / 3.0).all(axis=2)
+    assert 0.05 < miss.mean() < 0.15
+    # chunked generation equals whole generation
+    c = oracle.synth_raw(20251018, 0.1, 11, 50, site0=150)
+    assert np.array_equal(a[150:], c)
+    assert ((a > 0) & (a < 1)).all()
