@@ -1,0 +1,147 @@
+/* ngsdist_b200.h -- C ABI of the B200-native ngsDist pairwise-distance hot path.
+ *
+ * ngsDist has no plugin / FFI interface; its only internal seam is the code between
+ * "read_geno returned" (ngsDist.cpp:156) and "print matrix" (ngsDist.cpp:282-287):
+ *   - the per-individual-site front end      ngsDist.cpp:161-174 (+ the normalisation half that lives in the
+ *                                             reader, shared/read_data.cpp:37-45,83-99)
+ *   - the pair dispatch + gen_dist()          ngsDist.cpp:197-269, 325-412
+ *   - the bootstrap re-mapping                ngsDist.cpp:235-238, 416-437 (RNG stays on the host)
+ * This library replaces exactly that code.  A maintainer keeps parse_args.cpp, the readers and the writer and
+ * calls the entry points below instead (INTEGRATION.md shows the patch).
+ *
+ * Conventions: plain pointers and sizes, no C++/torch types; every function returns 0 on success or a
+ * negative ngsd_status and records a message retrievable with ngsd_last_error() -- the host turns it into the
+ * reference's error(__FUNCTION__, msg) (shared/gen_func.cpp:12-18).  No CPU fallback exists: without a CUDA
+ * device ngsd_create fails with NGSD_ERR_CUDA.  One host thread drives one context; contexts are independent
+ * (one per GPU / per rank).
+ */
+#ifndef NGSDIST_B200_H
+#define NGSDIST_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGSD_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define NGSD_API __attribute__((visibility("default")))
+#else
+#define NGSD_API
+#endif
+
+typedef enum {
+  NGSD_OK = 0,
+  NGSD_ERR_ARG = -1,       /* invalid argument / configuration                                    */
+  NGSD_ERR_CUDA = -2,      /* CUDA runtime failure (including "no device")                        */
+  NGSD_ERR_NAN = -3,       /* "NaN found! Is the file format correct?"   (read_data.cpp:42-45)    */
+  NGSD_ERR_THRESH = -4,    /* "missing data threshold must be smaller than calling genotype
+                              threshold!"                                (gen_func.cpp:887-888)   */
+  NGSD_ERR_MODEL = -5,     /* evol_model 3..6 "not yet supported" / invalid (ngsDist.cpp:387-401) */
+  NGSD_ERR_STATE = -6,     /* call order violated (e.g. distances before all sites were pushed)   */
+  NGSD_ERR_GENO = -7       /* "Genotypes must be coded as {-1,0,1,2} !"  (read_data.cpp:91-92)    */
+} ngsd_status;
+
+/* How raw values were read; selects the reader-side half of the front end (H2 in SURVEY §8a). */
+typedef enum {
+  NGSD_INPUT_BINARY_GL = 0,  /* read_data.cpp:29-47: log() unless log scale, -inf -> -1e15, normalise, NaN is fatal */
+  NGSD_INPUT_TEXT_GL = 1,    /* read_data.cpp:83-87,98: log() unless log scale, no clamp, normalise                 */
+  NGSD_INPUT_GENOTYPES = 2   /* read_data.cpp:88-95,98: codes {-1,0,1,2}; pushed with ngsd_push_genotypes          */
+} ngsd_input_kind;
+
+/* Mirrors the fields of `params` (ngsDist.hpp:11-44) that the hot path reads. */
+typedef struct {
+  uint64_t n_ind;            /* params.n_ind                                                        */
+  uint64_t n_sites;          /* params.n_sites (all sites of the data set)                          */
+  uint64_t tot_sites;        /* params.tot_sites; > 0 overrides the per-pair count (ngsDist.cpp:372) */
+  double score[9];           /* params.score[g1][g2], row-major (parse_args.cpp:25-27,134-137)      */
+  int32_t evol_model;        /* 0 raw p-distance, 1 -log(1-d), 2 JC69 (ngsDist.cpp:378-386)         */
+  int32_t pairwise_del;      /* params.pairwise_del                                                  */
+  int32_t indep_geno;        /* params.indep_geno AFTER the forcing rules of ngsDist.cpp:55-62      */
+  int32_t call_geno;         /* params.call_geno                                                     */
+  double N_thresh;           /* params.N_thresh                                                      */
+  double call_thresh;        /* params.call_thresh                                                   */
+  int32_t input_is_log;      /* params.in_logscale as given on the command line                     */
+  int32_t input_kind;        /* ngsd_input_kind                                                      */
+  int32_t device;            /* CUDA device ordinal this context owns                                */
+  int32_t reserved;          /* must be 0                                                            */
+} ngsd_cfg;
+
+typedef struct ngsd_ctx ngsd_ctx;
+
+/* Per-call device timings of the last ngsd_distances()/ngsd_push_* call, milliseconds, measured with CUDA
+ * events on the context's stream.  launches = number of this library's kernels launched by that call. */
+typedef struct {
+  float frontend_ms;         /* K1 front-end kernel(s)                                   */
+  float count_ms;            /* K3 mask-count kernel                                     */
+  float dist_ms;             /* K2 DMMA contraction (or K2b pair-site EM) kernel         */
+  float epilogue_ms;         /* K4 split reduction + epilogue kernel                     */
+  float total_ms;            /* first launch to last launch of the call                  */
+  int32_t launches;
+  int32_t dist_ctas;         /* grid size of the distance kernel                         */
+  uint64_t dist_dmma;        /* warp-level DMMA.8x8x4 instructions the K2 launch issued  */
+  uint64_t active_sites;     /* sites with non-zero weight in the call                   */
+} ngsd_timing;
+
+NGSD_API void ngsd_default_cfg(ngsd_cfg *cfg);   /* init_pars (parse_args.cpp:6-37) for the fields above */
+
+/* Creates a context: validates cfg (NGSD_ERR_THRESH when N_thresh > call_thresh with call_geno, NGSD_ERR_MODEL for
+ * evol_model outside 0..2, NGSD_ERR_ARG for tot_sites with pairwise_del as parse_args.cpp:209-210), selects the device
+ * and allocates the packed operand planes for n_ind x n_sites.  The library owns all device memory. */
+NGSD_API int ngsd_create(const ngsd_cfg *cfg, ngsd_ctx **out);
+NGSD_API int ngsd_destroy(ngsd_ctx *ctx);
+NGSD_API const char *ngsd_last_error(const ngsd_ctx *ctx);   /* ctx may be NULL: last error of ngsd_create */
+
+/* Front end (H2+H3+H4).  `raw` holds n sites starting at site0 exactly as the reader obtained them, binary layout
+ * [site][ind][3] doubles (read_data.cpp:28-31), un-normalised.  Replaces read_data.cpp:37-45 / :83-99 (normalisation)
+ * and ngsDist.cpp:165-174 (call_geno + exp).  site0 must be a multiple of 64 (chunks are independent, so the host reader
+ * never holds the whole data set).  The host variant copies asynchronously from `raw` (pinned memory recommended) and
+ * returns when the copy has been consumed; the device variant reads a device pointer in place. */
+NGSD_API int ngsd_push_sites(ngsd_ctx *ctx, const double *raw_host, uint64_t site0, uint64_t n);
+NGSD_API int ngsd_push_sites_device(ngsd_ctx *ctx, const double *raw_dev, uint64_t site0, uint64_t n);
+/* Genotype input (no --probs): codes [site][ind] in {-1,0,1,2}; NGSD_ERR_GENO for anything > 2. */
+NGSD_API int ngsd_push_genotypes(ngsd_ctx *ctx, const int8_t *codes_host, uint64_t site0, uint64_t n);
+/* Completes the front end: checks that every site was pushed and raises the deferred NGSD_ERR_NAN. */
+NGSD_API int ngsd_frontend(ngsd_ctx *ctx);
+
+/* One distance matrix = one pass of ngsDist.cpp:244-269 (all pairs through gen_dist).
+ *   block_counts == NULL : replicate 0, all n_sites sites, weight 1.
+ *   block_counts != NULL : a bootstrap replicate.  block_counts[b] = how many times source block b was drawn by
+ *                          rnd_map_data (ngsDist.cpp:416-437) for this replicate; n_blocks * block_size sites are
+ *                          used (the persistent truncation of ngsDist.cpp:236).  The RNG stays on the host.
+ *   out      : n_ind x n_ind row-major, symmetric, 0.0 diagonal (ngsDist.cpp:200,411), model-transformed distances.
+ *   num_opt  : optional, same shape: the raw accumulator `dist` before normalisation (the --verbose 3 value, :366-367).
+ *   cnt_opt  : optional, same shape: the number of valid sites per pair BEFORE the tot_sites override.
+ * All three are host pointers (may be pageable). */
+NGSD_API int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_blocks, uint64_t block_size,
+                   double *out, double *num_opt, uint64_t *cnt_opt);
+
+/* Host-side helper with the reference's RNG semantics (gsl_rng_taus; ngsDist.cpp:179-180, gen_func.cpp:117-119):
+ * state[3] is seeded by ngsd_taus_seed and advanced by n_blocks draws per call of ngsd_boot_block_counts, which
+ * fills counts[n_blocks] for one replicate exactly as rnd_map_data would have re-pointed the blocks. */
+NGSD_API void ngsd_taus_seed(uint32_t state[3], uint32_t seed);
+NGSD_API uint32_t ngsd_taus_get(uint32_t state[3]);
+NGSD_API void ngsd_boot_block_counts(uint32_t state[3], uint64_t n_blocks, uint32_t *counts);
+
+/* Inspection (tests, --verbose): copy the front-end results back in the reference's own shapes.
+ *   P    : [ind][site][3] normal-space posteriors as gen_dist would read them (params.geno_lkl).
+ *   miss : [ind][site] 1 where miss_data() is true (gen_func.cpp:862-868). */
+NGSD_API int ngsd_get_posteriors(ngsd_ctx *ctx, double *P_host, uint8_t *miss_host);
+
+/* Measurement support (bench.py): device-side synthetic raw GLs (SURVEY §8(d) generator, bit-identical to the CPU
+ * restatement), timings of the last call, the context's stream, and an FP64 DMMA issue-rate probe used as the
+ * roofline denominator when MEASURED_PEAKS.json has no FP64 figure. */
+NGSD_API int ngsd_synth_raw_device(ngsd_ctx *ctx, double *raw_dev, uint64_t seed, double miss_rate, uint64_t site0, uint64_t n);
+NGSD_API int ngsd_get_timing(const ngsd_ctx *ctx, ngsd_timing *t);
+NGSD_API void *ngsd_stream(ngsd_ctx *ctx);                       /* cudaStream_t */
+NGSD_API int ngsd_probe_fp64_tflops(int device, double *dmma_tflops);
+NGSD_API void *ngsd_host_alloc(uint64_t bytes);                  /* pinned host memory for push/out buffers */
+NGSD_API void ngsd_host_free(void *p);
+NGSD_API int ngsd_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGSDIST_B200_H */

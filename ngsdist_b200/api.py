@@ -1,0 +1,300 @@
+"""ctypes mirror of include/ngsdist_b200.h.
+
+`Params` carries the fields of the reference's `params` struct (ngsDist.hpp:11-44) that the hot path reads, under
+the reference's own names; `NgsDistB200` drives the library the way main() drives gen_dist (ngsDist.cpp:156-289):
+front end once, then one matrix for the full data set and one per bootstrap replicate, with the host-side
+gsl_rng_taus stream deciding the block multiplicities.
+"""
+import ctypes as C
+import os
+import subprocess
+from dataclasses import dataclass, field
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "libngsdist_b200.so")
+
+ABI_SYMBOLS = [
+    "ngsd_abi_version", "ngsd_default_cfg", "ngsd_create", "ngsd_destroy", "ngsd_last_error", "ngsd_push_sites",
+    "ngsd_push_sites_device", "ngsd_push_genotypes", "ngsd_frontend", "ngsd_distances", "ngsd_taus_seed", "ngsd_taus_get",
+    "ngsd_boot_block_counts", "ngsd_get_posteriors", "ngsd_synth_raw_device", "ngsd_get_timing", "ngsd_stream",
+    "ngsd_probe_fp64_tflops", "ngsd_host_alloc", "ngsd_host_free",
+]
+
+
+class NgsDistError(RuntimeError):
+    """An error the reference would have reported through error(__FUNCTION__, msg) (gen_func.cpp:12-18)."""
+
+    def __init__(self, code, msg):
+        super().__init__("[ngsd %d] %s" % (code, msg))
+        self.code = code
+        self.msg = msg
+
+
+class _Cfg(C.Structure):
+    _fields_ = [("n_ind", C.c_uint64), ("n_sites", C.c_uint64), ("tot_sites", C.c_uint64), ("score", C.c_double * 9),
+                ("evol_model", C.c_int32), ("pairwise_del", C.c_int32), ("indep_geno", C.c_int32), ("call_geno", C.c_int32),
+                ("N_thresh", C.c_double), ("call_thresh", C.c_double), ("input_is_log", C.c_int32), ("input_kind", C.c_int32),
+                ("device", C.c_int32), ("reserved", C.c_int32)]
+
+
+class Timing(C.Structure):
+    _fields_ = [("frontend_ms", C.c_float), ("count_ms", C.c_float), ("dist_ms", C.c_float), ("epilogue_ms", C.c_float),
+                ("total_ms", C.c_float), ("launches", C.c_int32), ("dist_ctas", C.c_int32), ("dist_dmma", C.c_uint64),
+                ("active_sites", C.c_uint64)]
+
+    def as_dict(self):
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+def lib_path():
+    return _LIB
+
+
+def build_library(verbose=False):
+    """Compile csrc/*.cu for sm_100a into libngsdist_b200.so (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"] + ([] if verbose else ["-s"])
+    subprocess.check_call(cmd)
+    return _LIB
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library; never falls back to anything else."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB):
+        raise ImportError("libngsdist_b200.so is not built (run `python -c 'import __graft_entry__ as g; g.build()'` or "
+                          "`make -C ngsdist_b200/csrc`); ngsdist_b200 has no CPU fallback")
+    L = C.CDLL(_LIB)
+    vp, u64, i32, dbl = C.c_void_p, C.c_uint64, C.c_int, C.c_double
+    L.ngsd_abi_version.restype = i32
+    L.ngsd_default_cfg.argtypes = [C.POINTER(_Cfg)]
+    L.ngsd_default_cfg.restype = None
+    L.ngsd_create.argtypes = [C.POINTER(_Cfg), C.POINTER(vp)]
+    L.ngsd_destroy.argtypes = [vp]
+    L.ngsd_last_error.argtypes = [vp]
+    L.ngsd_last_error.restype = C.c_char_p
+    L.ngsd_push_sites.argtypes = [vp, vp, u64, u64]
+    L.ngsd_push_sites_device.argtypes = [vp, vp, u64, u64]
+    L.ngsd_push_genotypes.argtypes = [vp, vp, u64, u64]
+    L.ngsd_frontend.argtypes = [vp]
+    L.ngsd_distances.argtypes = [vp, vp, u64, u64, vp, vp, vp]
+    L.ngsd_taus_seed.argtypes = [vp, C.c_uint32]
+    L.ngsd_taus_seed.restype = None
+    L.ngsd_taus_get.argtypes = [vp]
+    L.ngsd_taus_get.restype = C.c_uint32
+    L.ngsd_boot_block_counts.argtypes = [vp, u64, vp]
+    L.ngsd_boot_block_counts.restype = None
+    L.ngsd_get_posteriors.argtypes = [vp, vp, vp]
+    L.ngsd_synth_raw_device.argtypes = [vp, vp, u64, dbl, u64, u64]
+    L.ngsd_get_timing.argtypes = [vp, C.POINTER(Timing)]
+    L.ngsd_stream.argtypes = [vp]
+    L.ngsd_stream.restype = vp
+    L.ngsd_probe_fp64_tflops.argtypes = [i32, C.POINTER(dbl)]
+    L.ngsd_host_alloc.argtypes = [u64]
+    L.ngsd_host_alloc.restype = vp
+    L.ngsd_host_free.argtypes = [vp]
+    L.ngsd_host_free.restype = None
+    for name in ("ngsd_create", "ngsd_destroy", "ngsd_push_sites", "ngsd_push_sites_device", "ngsd_push_genotypes", "ngsd_frontend",
+                 "ngsd_distances", "ngsd_get_posteriors", "ngsd_synth_raw_device", "ngsd_get_timing", "ngsd_probe_fp64_tflops"):
+        getattr(L, name).restype = i32
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    return C.c_void_p(int(a))   # raw address (e.g. torch tensor.data_ptr())
+
+
+@dataclass
+class Params:
+    """Subset of the reference `params` (ngsDist.hpp:11-44); defaults follow init_pars (parse_args.cpp:6-37)."""
+    n_ind: int = 0
+    n_sites: int = 0
+    tot_sites: int = 0
+    in_probs: bool = True
+    in_logscale: bool = False
+    call_geno: bool = False
+    N_thresh: float = 0.0
+    call_thresh: float = 0.0
+    pairwise_del: bool = False
+    avg_nuc_dist: bool = False
+    score: list = field(default_factory=lambda: [0, 0.5, 1, 0.5, 0, 0.5, 1, 0.5, 0])
+    evol_model: int = 1
+    indep_geno: bool = False
+    n_boot_rep: int = 0
+    boot_block_size: int = 1
+    seed: int = 12345
+    in_text: bool = False      # text reader semantics (no -inf clamp) instead of the binary reader's
+
+    def resolved(self):
+        """Apply the parse-time implications and main()'s forcing rules (parse_args.cpp:91-94,123-130; ngsDist.cpp:55-62)."""
+        p = Params(**{**self.__dict__, "score": list(self.score)})
+        if p.avg_nuc_dist:
+            p.score[4] = 0.5
+        if p.in_logscale:
+            p.in_probs = True
+        if p.N_thresh != 0 or p.call_thresh != 0:
+            p.call_geno = True
+        if p.call_geno and not p.in_probs:
+            raise NgsDistError(-1, "can only call genotypes from likelihoods/probabilities!")
+        if not p.in_probs or p.call_geno:
+            p.indep_geno = True
+        return p
+
+
+def taus_block_counts(state, n_blocks):
+    counts = np.zeros(n_blocks, dtype=np.uint32)
+    lib().ngsd_boot_block_counts(_ptr(state), n_blocks, _ptr(counts))
+    return counts
+
+
+def probe_fp64_tflops(device=0):
+    v = C.c_double(0)
+    rc = lib().ngsd_probe_fp64_tflops(device, C.byref(v))
+    if rc:
+        raise NgsDistError(rc, "FP64 probe failed")
+    return v.value
+
+
+class NgsDistB200:
+    """One context = one GPU = the hot path of one ngsDist run."""
+
+    def __init__(self, params: Params, device=0):
+        self.p = params.resolved()
+        L = lib()
+        cfg = _Cfg()
+        L.ngsd_default_cfg(C.byref(cfg))
+        p = self.p
+        cfg.n_ind, cfg.n_sites, cfg.tot_sites = p.n_ind, p.n_sites, p.tot_sites
+        for k in range(9):
+            cfg.score[k] = float(p.score[k])
+        cfg.evol_model = p.evol_model
+        cfg.pairwise_del = int(p.pairwise_del)
+        cfg.indep_geno = int(p.indep_geno)
+        cfg.call_geno = int(p.call_geno)
+        cfg.N_thresh, cfg.call_thresh = p.N_thresh, p.call_thresh
+        cfg.input_is_log = int(p.in_logscale)
+        cfg.input_kind = 2 if not p.in_probs else (1 if p.in_text else 0)
+        cfg.device = device
+        self._h = C.c_void_p()
+        rc = L.ngsd_create(C.byref(cfg), C.byref(self._h))
+        if rc:
+            raise NgsDistError(rc, L.ngsd_last_error(None).decode())
+        self._taus = np.zeros(3, dtype=np.uint32)
+        L.ngsd_taus_seed(_ptr(self._taus), p.seed & 0xFFFFFFFF)
+        self._n_sites_boot = p.n_sites   # the persistently truncated n_sites of ngsDist.cpp:236
+
+    # -- lifetime --
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ngsd_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc):
+        if rc:
+            raise NgsDistError(rc, lib().ngsd_last_error(self._h).decode())
+
+    # -- front end --
+    def push_sites(self, raw, site0=0):
+        """raw: numpy [n][n_ind][3] float64 host array exactly as the reader produced it."""
+        raw = np.ascontiguousarray(raw, dtype=np.float64)
+        assert raw.shape[1:] == (self.p.n_ind, 3), raw.shape
+        self._check(lib().ngsd_push_sites(self._h, _ptr(raw), site0, raw.shape[0]))
+
+    def push_sites_ptr(self, host_ptr, site0, n):
+        self._check(lib().ngsd_push_sites(self._h, _ptr(host_ptr), site0, n))
+
+    def push_sites_device(self, dev_ptr, site0, n):
+        self._check(lib().ngsd_push_sites_device(self._h, _ptr(dev_ptr), site0, n))
+
+    def push_genotypes(self, codes, site0=0):
+        codes = np.ascontiguousarray(codes, dtype=np.int8)
+        assert codes.shape[1] == self.p.n_ind
+        self._check(lib().ngsd_push_genotypes(self._h, _ptr(codes), site0, codes.shape[0]))
+
+    def frontend(self):
+        self._check(lib().ngsd_frontend(self._h))
+
+    def posteriors(self, want_P=True, want_miss=True):
+        n, s = self.p.n_ind, self.p.n_sites
+        P = np.empty((n, s, 3), dtype=np.float64) if want_P else None
+        m = np.empty((n, s), dtype=np.uint8) if want_miss else None
+        self._check(lib().ngsd_get_posteriors(self._h, _ptr(P), _ptr(m)))
+        return P, m
+
+    # -- distances --
+    def distances(self, block_counts=None, block_size=1, want_num=False, want_cnt=False, out=None):
+        n = self.p.n_ind
+        if out is None:
+            out = np.empty((n, n), dtype=np.float64)
+        num = np.empty((n, n), dtype=np.float64) if want_num else None
+        cnt = np.empty((n, n), dtype=np.uint64) if want_cnt else None
+        if block_counts is not None:
+            block_counts = np.ascontiguousarray(block_counts, dtype=np.uint32)
+            nb = len(block_counts)
+        else:
+            nb = 0
+        self._check(lib().ngsd_distances(self._h, _ptr(block_counts), nb, block_size, _ptr(out), _ptr(num), _ptr(cnt)))
+        res = dict(dist=out)
+        if want_num:
+            res["num"] = num
+        if want_cnt:
+            res["cnt"] = cnt
+        return res
+
+    def distances_raw(self, counts_ptr, n_blocks, block_size, out_ptr):
+        """Pointer-level call for bench.py (pinned buffers, no numpy allocation in the timed region)."""
+        self._check(lib().ngsd_distances(self._h, _ptr(counts_ptr), n_blocks, block_size, _ptr(out_ptr), None, None))
+
+    def next_boot_counts(self):
+        """Advance the host RNG by one replicate (ngsDist.cpp:235-238): returns (block_counts, block_size)."""
+        bs = self.p.boot_block_size
+        self._n_sites_boot -= self._n_sites_boot % bs
+        n_blocks = self._n_sites_boot // bs
+        return taus_block_counts(self._taus, n_blocks), bs
+
+    def run(self, want_num=False, want_cnt=False):
+        """The replicate loop of main() (ngsDist.cpp:217-289): list of 1 + n_boot_rep result dicts."""
+        self.frontend()
+        res = []
+        for rep in range(self.p.n_boot_rep + 1):
+            if rep == 0:
+                res.append(self.distances(want_num=want_num, want_cnt=want_cnt))
+            else:
+                counts, bs = self.next_boot_counts()
+                res.append(self.distances(counts, bs, want_num=want_num, want_cnt=want_cnt))
+        return res
+
+    # -- measurement --
+    def timing(self):
+        t = Timing()
+        self._check(lib().ngsd_get_timing(self._h, C.byref(t)))
+        return t
+
+    def synth_raw_device(self, dev_ptr, seed, miss_rate, site0, n):
+        self._check(lib().ngsd_synth_raw_device(self._h, _ptr(dev_ptr), seed, float(miss_rate), site0, n))
+
+    def stream(self):
+        return lib().ngsd_stream(self._h)

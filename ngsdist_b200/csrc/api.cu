@@ -1,0 +1,575 @@
+// C ABI of libngsdist_b200.so (include/ngsdist_b200.h): context management, the chunked front-end pushes, the
+// host-side bootstrap bookkeeping (RNG + block multiplicities, ngsDist.cpp:235-238,416-437) and the orchestration of
+// K3 -> K2 -> K4 for one distance matrix.  No CPU implementation of the hot path exists in this library.
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <algorithm>
+#include <new>
+
+#include "ngsd_internal.h"
+
+static char g_create_err[512] = "";
+
+void ngsd_set_error(ngsd_ctx *ctx, const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(ctx ? ctx->err : g_create_err, 512, fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+template <typename T>
+cudaError_t dev_alloc(T **p, uint64_t count) {
+  return cudaMalloc((void **) p, std::max<uint64_t>(count, 1) * sizeof(T));
+}
+
+int ensure_pinned(ngsd_ctx *ctx, uint64_t bytes) {
+  if (ctx->h_pin_bytes >= bytes) return NGSD_OK;
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  ctx->h_pin = nullptr;
+  ctx->h_pin_bytes = 0;
+  NGSD_CUDA(ctx, cudaHostAlloc(&ctx->h_pin, bytes, cudaHostAllocDefault));
+  ctx->h_pin_bytes = bytes;
+  return NGSD_OK;
+}
+
+// Upper-triangle tile list (ti <= tj) in bands of `band` tile-rows/columns so that consecutive tiles (= the CTAs
+// resident together) share row blocks through L2.
+std::vector<ngsd_tile> make_tiles(uint32_t RB) {
+  std::vector<ngsd_tile> t;
+  const uint32_t band = 12;
+  for (uint32_t bi = 0; bi < RB; bi += band)
+    for (uint32_t bj = bi; bj < RB; bj += band)
+      for (uint32_t ti = bi; ti < std::min(bi + band, RB); ti++)
+        for (uint32_t tj = std::max(bj, ti); tj < std::min(bj + band, RB); tj++) t.push_back({(uint16_t) ti, (uint16_t) tj});
+  return t;
+}
+
+// Number of K splits: enough (split, tile) units for ~8-16 units per CTA, an exact multiple of the grid when one
+// exists in that range, at least 16 chunks per unit, and a bounded partial workspace.
+uint32_t choose_splits(uint32_t n_tiles, uint32_t n_chunks, int grid) {
+  if (n_chunks == 0) return 1;
+  uint64_t lo = std::max<uint64_t>(1, ((uint64_t) 6 * grid + n_tiles - 1) / n_tiles);
+  uint64_t hi = std::max<uint64_t>(lo, ((uint64_t) 16 * grid + n_tiles - 1) / n_tiles);
+  const uint64_t cap_chunks = std::max<uint64_t>(1, n_chunks / 16);
+  const uint64_t cap_mem = std::max<uint64_t>(1, ((uint64_t) 6 << 30) / ((uint64_t) n_tiles * NGSD_TILE_ELEMS * 8));
+  const uint64_t cap = std::min(cap_chunks, cap_mem);
+  lo = std::min(lo, cap);
+  hi = std::min(hi, cap);
+  uint64_t best = lo;
+  double best_waste = 1e30;
+  for (uint64_t s = lo; s <= hi; s++) {
+    const uint64_t u = s * n_tiles, waves = (u + grid - 1) / grid;
+    const double waste = (double) (waves * grid) / (double) u - 1.0;
+    if (waste < best_waste - 1e-12) { best_waste = waste; best = s; }
+  }
+  return (uint32_t) best;
+}
+
+void tick(ngsd_ctx *ctx, int k) { cudaEventRecord(ctx->ev[k], ctx->stream); }
+
+}  // namespace
+
+extern "C" {
+
+int ngsd_abi_version(void) { return NGSD_ABI_VERSION; }
+
+void ngsd_default_cfg(ngsd_cfg *cfg) {
+  memset(cfg, 0, sizeof(*cfg));
+  const double s[9] = {0, 0.5, 1, 0.5, 0, 0.5, 1, 0.5, 0};   // parse_args.cpp:25-27
+  memcpy(cfg->score, s, sizeof(s));
+  cfg->evol_model = 1;                                       // parse_args.cpp:28
+  cfg->input_kind = NGSD_INPUT_BINARY_GL;
+}
+
+const char *ngsd_last_error(const ngsd_ctx *ctx) { return ctx ? ctx->err : g_create_err; }
+
+int ngsd_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
+  if (!cfg || !out) { ngsd_set_error(nullptr, "null argument"); return NGSD_ERR_ARG; }
+  *out = nullptr;
+  if (cfg->n_ind == 0) { ngsd_set_error(nullptr, "number of individuals (--n_ind) missing!"); return NGSD_ERR_ARG; }
+  if (cfg->n_sites == 0) { ngsd_set_error(nullptr, "number of sites (--n_sites) missing!"); return NGSD_ERR_ARG; }
+  if (cfg->n_ind > 65535u * NGSD_TILE) { ngsd_set_error(nullptr, "n_ind too large for the tile index type"); return NGSD_ERR_ARG; }
+  if (cfg->tot_sites > 0 && cfg->pairwise_del) {
+    ngsd_set_error(nullptr, "cannot specify total number of sites (--tot_sites) with pairwise deletion (--pairwise_del)!");
+    return NGSD_ERR_ARG;
+  }
+  if (cfg->evol_model < 0 || cfg->evol_model > 6) { ngsd_set_error(nullptr, "invalid evolutionary model specified!"); return NGSD_ERR_MODEL; }
+  if (cfg->evol_model > 2) {
+    static const char *names[] = {"K80", "F81", "HKY85", "TN93"};
+    ngsd_set_error(nullptr, "%s model not yet supported", names[cfg->evol_model - 3]);
+    return NGSD_ERR_MODEL;
+  }
+  if (cfg->call_geno && cfg->N_thresh > cfg->call_thresh) {
+    ngsd_set_error(nullptr, "missing data threshold must be smaller than calling genotype threshold!");
+    return NGSD_ERR_THRESH;
+  }
+  if (cfg->input_kind < 0 || cfg->input_kind > 2 || cfg->reserved != 0) { ngsd_set_error(nullptr, "invalid input_kind / reserved"); return NGSD_ERR_ARG; }
+  if ((cfg->input_kind == NGSD_INPUT_GENOTYPES || cfg->call_geno) && !cfg->indep_geno) {
+    ngsd_set_error(nullptr, "indep_geno must be set for genotype input / call_geno (ngsDist.cpp:55-62)");
+    return NGSD_ERR_ARG;
+  }
+
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0) {
+    ngsd_set_error(nullptr, "no CUDA device available (%s); this library has no CPU fallback", cudaGetErrorString(ce));
+    return NGSD_ERR_CUDA;
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) { ngsd_set_error(nullptr, "invalid device ordinal %d", cfg->device); return NGSD_ERR_ARG; }
+
+  ngsd_ctx *ctx = new (std::nothrow) ngsd_ctx();
+  if (!ctx) { ngsd_set_error(nullptr, "out of host memory"); return NGSD_ERR_ARG; }
+  ctx->cfg = *cfg;
+  ctx->device = cfg->device;
+#define CREATE_CUDA(call)                                                                      \
+  do {                                                                                         \
+    cudaError_t e_ = (call);                                                                   \
+    if (e_ != cudaSuccess) {                                                                   \
+      ngsd_set_error(nullptr, "CUDA error: %s (%s)", cudaGetErrorString(e_), #call);           \
+      ngsd_destroy(ctx);                                                                       \
+      return NGSD_ERR_CUDA;                                                                    \
+    }                                                                                          \
+  } while (0)
+  CREATE_CUDA(cudaSetDevice(ctx->device));
+  cudaDeviceProp prop;
+  CREATE_CUDA(cudaGetDeviceProperties(&prop, ctx->device));
+  if (prop.major != 10) {
+    ngsd_set_error(nullptr, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", ctx->device, prop.major, prop.minor);
+    ngsd_destroy(ctx);
+    return NGSD_ERR_CUDA;
+  }
+  ctx->n_sm = prop.multiProcessorCount;
+  CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  for (auto &e : ctx->ev) CREATE_CUDA(cudaEventCreate(&e));
+  for (int b = 0; b < 2; b++) {
+    CREATE_CUDA(cudaEventCreateWithFlags(&ctx->stage_free[b], cudaEventDisableTiming));
+    CREATE_CUDA(cudaEventCreateWithFlags(&ctx->stage_ready[b], cudaEventDisableTiming));
+  }
+  ctx->n_ind = cfg->n_ind;
+  ctx->n_sites = cfg->n_sites;
+  ctx->n_pad = (cfg->n_ind + NGSD_TILE - 1) / NGSD_TILE * NGSD_TILE;
+  ctx->RB = ctx->n_pad / NGSD_TILE;
+  ctx->NW = (cfg->n_sites + 63) / 64;
+  ctx->NC = ctx->NW * 8;
+  ctx->pushed.assign(ctx->NW, 0);
+  const uint64_t plane = ctx->RB * ctx->NC * NGSD_TILE_DOUBLES;
+  CREATE_CUDA(dev_alloc(&ctx->Apack, plane));
+  CREATE_CUDA(dev_alloc(&ctx->Bpack, plane));
+  CREATE_CUDA(dev_alloc(&ctx->mask, ctx->RB * ctx->NW * 128));
+  CREATE_CUDA(dev_alloc(&ctx->d_err, 1));
+  CREATE_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
+  std::vector<ngsd_tile> tiles = make_tiles((uint32_t) ctx->RB);
+  ctx->n_tiles = (uint32_t) tiles.size();
+  CREATE_CUDA(dev_alloc(&ctx->d_tiles, tiles.size()));
+  CREATE_CUDA(cudaMemcpy(ctx->d_tiles, tiles.data(), tiles.size() * sizeof(ngsd_tile), cudaMemcpyHostToDevice));
+#undef CREATE_CUDA
+  *out = ctx;
+  return NGSD_OK;
+}
+
+int ngsd_destroy(ngsd_ctx *ctx) {
+  if (!ctx) return NGSD_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  cudaFree(ctx->Apack); cudaFree(ctx->Bpack); cudaFree(ctx->mask); cudaFree(ctx->d_err);
+  cudaFree(ctx->stage_dev[0]); cudaFree(ctx->stage_dev[1]);
+  cudaFree(ctx->d_tiles); cudaFree(ctx->d_partials); cudaFree(ctx->d_weights); cudaFree(ctx->d_chunk_ids);
+  cudaFree(ctx->d_ent_word); cudaFree(ctx->d_ent_mask); cudaFree(ctx->d_cnt);
+  cudaFree(ctx->d_out); cudaFree(ctx->d_num); cudaFree(ctx->d_cntout);
+  if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
+  for (int b = 0; b < 2; b++) {
+    if (ctx->stage_free[b]) cudaEventDestroy(ctx->stage_free[b]);
+    if (ctx->stage_ready[b]) cudaEventDestroy(ctx->stage_ready[b]);
+  }
+  if (ctx->stream) cudaStreamDestroy(ctx->stream);
+  if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  delete ctx;
+  return NGSD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- front end ----
+
+static int check_push(ngsd_ctx *ctx, uint64_t site0, uint64_t n) {
+  if (!ctx) return NGSD_ERR_ARG;
+  if (n == 0) { ngsd_set_error(ctx, "empty push"); return NGSD_ERR_ARG; }
+  if (site0 % 64 != 0) { ngsd_set_error(ctx, "site0 must be a multiple of 64"); return NGSD_ERR_ARG; }
+  if (site0 + n > ctx->n_sites) { ngsd_set_error(ctx, "push beyond n_sites"); return NGSD_ERR_ARG; }
+  if ((n % 64 != 0) && site0 + n != ctx->n_sites) { ngsd_set_error(ctx, "only the last push may hold a partial 64-site word"); return NGSD_ERR_ARG; }
+  return NGSD_OK;
+}
+
+static void mark_pushed(ngsd_ctx *ctx, uint64_t site0, uint64_t n) {
+  for (uint64_t w = site0 / 64; w < (site0 + n + 63) / 64; w++)
+    if (!ctx->pushed[w]) { ctx->pushed[w] = 1; ctx->words_pushed++; }
+  ctx->frontend_done = false;
+}
+
+int ngsd_push_sites_device(ngsd_ctx *ctx, const double *raw_dev, uint64_t site0, uint64_t n) {
+  int rc = check_push(ctx, site0, n);
+  if (rc) return rc;
+  if (ctx->cfg.input_kind == NGSD_INPUT_GENOTYPES) { ngsd_set_error(ctx, "context expects genotype codes"); return NGSD_ERR_ARG; }
+  NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->timing = ngsd_timing();
+  tick(ctx, 0);
+  ngsd_frontend_args a{raw_dev, nullptr, site0, n};
+  NGSD_CUDA(ctx, ngsd_launch_frontend(ctx, a));
+  tick(ctx, 1);
+  ctx->timing.launches = 1;
+  ctx->timing.total_ms = -1.f;   // resolved lazily in ngsd_get_timing
+  mark_pushed(ctx, site0, n);
+  return NGSD_OK;
+}
+
+static int ensure_staging(ngsd_ctx *ctx, uint64_t bytes_per_site) {
+  if (ctx->stage_dev[0]) return NGSD_OK;
+  uint64_t sites = ((uint64_t) 64 << 20) / bytes_per_site / 64 * 64;
+  sites = std::max<uint64_t>(sites, 64);
+  sites = std::min<uint64_t>(sites, (ctx->n_sites + 63) / 64 * 64);
+  ctx->stage_sites = sites;
+  for (int b = 0; b < 2; b++) {
+    NGSD_CUDA(ctx, cudaMalloc((void **) &ctx->stage_dev[b], sites * bytes_per_site));
+    NGSD_CUDA(ctx, cudaEventRecord(ctx->stage_free[b], ctx->stream));
+  }
+  return NGSD_OK;
+}
+
+int ngsd_push_sites(ngsd_ctx *ctx, const double *raw_host, uint64_t site0, uint64_t n) {
+  int rc = check_push(ctx, site0, n);
+  if (rc) return rc;
+  if (!raw_host) { ngsd_set_error(ctx, "null raw pointer"); return NGSD_ERR_ARG; }
+  if (ctx->cfg.input_kind == NGSD_INPUT_GENOTYPES) { ngsd_set_error(ctx, "context expects genotype codes"); return NGSD_ERR_ARG; }
+  NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint64_t bps = ctx->n_ind * 3 * sizeof(double);
+  rc = ensure_staging(ctx, bps);
+  if (rc) return rc;
+  ctx->timing = ngsd_timing();
+  tick(ctx, 0);
+  int launches = 0;
+  for (uint64_t off = 0; off < n; off += ctx->stage_sites) {
+    const uint64_t m = std::min(ctx->stage_sites, n - off);
+    const int b = ctx->stage_next;
+    ctx->stage_next ^= 1;
+    NGSD_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[b], 0));
+    NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->stage_dev[b], raw_host + off * ctx->n_ind * 3, m * bps, cudaMemcpyHostToDevice, ctx->copy_stream));
+    NGSD_CUDA(ctx, cudaEventRecord(ctx->stage_ready[b], ctx->copy_stream));
+    NGSD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->stage_ready[b], 0));
+    ngsd_frontend_args a{ctx->stage_dev[b], nullptr, site0 + off, m};
+    NGSD_CUDA(ctx, ngsd_launch_frontend(ctx, a));
+    NGSD_CUDA(ctx, cudaEventRecord(ctx->stage_free[b], ctx->stream));
+    launches++;
+  }
+  tick(ctx, 1);
+  ctx->timing.launches = launches;
+  ctx->timing.total_ms = -1.f;
+  NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the caller may now reuse raw_host
+  mark_pushed(ctx, site0, n);
+  return NGSD_OK;
+}
+
+int ngsd_push_genotypes(ngsd_ctx *ctx, const int8_t *codes_host, uint64_t site0, uint64_t n) {
+  int rc = check_push(ctx, site0, n);
+  if (rc) return rc;
+  if (!codes_host) { ngsd_set_error(ctx, "null codes pointer"); return NGSD_ERR_ARG; }
+  if (ctx->cfg.input_kind != NGSD_INPUT_GENOTYPES) { ngsd_set_error(ctx, "context expects genotype likelihoods"); return NGSD_ERR_ARG; }
+  NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
+  int8_t *d = nullptr;
+  NGSD_CUDA(ctx, cudaMalloc((void **) &d, n * ctx->n_ind));
+  cudaError_t e = cudaMemcpyAsync(d, codes_host, n * ctx->n_ind, cudaMemcpyHostToDevice, ctx->stream);
+  ctx->timing = ngsd_timing();
+  tick(ctx, 0);
+  ngsd_frontend_args a{nullptr, d, site0, n};
+  if (e == cudaSuccess) e = ngsd_launch_frontend(ctx, a);
+  tick(ctx, 1);
+  ctx->timing.launches = 1;
+  ctx->timing.total_ms = -1.f;
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d);
+  NGSD_CUDA(ctx, e);
+  mark_pushed(ctx, site0, n);
+  return NGSD_OK;
+}
+
+int ngsd_frontend(ngsd_ctx *ctx) {
+  if (!ctx) return NGSD_ERR_ARG;
+  if (ctx->words_pushed != ctx->NW) {
+    ngsd_set_error(ctx, "front end incomplete: %llu of %llu 64-site words pushed", (unsigned long long) ctx->words_pushed, (unsigned long long) ctx->NW);
+    return NGSD_ERR_STATE;
+  }
+  NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
+  int flags = 0;
+  NGSD_CUDA(ctx, cudaMemcpyAsync(&flags, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (flags & 1) { ngsd_set_error(ctx, "NaN found! Is the file format correct?"); return NGSD_ERR_NAN; }
+  if (flags & 2) { ngsd_set_error(ctx, "wrong GENO file format. Genotypes must be coded as {-1,0,1,2} !"); return NGSD_ERR_GENO; }
+  ctx->frontend_done = true;
+  return NGSD_OK;
+}
+
+int ngsd_get_posteriors(ngsd_ctx *ctx, double *P_host, uint8_t *miss_host) {
+  if (!ctx) return NGSD_ERR_ARG;
+  NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint64_t tot = ctx->n_ind * ctx->n_sites;
+  double *dP = nullptr;
+  uint8_t *dM = nullptr;
+  if (P_host) NGSD_CUDA(ctx, cudaMalloc((void **) &dP, tot * 3 * sizeof(double)));
+  if (miss_host) NGSD_CUDA(ctx, cudaMalloc((void **) &dM, tot));
+  cudaError_t e = ngsd_launch_unpack(ctx, dP, dM);
+  if (e == cudaSuccess && P_host) e = cudaMemcpyAsync(P_host, dP, tot * 3 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess && miss_host) e = cudaMemcpyAsync(miss_host, dM, tot, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(dP);
+  cudaFree(dM);
+  NGSD_CUDA(ctx, e);
+  return NGSD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- distances ----
+
+static int ensure_dist_buffers(ngsd_ctx *ctx, uint64_t slots) {
+  const uint64_t n2 = ctx->n_ind * ctx->n_ind;
+  if (!ctx->d_out) {
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_out, n2));
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_num, n2));
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_cntout, n2));
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_weights, ctx->NC * NGSD_SC));
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_chunk_ids, ctx->NC));
+    if (ctx->cfg.pairwise_del) NGSD_CUDA(ctx, dev_alloc(&ctx->d_cnt, ctx->n_pad * ctx->n_pad));
+  }
+  if (slots > ctx->partial_slots) {
+    cudaFree(ctx->d_partials);
+    ctx->d_partials = nullptr;
+    ctx->partial_slots = 0;
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_partials, slots * NGSD_TILE_ELEMS));
+    ctx->partial_slots = slots;
+  }
+  return NGSD_OK;
+}
+
+static int ensure_entries(ngsd_ctx *ctx, uint64_t n) {
+  if (n <= ctx->ent_cap) return NGSD_OK;
+  cudaFree(ctx->d_ent_word);
+  cudaFree(ctx->d_ent_mask);
+  ctx->d_ent_word = nullptr;
+  ctx->d_ent_mask = nullptr;
+  ctx->ent_cap = 0;
+  const uint64_t cap = n + n / 4 + 64;
+  NGSD_CUDA(ctx, dev_alloc(&ctx->d_ent_word, cap));
+  NGSD_CUDA(ctx, dev_alloc(&ctx->d_ent_mask, cap));
+  ctx->ent_cap = cap;
+  return NGSD_OK;
+}
+
+int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_blocks, uint64_t block_size, double *out,
+                   double *num_opt, uint64_t *cnt_opt) {
+  if (!ctx) return NGSD_ERR_ARG;
+  NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (!ctx->frontend_done) {
+    int rc = ngsd_frontend(ctx);
+    if (rc) return rc;
+  }
+  if (!ctx->cfg.indep_geno) {
+    ngsd_set_error(ctx, "per pair-site EM path (indep_geno = 0) not available in this build");
+    return NGSD_ERR_ARG;
+  }
+  const bool weighted = block_counts != nullptr;
+  uint64_t n_eff = ctx->n_sites;
+  if (weighted) {
+    if (block_size == 0 || n_blocks == 0 || n_blocks * block_size > ctx->n_sites) {
+      ngsd_set_error(ctx, "invalid bootstrap geometry: %llu blocks of %llu sites", (unsigned long long) n_blocks, (unsigned long long) block_size);
+      return NGSD_ERR_ARG;
+    }
+    n_eff = n_blocks * block_size;
+  }
+  const uint64_t NCu = (ctx->n_sites + NGSD_SC - 1) / NGSD_SC;   // chunks that hold data
+
+  // ---- host-side bootstrap bookkeeping: per-site weights, active chunk list, level-mask entries ----
+  uint64_t n_chunks = NCu, n_entries = 0, active_sites = n_eff;
+  uint32_t maxw = 1;
+  if (weighted)
+    for (uint64_t b = 0; b < n_blocks; b++) maxw = std::max(maxw, block_counts[b]);
+  const uint64_t ent_max = ctx->cfg.pairwise_del ? ctx->NW * (weighted ? maxw : 1) : 0;
+  const uint64_t bytes_w = ctx->NC * NGSD_SC * sizeof(double), bytes_c = ctx->NC * sizeof(uint32_t);
+  const uint64_t bytes_e = ent_max * (sizeof(uint32_t) + sizeof(uint64_t));
+  int rc = ensure_pinned(ctx, bytes_w + bytes_c + bytes_e + 64);
+  if (rc) return rc;
+  double *h_w = (double *) ctx->h_pin;
+  uint64_t *h_em = (uint64_t *) ((char *) ctx->h_pin + bytes_w);
+  uint32_t *h_c = (uint32_t *) ((char *) h_em + ent_max * sizeof(uint64_t));
+  uint32_t *h_ew = h_c + ctx->NC;
+  if (weighted) {
+    active_sites = 0;
+    memset(h_w, 0, bytes_w);
+    for (uint64_t b = 0; b < n_blocks; b++) {
+      if (!block_counts[b]) continue;
+      const double w = (double) block_counts[b];
+      for (uint64_t s = b * block_size; s < (b + 1) * block_size; s++) h_w[s] = w;
+      active_sites += block_size;
+    }
+    n_chunks = 0;
+    for (uint64_t c = 0; c < NCu; c++) {
+      bool any = false;
+      for (int k = 0; k < NGSD_SC; k++) any |= h_w[c * NGSD_SC + k] != 0.0;
+      if (any) h_c[n_chunks++] = (uint32_t) c;
+    }
+  }
+  if (ctx->cfg.pairwise_del) {
+    if (!weighted) {
+      for (uint64_t w = 0; w < ctx->NW; w++) { h_ew[w] = (uint32_t) w; h_em[w] = ~0ull; }
+      n_entries = ctx->NW;
+    } else {
+      std::vector<uint64_t> level(ctx->NW);
+      for (uint32_t v = 1; v <= maxw; v++) {
+        std::fill(level.begin(), level.end(), 0ull);
+        for (uint64_t b = 0; b < n_blocks; b++) {
+          if (block_counts[b] < v) continue;
+          uint64_t s0 = b * block_size, s1 = s0 + block_size;
+          while (s0 < s1) {   // set bits [s0, s1) word by word
+            const uint64_t w = s0 >> 6, lo = s0 & 63, hi = std::min<uint64_t>(64, lo + (s1 - s0));
+            const uint64_t m = (hi == 64 ? ~0ull : ((1ull << hi) - 1)) & ~((1ull << lo) - 1);
+            level[w] |= m;
+            s0 += hi - lo;
+          }
+        }
+        for (uint64_t w = 0; w < ctx->NW; w++)
+          if (level[w]) { h_ew[n_entries] = (uint32_t) w; h_em[n_entries] = level[w]; n_entries++; }
+      }
+    }
+  }
+
+  ngsd_dist_plan plan;
+  plan.weighted = weighted;
+  plan.n_chunks = (uint32_t) n_chunks;
+  plan.grid = ctx->n_sm;
+  plan.n_splits = choose_splits(ctx->n_tiles, plan.n_chunks, plan.grid);
+  plan.n_units = plan.n_splits * ctx->n_tiles;
+  plan.grid = (int) std::min<uint64_t>(plan.grid, plan.n_units);
+  rc = ensure_dist_buffers(ctx, plan.n_units);
+  if (rc) return rc;
+  if (ctx->cfg.pairwise_del) {
+    rc = ensure_entries(ctx, n_entries);
+    if (rc) return rc;
+  }
+
+  ctx->timing = ngsd_timing();
+  if (weighted) {
+    NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_weights, h_w, bytes_w, cudaMemcpyHostToDevice, ctx->stream));
+    NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_chunk_ids, h_c, n_chunks * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (n_entries) {
+    NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_ent_word, h_ew, n_entries * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_ent_mask, h_em, n_entries * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  int launches = 0;
+  tick(ctx, 2);
+  if (ctx->cfg.pairwise_del) {
+    NGSD_CUDA(ctx, ngsd_launch_mask_count(ctx, n_entries));
+    launches += n_entries ? 1 : 0;
+  }
+  tick(ctx, 3);
+  if (plan.n_chunks > 0) {
+    NGSD_CUDA(ctx, ngsd_launch_dist_dmma(ctx, plan));
+    launches++;
+  } else {
+    NGSD_CUDA(ctx, cudaMemsetAsync(ctx->d_partials, 0, (uint64_t) plan.n_units * NGSD_TILE_ELEMS * sizeof(double), ctx->stream));
+  }
+  tick(ctx, 4);
+  ngsd_epilogue_args ea;
+  ea.n_splits = plan.n_splits;
+  ea.const_cnt = n_eff;
+  ea.use_cnt = ctx->cfg.pairwise_del != 0;
+  NGSD_CUDA(ctx, ngsd_launch_epilogue(ctx, ea));
+  launches += 2;
+  tick(ctx, 5);
+  const uint64_t n2 = ctx->n_ind * ctx->n_ind;
+  if (out) NGSD_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, n2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (num_opt) NGSD_CUDA(ctx, cudaMemcpyAsync(num_opt, ctx->d_num, n2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (cnt_opt) NGSD_CUDA(ctx, cudaMemcpyAsync(cnt_opt, ctx->d_cntout, n2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms;
+  cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->timing.count_ms = ms;
+  cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->timing.dist_ms = ms;
+  cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->timing.epilogue_ms = ms;
+  cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[5]); ctx->timing.total_ms = ms;
+  ctx->timing.launches = launches;
+  ctx->timing.dist_ctas = plan.grid;
+  ctx->timing.dist_dmma = (uint64_t) ctx->n_tiles * plan.n_chunks * NGSD_K4_PER_CHUNK * 256ull;
+  ctx->timing.active_sites = active_sites;
+  return NGSD_OK;
+}
+
+// ------------------------------------------------------------------------------------------- bootstrap RNG ----
+// gsl_rng_taus (GSL rng/taus.c semantics): the reference seeds it at ngsDist.cpp:179-180 and draws
+// n_blocks uniforms per replicate in rnd_map_data (ngsDist.cpp:421-423) through draw_rnd (gen_func.cpp:117-119).
+
+static inline uint32_t taus_step(uint32_t *s) {
+#define NGSD_TAUS(x, a, b, c, d) ((((x) & (c)) << (d)) ^ ((((x) << (a)) ^ (x)) >> (b)))
+  s[0] = NGSD_TAUS(s[0], 13, 19, 4294967294u, 12);
+  s[1] = NGSD_TAUS(s[1], 2, 25, 4294967288u, 4);
+  s[2] = NGSD_TAUS(s[2], 3, 11, 4294967280u, 17);
+#undef NGSD_TAUS
+  return s[0] ^ s[1] ^ s[2];
+}
+
+void ngsd_taus_seed(uint32_t state[3], uint32_t seed) {
+  if (seed == 0) seed = 1;
+  state[0] = 69069u * seed;
+  state[1] = 69069u * state[0];
+  state[2] = 69069u * state[1];
+  for (int i = 0; i < 6; i++) taus_step(state);
+}
+
+uint32_t ngsd_taus_get(uint32_t state[3]) { return taus_step(state); }
+
+void ngsd_boot_block_counts(uint32_t state[3], uint64_t n_blocks, uint32_t *counts) {
+  memset(counts, 0, n_blocks * sizeof(uint32_t));
+  for (uint64_t b = 0; b < n_blocks; b++) {
+    const double u = taus_step(state) / 4294967296.0;
+    const uint64_t rb = (uint64_t) floor(0.0 + u * (double) n_blocks);
+    counts[rb]++;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- measurement ----
+
+int ngsd_synth_raw_device(ngsd_ctx *ctx, double *raw_dev, uint64_t seed, double miss_rate, uint64_t site0, uint64_t n) {
+  if (!ctx || !raw_dev) return NGSD_ERR_ARG;
+  NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
+  NGSD_CUDA(ctx, ngsd_launch_synth(ctx, raw_dev, seed, miss_rate, site0, n));
+  NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return NGSD_OK;
+}
+
+int ngsd_get_timing(const ngsd_ctx *ctx, ngsd_timing *t) {
+  if (!ctx || !t) return NGSD_ERR_ARG;
+  ngsd_ctx *c = const_cast<ngsd_ctx *>(ctx);
+  if (c->timing.total_ms < 0) {   // a push: events 0..1
+    if (cudaEventSynchronize(c->ev[1]) != cudaSuccess) return NGSD_ERR_CUDA;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]);
+    c->timing.frontend_ms = ms;
+    c->timing.total_ms = ms;
+  }
+  *t = c->timing;
+  return NGSD_OK;
+}
+
+void *ngsd_stream(ngsd_ctx *ctx) { return ctx ? (void *) ctx->stream : nullptr; }
+
+void *ngsd_host_alloc(uint64_t bytes) {
+  void *p = nullptr;
+  if (cudaHostAlloc(&p, bytes, cudaHostAllocDefault) != cudaSuccess) return nullptr;
+  return p;
+}
+
+void ngsd_host_free(void *p) {
+  if (p) cudaFreeHost(p);
+}
+
+}  // extern "C"

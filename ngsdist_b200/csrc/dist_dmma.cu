@@ -1,0 +1,244 @@
+// K2 dist_dmma: the per-pair, per-site loop of gen_dist with indep_geno (ngsDist.cpp:333-364) as a weighted
+// FP64 tensor-core contraction
+//     num(i,j) = sum_s w_s * sum_g p_i(s,g) * (score . p_j(s))_g          (K = 3 * n_sites)
+// on DMMA.8x8x4 (mma.sync.m8n8k4.f64; the only FP64 tensor instruction on sm_100a -- tcgen05 has no kind::f64).
+//
+// Structure (one persistent CTA per SM):
+//   warp 8        producer: one elected lane stages (A tile, B tile[, 8 weights]) of one 8-site chunk per pipeline
+//                 step with cp.async.bulk (TMA bulk copy, SASS UBLKCP) completing on an mbarrier; 4 stages x 48 KiB.
+//   warps 0..7    consumers, 2 (M) x 4 (N): each owns a 64 x 32 sub-tile = 8 x 4 DMMA accumulators (128 registers);
+//                 fragments come straight from the packed layout with conflict-free 256-byte LDS.64.
+// Work units are (K-split q, upper-triangle tile t), ordered split-major so that the CTAs resident at any moment
+// sweep the same site range of neighbouring tiles (operand tiles are shared through L2); CTA c takes units
+// c, c+grid, ...  Each unit writes its 128 x 128 partial in fragment order to a workspace slot; K4 (epilogue.cu)
+// reduces the splits in a fixed order (deterministic) and applies the normalisation + evolutionary model.
+// Bootstrap replicates (ngsDist.cpp:235-238,416-437) run as block-multiplicity weights: the chunk list skips chunks whose
+// 8 weights are all zero and B fragments are scaled in registers (exact: weights are small integers).
+#include "ngsd_internal.h"
+
+namespace {
+
+constexpr int kStages = 4;
+constexpr int kConsumerWarps = 8;
+constexpr int kThreads = (kConsumerWarps + 1) * 32;
+constexpr int kStageBytes = 2 * NGSD_TILE_BYTES + 64;   // A + B + 8 weights
+constexpr size_t kSmemBytes = (size_t) kStages * kStageBytes + 2 * kStages * sizeof(uint64_t) + 128;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+// TMA bulk copy global -> shared, completion counted in bytes on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};" : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
+}
+
+struct DistArgs {
+  const double *Apack, *Bpack;
+  const double *weights;        // [NC*8] or nullptr
+  const uint32_t *chunk_ids;    // [n_chunks] or nullptr (identity)
+  const ngsd_tile *tiles;
+  double *partials;             // [n_units][16384]
+  uint64_t NC;                  // chunk stride of the packed planes
+  uint32_t n_chunks, n_splits, n_tiles, n_units;
+};
+
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(kThreads, 1) k_dist_dmma(DistArgs a) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  double *sA = reinterpret_cast<double *>(smem);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t) kStages * kStageBytes);
+  uint64_t *empty = full + kStages;
+  auto stageA = [&](int s) { return reinterpret_cast<double *>(smem + (size_t) s * kStageBytes); };
+  auto stageB = [&](int s) { return reinterpret_cast<double *>(smem + (size_t) s * kStageBytes + NGSD_TILE_BYTES); };
+  auto stageW = [&](int s) { return reinterpret_cast<double *>(smem + (size_t) s * kStageBytes + 2 * NGSD_TILE_BYTES); };
+  (void) sA;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], kConsumerWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  int stage = 0;
+  uint32_t phase = 0;
+
+  if (warp == kConsumerWarps) {
+    // ===== producer =====
+    if (lane == 0) {
+      for (uint32_t u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+        const uint32_t q = u / a.n_tiles, t = u - q * a.n_tiles;
+        const ngsd_tile tl = a.tiles[t];
+        const uint32_t c0 = (uint32_t) (((uint64_t) q * a.n_chunks) / a.n_splits);
+        const uint32_t c1 = (uint32_t) (((uint64_t) (q + 1) * a.n_chunks) / a.n_splits);
+        const double *Ab = a.Apack + (uint64_t) tl.ti * a.NC * NGSD_TILE_DOUBLES;
+        const double *Bb = a.Bpack + (uint64_t) tl.tj * a.NC * NGSD_TILE_DOUBLES;
+        for (uint32_t c = c0; c < c1; c++) {
+          const uint64_t chunk = a.chunk_ids ? a.chunk_ids[c] : c;
+          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_expect_tx(&full[stage], WEIGHTED ? kStageBytes : 2 * NGSD_TILE_BYTES);
+          bulk_g2s(stageA(stage), Ab + chunk * NGSD_TILE_DOUBLES, NGSD_TILE_BYTES, &full[stage]);
+          bulk_g2s(stageB(stage), Bb + chunk * NGSD_TILE_DOUBLES, NGSD_TILE_BYTES, &full[stage]);
+          if (WEIGHTED) bulk_g2s(stageW(stage), a.weights + chunk * NGSD_SC, 64, &full[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    return;
+  }
+
+  // ===== consumers =====
+  const int wm = warp >> 2, wn = warp & 3;            // 2 x 4 warps; warp tile 64 (rows) x 32 (cols)
+  const int offA = (wm * 8) * 32 + lane;              // row-group wm*8 + mi
+  const int offB = (wn * 4) * 32 + lane;              // col-group wn*4 + ni
+  for (uint32_t u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+    const uint32_t q = u / a.n_tiles;
+    const uint32_t c0 = (uint32_t) (((uint64_t) q * a.n_chunks) / a.n_splits);
+    const uint32_t c1 = (uint32_t) (((uint64_t) (q + 1) * a.n_chunks) / a.n_splits);
+    double acc[8][4][2];
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
+
+    for (uint32_t c = c0; c < c1; c++) {
+      mbar_wait(&full[stage], phase);
+      const double *As = stageA(stage) + offA;
+      const double *Bs = stageB(stage) + offB;
+      double w0 = 1.0, w1 = 1.0;
+      if (WEIGHTED) {
+        const double *Ws = stageW(stage);
+        w0 = Ws[lane & 3];
+        w1 = Ws[4 + (lane & 3)];
+      }
+#pragma unroll
+      for (int k4 = 0; k4 < NGSD_K4_PER_CHUNK; k4++) {
+        double af[8], bf[4];
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++) af[mi] = As[(k4 * 16 + mi) * 32];
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+          bf[ni] = Bs[(k4 * 16 + ni) * 32];
+          if (WEIGHTED) bf[ni] *= (k4 & 1) ? w1 : w0;
+        }
+#pragma unroll
+        for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+          for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+      if (++stage == kStages) { stage = 0; phase ^= 1; }
+    }
+    // partial tile in fragment order: [warp][mi*4+ni][lane][2]
+    double2 *dst = reinterpret_cast<double2 *>(a.partials + (uint64_t) u * NGSD_TILE_ELEMS) + (warp * 32) * 32 + lane;
+#pragma unroll
+    for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+      for (int ni = 0; ni < 4; ni++) dst[(mi * 4 + ni) * 32] = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+  }
+}
+
+// register-only DMMA loop: the FP64-tensor issue-rate ceiling used as roofline denominator
+__global__ void k_dmma_peak(double *out, int iters) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; i++) c[i][0] = c[i][1] = 0;
+  double x = 1.0 + threadIdx.x, y = 2.0 - threadIdx.x;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) dmma884(c[i][0], c[i][1], x, y);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+  if (s == 12345.678) out[0] = s;
+}
+
+}  // namespace
+
+size_t ngsd_dist_smem_bytes() { return kSmemBytes; }
+
+cudaError_t ngsd_launch_dist_dmma(ngsd_ctx *ctx, const ngsd_dist_plan &p) {
+  static bool attr_set[64] = {};
+  if (!attr_set[ctx->device & 63]) {
+    cudaError_t e = cudaFuncSetAttribute(k_dist_dmma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_dist_dmma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set[ctx->device & 63] = true;
+  }
+  DistArgs a;
+  a.Apack = ctx->Apack;
+  a.Bpack = ctx->Bpack;
+  a.weights = p.weighted ? ctx->d_weights : nullptr;
+  a.chunk_ids = p.weighted ? ctx->d_chunk_ids : nullptr;
+  a.tiles = ctx->d_tiles;
+  a.partials = ctx->d_partials;
+  a.NC = ctx->NC;
+  a.n_chunks = p.n_chunks;
+  a.n_splits = p.n_splits;
+  a.n_tiles = ctx->n_tiles;
+  a.n_units = p.n_units;
+  if (p.weighted)
+    k_dist_dmma<true><<<p.grid, kThreads, kSmemBytes, ctx->stream>>>(a);
+  else
+    k_dist_dmma<false><<<p.grid, kThreads, kSmemBytes, ctx->stream>>>(a);
+  return cudaGetLastError();
+}
+
+extern "C" int ngsd_probe_fp64_tflops(int device, double *dmma_tflops) {
+  if (cudaSetDevice(device) != cudaSuccess) return NGSD_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return NGSD_ERR_CUDA;
+  double *d = nullptr;
+  if (cudaMalloc(&d, 64) != cudaSuccess) return NGSD_ERR_CUDA;
+  const int iters = 8192, warps = 16, nsm = prop.multiProcessorCount;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int r = 0; r < 4; r++) {
+    cudaEventRecord(e0);
+    k_dmma_peak<<<nsm, warps * 32>>>(d, iters);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return NGSD_ERR_CUDA; }
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *dmma_tflops = (double) nsm * warps * iters * 8 * 512.0 / (best * 1e-3) * 1e-12;
+  return NGSD_OK;
+}

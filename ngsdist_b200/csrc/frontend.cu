@@ -1,0 +1,238 @@
+// K1 front end: raw genotype likelihoods -> packed FP64 operand planes + presence bit masks.
+//
+// Replaces, per individual-site:
+//   shared/read_data.cpp:37-45 (binary) / :83-99 (text)  log-scale conversion + post_prob normalisation + NaN check
+//   shared/gen_func.cpp:123-151,920-932                 conv_space, logsum, post_prob
+//   ngsDist.cpp:165-174 + gen_func.cpp:73-98,886-914     call_geno (log space) and exp() back to normal space
+//   shared/gen_func.cpp:862-868                         miss_data predicate (EPSILON = 1e-5)
+// and writes what gen_dist (ngsDist.cpp:325-404) will contract: A = p, B = score.p in DMMA fragment order.
+//
+// HBM-bound by design: 24 B read + 48 B written per individual-site; one thread owns 4 consecutive sites of one
+// individual so that every global store is a full 32-byte sector and a warp stores 1 KiB contiguous per plane.
+#include "ngsd_internal.h"
+
+namespace {
+
+constexpr double kNegInfClamp = -1e15;               // "INF" of shared/gen_func.hpp:15
+constexpr double kEps = 1e-5;                        // EPSILON, shared/gen_func.hpp:16
+constexpr double kThird = 0x1.5555555555555p-2;      // exp(log(1/3)) as glibc evaluates it
+
+struct FrontCfg {
+  int kind;          // ngsd_input_kind
+  int in_log;
+  int call_geno;
+  int pairwise_del;
+  double N_thresh, call_thresh;
+  double score[9];
+};
+
+// Normal-space posterior triple of one individual-site, following the reference step by step.
+// Returns false when a NaN was produced on the binary path (fatal in the reference).
+__device__ __forceinline__ bool posterior(const FrontCfg &c, double x0, double x1, double x2, double p[3]) {
+  double L[3] = {x0, x1, x2};
+  if (!c.in_log) {
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      L[g] = log(L[g]);
+      if (c.kind == NGSD_INPUT_BINARY_GL && L[g] == -INFINITY) L[g] = kNegInfClamp;   // conv_space, gen_func.cpp:127-128
+    }
+  }
+  // logsum + post_prob (gen_func.cpp:135-151, 920-932)
+  double M = L[0];
+  M = (L[1] >= M ? L[1] : M);
+  M = (L[2] >= M ? L[2] : M);
+  double norm;
+  if (M == -INFINITY) {
+    norm = -INFINITY;
+  } else {
+    double sum = 0;
+    sum += exp(L[0] - M);
+    sum += exp(L[1] - M);
+    sum += exp(L[2] - M);
+    norm = log(sum) + M;
+  }
+#pragma unroll
+  for (int g = 0; g < 3; g++) L[g] -= norm;
+  bool ok = true;
+  if (c.kind == NGSD_INPUT_BINARY_GL && (isnan(L[0]) || isnan(L[1]) || isnan(L[2]))) ok = false;   // read_data.cpp:42-45
+  if (c.call_geno) {
+    // array_max_pos / array_min_pos: first strict extremum (gen_func.cpp:73-98)
+    int max_pos = 0, min_pos = 0;
+    double mx = -INFINITY, mn = INFINITY;
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      if (L[g] > mx) { max_pos = g; mx = L[g]; }
+      if (L[g] < mn) { min_pos = g; mn = L[g]; }
+    }
+    double max_pp = exp(L[max_pos]);
+    if (L[min_pos] == L[max_pos]) max_pp = -1;                      // gen_func.cpp:895-897 (miss_data == 0)
+    bool to_missing = max_pp < c.N_thresh;                          // :903-905
+    bool to_call = max_pp >= c.call_thresh;                         // :908-913
+    if (to_call) {
+#pragma unroll
+      for (int g = 0; g < 3; g++) p[g] = (g == max_pos) ? 1.0 : 0.0;   // exp(-1e15) = 0, exp(log(1)) = 1
+      return ok;
+    }
+    if (to_missing) {
+      p[0] = p[1] = p[2] = kThird;                                  // exp(log(1/3))
+      return ok;
+    }
+  }
+#pragma unroll
+  for (int g = 0; g < 3; g++) p[g] = exp(L[g]);                     // ngsDist.cpp:172-173
+  return ok;
+}
+
+// Genotype-code input (read_data.cpp:88-95,98 followed by ngsDist.cpp:172-173): exact one-hot / uniform triples.
+__device__ __forceinline__ bool posterior_from_code(int g, double p[3]) {
+  if (g > 2) { p[0] = p[1] = p[2] = 0; return false; }
+  if (g < 0) { p[0] = p[1] = p[2] = kThird; return true; }
+  p[0] = (g == 0) ? 1.0 : 0.0; p[1] = (g == 1) ? 1.0 : 0.0; p[2] = (g == 2) ? 1.0 : 0.0;
+  return true;
+}
+
+__device__ __forceinline__ bool miss_data(const double p[3]) {      // gen_func.cpp:862-868
+  return fabs(p[0] - p[1]) < kEps && fabs(p[1] - p[2]) < kEps;
+}
+
+// grid (n_pad/32, ceil(n/64)); block (32 individuals, 16 site groups of 4) = one 64-site mask word per individual.
+__global__ void __launch_bounds__(512) k_frontend(FrontCfg c, const double *__restrict__ raw, const int8_t *__restrict__ codes,
+                                                   uint64_t n_ind, uint64_t site0, uint64_t n, uint64_t NC, uint64_t NW,
+                                                   double *__restrict__ Apack, double *__restrict__ Bpack,
+                                                   uint64_t *__restrict__ mask, int *__restrict__ err) {
+  __shared__ unsigned nib[16][32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const uint64_t i = (uint64_t) blockIdx.x * 32 + tx;
+  const uint64_t word = site0 / 64 + blockIdx.y;
+  const uint64_t s_local0 = (uint64_t) blockIdx.y * 64 + ty * 4;   // first of this thread's 4 sites, relative to site0
+
+  double A[3][4], B[3][4];
+  unsigned bits = 0;
+  int bad = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint64_t sl = s_local0 + q;
+    double p[3] = {0, 0, 0};
+    bool present = false;
+    if (i < n_ind && sl < n) {
+      bool ok;
+      if (codes) {
+        ok = posterior_from_code((int) codes[sl * n_ind + i], p);
+        if (!ok) bad |= 2;
+      } else {
+        const double *x = raw + (sl * n_ind + i) * 3;
+        ok = posterior(c, x[0], x[1], x[2], p);
+        if (!ok) bad |= 1;
+      }
+      present = !miss_data(p);
+      if (c.pairwise_del && !present) p[0] = p[1] = p[2] = 0;       // the skip of ngsDist.cpp:335-338, folded into the operands
+    }
+    bits |= (present ? 1u : 0u) << q;
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      A[g][q] = p[g];
+      // (score . p)_g ; evaluated as in the reference's inner product order over g2 (ngsDist.cpp:351-353)
+      double b = c.score[3 * g + 0] * p[0];
+      b += c.score[3 * g + 1] * p[1];
+      b += c.score[3 * g + 2] * p[2];
+      B[g][q] = b;
+    }
+  }
+  if (bad) atomicOr(err, bad);
+
+  // packed stores: 32 bytes per plane per operand
+  const uint64_t rb = i >> 7, r = i & 127;
+  const uint64_t sgrp = site0 / 4 + (uint64_t) blockIdx.y * 16 + ty;     // global 4-site group
+  const uint64_t chunk = sgrp >> 1, h = sgrp & 1;
+  const uint64_t base = (rb * NC + chunk) * NGSD_TILE_DOUBLES + (r >> 3) * 32 + (r & 7) * 4;
+#pragma unroll
+  for (int g = 0; g < 3; g++) {
+    const uint64_t o = base + (uint64_t) (g * 2 + h) * (16 * 32);
+    double2 *pa = reinterpret_cast<double2 *>(Apack + o);
+    double2 *pb = reinterpret_cast<double2 *>(Bpack + o);
+    pa[0] = make_double2(A[g][0], A[g][1]);
+    pa[1] = make_double2(A[g][2], A[g][3]);
+    pb[0] = make_double2(B[g][0], B[g][1]);
+    pb[1] = make_double2(B[g][2], B[g][3]);
+  }
+
+  nib[ty][tx] = bits;
+  __syncthreads();
+  if (ty == 0) {
+    uint64_t w = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) w |= (uint64_t) nib[k][tx] << (4 * k);
+    mask[(rb * NW + word) * 128 + r] = w;
+  }
+}
+
+// Inspection: packed A planes + mask -> [ind][site][3] / [ind][site]
+__global__ void k_unpack(const double *__restrict__ Apack, const uint64_t *__restrict__ mask, uint64_t n_ind, uint64_t n_sites,
+                         uint64_t NC, uint64_t NW, double *__restrict__ P, uint8_t *__restrict__ miss) {
+  const uint64_t idx = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_ind * n_sites) return;
+  const uint64_t i = idx / n_sites, s = idx % n_sites;
+  const uint64_t rb = i >> 7, r = i & 127, chunk = s >> 3, h = (s >> 2) & 1, q = s & 3;
+  const uint64_t base = (rb * NC + chunk) * NGSD_TILE_DOUBLES + (r >> 3) * 32 + (r & 7) * 4 + q;
+  if (P)
+    for (int g = 0; g < 3; g++) P[idx * 3 + g] = Apack[base + (uint64_t) (g * 2 + h) * 512];
+  if (miss) miss[idx] = !((mask[(rb * NW + (s >> 6)) * 128 + r] >> (s & 63)) & 1);
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+  x += 0x9E3779B97F4A7C15ull;
+  x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+  x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+  return x ^ (x >> 31);
+}
+
+// SURVEY §8(d) synthetic generator (transcendental-free; bit-identical to oracle/ngsdist_oracle.c:ngsd_oracle_synth_raw)
+__global__ void k_synth(double *__restrict__ raw, uint64_t seed, uint64_t thr, int use_miss, uint64_t n_ind, uint64_t site0, uint64_t n) {
+  const uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n * n_ind) return;
+  const uint64_t idx = site0 * n_ind + k;
+  double *x = raw + k * 3;
+  if (use_miss && splitmix64((seed + 1) ^ idx) < thr) {
+    x[0] = x[1] = x[2] = 1.0 / 3.0;
+    return;
+  }
+#pragma unroll
+  for (uint64_t g = 0; g < 3; g++) {
+    const uint64_t hsh = splitmix64(seed ^ splitmix64(idx * 4 + g));
+    const double u = ((double) (hsh >> 11) + 0.5) * 0x1p-53;
+    const double u2 = u * u, u4 = u2 * u2;
+    x[g] = u4 * u4;
+  }
+}
+
+}  // namespace
+
+cudaError_t ngsd_launch_frontend(ngsd_ctx *ctx, const ngsd_frontend_args &a) {
+  FrontCfg c;
+  c.kind = ctx->cfg.input_kind;
+  c.in_log = ctx->cfg.input_is_log;
+  c.call_geno = ctx->cfg.call_geno;
+  c.pairwise_del = ctx->cfg.pairwise_del;
+  c.N_thresh = ctx->cfg.N_thresh;
+  c.call_thresh = ctx->cfg.call_thresh;
+  for (int k = 0; k < 9; k++) c.score[k] = ctx->cfg.score[k];
+  dim3 grid((unsigned) (ctx->n_pad / 32), (unsigned) ((a.n + 63) / 64)), block(32, 16);
+  k_frontend<<<grid, block, 0, ctx->stream>>>(c, a.raw, a.codes, ctx->n_ind, a.site0, a.n, ctx->NC, ctx->NW, ctx->Apack,
+                                              ctx->Bpack, ctx->mask, ctx->d_err);
+  return cudaGetLastError();
+}
+
+cudaError_t ngsd_launch_unpack(ngsd_ctx *ctx, double *P_dev, uint8_t *miss_dev) {
+  const uint64_t tot = ctx->n_ind * ctx->n_sites;
+  k_unpack<<<(unsigned) ((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->Apack, ctx->mask, ctx->n_ind, ctx->n_sites, ctx->NC,
+                                                                    ctx->NW, P_dev, miss_dev);
+  return cudaGetLastError();
+}
+
+cudaError_t ngsd_launch_synth(ngsd_ctx *ctx, double *raw_dev, uint64_t seed, double miss_rate, uint64_t site0, uint64_t n) {
+  long double t = (long double) miss_rate * 18446744073709551616.0L;
+  uint64_t thr = t >= 18446744073709551615.0L ? UINT64_MAX : (uint64_t) t;
+  const uint64_t tot = n * ctx->n_ind;
+  k_synth<<<(unsigned) ((tot + 255) / 256), 256, 0, ctx->stream>>>(raw_dev, seed, thr, miss_rate > 0 ? 1 : 0, ctx->n_ind, site0, n);
+  return cudaGetLastError();
+}

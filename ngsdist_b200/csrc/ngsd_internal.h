@@ -1,0 +1,106 @@
+// Internal declarations shared by the .cu files of libngsdist_b200.so (not part of the ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/ngsdist_b200.h"
+
+// ---------------------------------------------------------------------------------------------
+// Geometry of the packed operand planes (DESIGN.md "Data layout in HBM")
+//
+//   row block  : 128 individuals           (n_pad = ceil(n_ind/128)*128, RB = n_pad/128)
+//   site chunk : 8 sites                   (NC = ceil(n_sites/8))
+//   one (row block, chunk) tile of an operand = 6 k4-groups x 16 row-groups x 32 doubles = 24 KiB, contiguous:
+//       k4-group  kg = g*2 + h     genotype plane g in 0..2, half h in 0..1 (sites chunk*8 + h*4 .. +3)
+//       row-group r8               8 consecutive individuals
+//       32 doubles in DMMA.8x8x4 fragment order: lane = (ind&7)*4 + (site&3)
+//   so a warp reads one A or B fragment of mma.m8n8k4.f64 with a single conflict-free 256-byte LDS.64, and the
+//   producer stages a whole pipeline step with ONE cp.async.bulk (TMA) copy per operand.
+//   A planes hold p_g (zeroed where --pairwise_del drops the individual-site),
+//   B planes hold (score . p)_g, also zeroed there; bootstrap weights scale B fragments in registers.
+// ---------------------------------------------------------------------------------------------
+constexpr int NGSD_TILE = 128;                 // individuals per row block / CTA tile edge
+constexpr int NGSD_SC = 8;                     // sites per chunk (= one pipeline stage)
+constexpr int NGSD_K4_PER_CHUNK = 6;           // 3 planes x 2 halves
+constexpr int NGSD_TILE_DOUBLES = NGSD_K4_PER_CHUNK * 16 * 32;   // 3072 doubles = 24 KiB
+constexpr int NGSD_TILE_BYTES = NGSD_TILE_DOUBLES * 8;
+constexpr int NGSD_TILE_ELEMS = NGSD_TILE * NGSD_TILE;           // accumulator elements per tile
+
+struct ngsd_tile { uint16_t ti, tj; };
+
+struct ngsd_ctx {
+  ngsd_cfg cfg;
+  int device = 0;
+  int n_sm = 0;
+  cudaStream_t stream = nullptr;      // compute stream (all kernels)
+  cudaStream_t copy_stream = nullptr; // H2D staging
+  uint64_t n_ind = 0, n_pad = 0, RB = 0, n_sites = 0, NC = 0, NW = 0;
+  double *Apack = nullptr, *Bpack = nullptr;   // [RB][NC][3072]
+  uint64_t *mask = nullptr;                    // [RB][NW][128] presence bits (1 = data present)
+  int *d_err = nullptr;                        // device error flags (bit0 NaN, bit1 bad genotype code)
+  // push state
+  std::vector<uint8_t> pushed;                 // per 64-site word: pushed?
+  uint64_t words_pushed = 0;
+  bool frontend_done = false;
+  double *stage_dev[2] = {nullptr, nullptr};   // device staging for host pushes
+  cudaEvent_t stage_free[2] = {nullptr, nullptr};
+  cudaEvent_t stage_ready[2] = {nullptr, nullptr};
+  uint64_t stage_sites = 0;
+  int stage_next = 0;
+  // distance workspaces (allocated lazily)
+  ngsd_tile *d_tiles = nullptr; uint32_t n_tiles = 0;
+  double *d_partials = nullptr; uint64_t partial_slots = 0;
+  double *d_weights = nullptr;                 // [NC*8] per-site bootstrap weights
+  uint32_t *d_chunk_ids = nullptr;             // [NC] active chunk list
+  uint32_t *d_ent_word = nullptr; uint64_t *d_ent_mask = nullptr; uint64_t ent_cap = 0;   // mask-count entries
+  uint32_t *d_cnt = nullptr;                   // [n_pad][n_pad] shared-site counts
+  double *d_out = nullptr, *d_num = nullptr; uint64_t *d_cntout = nullptr;   // [n_ind][n_ind]
+  void *h_pin = nullptr; uint64_t h_pin_bytes = 0;    // pinned scratch for weights / lists / results
+  // timing
+  cudaEvent_t ev[8] = {};
+  ngsd_timing timing = {};
+  char err[512] = {0};
+};
+
+#define NGSD_CUDA(ctx, call)                                                                                  \
+  do {                                                                                                        \
+    cudaError_t e_ = (call);                                                                                  \
+    if (e_ != cudaSuccess) {                                                                                  \
+      ngsd_set_error((ctx), "CUDA error: %s (%s:%d: %s)", cudaGetErrorString(e_), __FILE__, __LINE__, #call); \
+      return NGSD_ERR_CUDA;                                                                                   \
+    }                                                                                                         \
+  } while (0)
+
+void ngsd_set_error(ngsd_ctx *ctx, const char *fmt, ...);
+
+// ---- kernel launchers (each .cu file owns its kernels) ----
+struct ngsd_frontend_args {
+  const double *raw;        // [n][n_ind][3] device, or nullptr for genotype codes
+  const int8_t *codes;      // [n][n_ind] device, or nullptr
+  uint64_t site0, n;
+};
+cudaError_t ngsd_launch_frontend(ngsd_ctx *ctx, const ngsd_frontend_args &a);
+cudaError_t ngsd_launch_unpack(ngsd_ctx *ctx, double *P_dev /*[ind][site][3]*/, uint8_t *miss_dev /*[ind][site]*/);
+cudaError_t ngsd_launch_synth(ngsd_ctx *ctx, double *raw_dev, uint64_t seed, double miss_rate, uint64_t site0, uint64_t n);
+
+struct ngsd_dist_plan {
+  uint32_t n_chunks;        // active chunks L
+  uint32_t n_splits;        // S
+  uint32_t n_units;         // S * n_tiles
+  bool weighted;
+  int grid;
+};
+cudaError_t ngsd_launch_dist_dmma(ngsd_ctx *ctx, const ngsd_dist_plan &p);
+cudaError_t ngsd_launch_mask_count(ngsd_ctx *ctx, uint64_t n_entries);
+struct ngsd_epilogue_args {
+  uint32_t n_splits;
+  uint64_t const_cnt;       // used when !pairwise_del
+  bool use_cnt;             // pairwise_del
+};
+cudaError_t ngsd_launch_epilogue(ngsd_ctx *ctx, const ngsd_epilogue_args &a);
+size_t ngsd_dist_smem_bytes();
