@@ -48,25 +48,35 @@ std::vector<ngsd_tile> make_tiles(uint32_t RB) {
   return t;
 }
 
-// Number of K splits: enough (split, tile) units for ~8-16 units per CTA, an exact multiple of the grid when one
-// exists in that range, at least 16 chunks per unit, and a bounded partial workspace.
-uint32_t choose_splits(uint32_t n_tiles, uint32_t n_chunks, int grid) {
-  if (n_chunks == 0) return 1;
-  uint64_t lo = std::max<uint64_t>(1, ((uint64_t) 6 * grid + n_tiles - 1) / n_tiles);
-  uint64_t hi = std::max<uint64_t>(lo, ((uint64_t) 16 * grid + n_tiles - 1) / n_tiles);
-  const uint64_t cap_chunks = std::max<uint64_t>(1, n_chunks / 16);
-  const uint64_t cap_mem = std::max<uint64_t>(1, ((uint64_t) 6 << 30) / ((uint64_t) n_tiles * NGSD_TILE_ELEMS * 8));
-  const uint64_t cap = std::min(cap_chunks, cap_mem);
-  lo = std::min(lo, cap);
-  hi = std::min(hi, cap);
-  uint64_t best = lo;
-  double best_waste = 1e30;
-  for (uint64_t s = lo; s <= hi; s++) {
-    const uint64_t u = s * n_tiles, waves = (u + grid - 1) / grid;
-    const double waste = (double) (waves * grid) / (double) u - 1.0;
-    if (waste < best_waste - 1e-12) { best_waste = waste; best = s; }
+// K-split boundaries (in positions of the active chunk list) for the dynamically scheduled (split, tile) units of
+// k_dist_dmma.  Two unit sizes: ~8 "main" units per CTA cover the first 84 % of the chunks, then units a quarter of
+// that size fill the tail so that the CTAs finish within one small unit of each other.  `cost_tiles` is the tile
+// count in full-tile equivalents (a diagonal tile costs 136/256).  The partial workspace (128 KiB per unit) is
+// capped at 6 GiB.
+std::vector<uint32_t> plan_splits(uint32_t n_chunks, uint32_t n_tiles, double cost_tiles, int grid) {
+  std::vector<uint32_t> b;
+  b.push_back(0);
+  if (n_chunks == 0) { b.push_back(0); return b; }
+  const uint64_t max_splits = std::max<uint64_t>(1, ((uint64_t) 6 << 30) / ((uint64_t) n_tiles * NGSD_TILE_ELEMS * 8));
+  if (n_chunks < 64 || max_splits < 4) {
+    const uint32_t s = (uint32_t) std::min<uint64_t>(max_splits, std::max<uint32_t>(1, n_chunks / 16));
+    for (uint32_t k = 1; k <= s; k++) b.push_back((uint32_t) ((uint64_t) k * n_chunks / s));
+    return b;
   }
-  return (uint32_t) best;
+  // tuning knobs (development only): NGSD_TUNE="main_units_per_cta,tail_ratio,main_fraction"
+  double upc = 8.0, ratio = 4.0, frac = 0.84;
+  if (const char *t = getenv("NGSD_TUNE")) sscanf(t, "%lf,%lf,%lf", &upc, &ratio, &frac);
+  const uint32_t Lm = (uint32_t) (frac * n_chunks);
+  uint64_t Sm = (uint64_t) llround(upc * grid / cost_tiles);
+  Sm = std::max<uint64_t>(1, std::min<uint64_t>(Sm, Lm / 16));
+  Sm = std::min<uint64_t>(Sm, std::max<uint64_t>(1, max_splits * 2 / 3));
+  const uint32_t cm = (uint32_t) ((Lm + Sm - 1) / Sm);
+  const uint32_t ct = std::max<uint32_t>(8, (uint32_t) (cm / ratio));
+  uint64_t St = std::max<uint64_t>(1, (n_chunks - Lm + ct - 1) / ct);
+  St = std::min<uint64_t>(St, std::max<uint64_t>(1, max_splits - Sm));
+  for (uint64_t k = 1; k <= Sm; k++) b.push_back((uint32_t) (k * Lm / Sm));
+  for (uint64_t k = 1; k <= St; k++) b.push_back(Lm + (uint32_t) (k * (n_chunks - Lm) / St));
+  return b;
 }
 
 void tick(ngsd_ctx *ctx, int k) { cudaEventRecord(ctx->ev[k], ctx->stream); }
@@ -162,9 +172,11 @@ int ngsd_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
   CREATE_CUDA(dev_alloc(&ctx->Bpack, plane));
   CREATE_CUDA(dev_alloc(&ctx->mask, ctx->RB * ctx->NW * 128));
   CREATE_CUDA(dev_alloc(&ctx->d_err, 1));
+  CREATE_CUDA(dev_alloc(&ctx->d_sched, 1));
   CREATE_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
   std::vector<ngsd_tile> tiles = make_tiles((uint32_t) ctx->RB);
   ctx->n_tiles = (uint32_t) tiles.size();
+  ctx->n_diag_tiles = (uint32_t) ctx->RB;
   CREATE_CUDA(dev_alloc(&ctx->d_tiles, tiles.size()));
   CREATE_CUDA(cudaMemcpy(ctx->d_tiles, tiles.data(), tiles.size() * sizeof(ngsd_tile), cudaMemcpyHostToDevice));
 #undef CREATE_CUDA
@@ -180,7 +192,7 @@ int ngsd_destroy(ngsd_ctx *ctx) {
   cudaFree(ctx->Apack); cudaFree(ctx->Bpack); cudaFree(ctx->mask); cudaFree(ctx->d_err);
   cudaFree(ctx->stage_dev[0]); cudaFree(ctx->stage_dev[1]);
   cudaFree(ctx->d_tiles); cudaFree(ctx->d_partials); cudaFree(ctx->d_weights); cudaFree(ctx->d_chunk_ids);
-  cudaFree(ctx->d_ent_word); cudaFree(ctx->d_ent_mask); cudaFree(ctx->d_cnt);
+  cudaFree(ctx->d_ent_word); cudaFree(ctx->d_ent_mask); cudaFree(ctx->d_cnt); cudaFree(ctx->d_split_begin); cudaFree(ctx->d_sched);
   cudaFree(ctx->d_out); cudaFree(ctx->d_num); cudaFree(ctx->d_cntout);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -447,9 +459,18 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   plan.weighted = weighted;
   plan.n_chunks = (uint32_t) n_chunks;
   plan.grid = ctx->n_sm;
-  plan.n_splits = choose_splits(ctx->n_tiles, plan.n_chunks, plan.grid);
+  const double cost_tiles = (double) (ctx->n_tiles - ctx->n_diag_tiles) + ctx->n_diag_tiles * (136.0 / 256.0);
+  std::vector<uint32_t> splits = plan_splits(plan.n_chunks, ctx->n_tiles, cost_tiles, plan.grid);
+  plan.n_splits = (uint32_t) splits.size() - 1;
   plan.n_units = plan.n_splits * ctx->n_tiles;
   plan.grid = (int) std::min<uint64_t>(plan.grid, plan.n_units);
+  if (splits.size() > ctx->split_cap) {
+    cudaFree(ctx->d_split_begin);
+    ctx->d_split_begin = nullptr;
+    ctx->split_cap = 0;
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_split_begin, splits.size() + 64));
+    ctx->split_cap = (uint32_t) splits.size() + 64;
+  }
   rc = ensure_dist_buffers(ctx, plan.n_units);
   if (rc) return rc;
   if (ctx->cfg.pairwise_del) {
@@ -458,6 +479,8 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   }
 
   ctx->timing = ngsd_timing();
+  // (pageable source: the copy is staged before the call returns, so `splits` may go out of scope afterwards)
+  NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_split_begin, splits.data(), splits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   if (weighted) {
     NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_weights, h_w, bytes_w, cudaMemcpyHostToDevice, ctx->stream));
     NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_chunk_ids, h_c, n_chunks * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -499,7 +522,7 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[5]); ctx->timing.total_ms = ms;
   ctx->timing.launches = launches;
   ctx->timing.dist_ctas = plan.grid;
-  ctx->timing.dist_dmma = (uint64_t) ctx->n_tiles * plan.n_chunks * NGSD_K4_PER_CHUNK * 256ull;
+  ctx->timing.dist_dmma = (uint64_t) plan.n_chunks * NGSD_K4_PER_CHUNK * ((uint64_t) (ctx->n_tiles - ctx->n_diag_tiles) * 256ull + (uint64_t) ctx->n_diag_tiles * 136ull);
   ctx->timing.active_sites = active_sites;
   return NGSD_OK;
 }

@@ -14,6 +14,8 @@
 // reduces the splits in a fixed order (deterministic) and applies the normalisation + evolutionary model.
 // Bootstrap replicates (ngsDist.cpp:235-238,416-437) run as block-multiplicity weights: the chunk list skips chunks whose
 // 8 weights are all zero and B fragments are scaled in registers (exact: weights are small integers).
+#include <stdlib.h>
+
 #include "ngsd_internal.h"
 
 namespace {
@@ -22,7 +24,7 @@ constexpr int kStages = 4;
 constexpr int kConsumerWarps = 8;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;
 constexpr int kStageBytes = 2 * NGSD_TILE_BYTES + 64;   // A + B + 8 weights
-constexpr size_t kSmemBytes = (size_t) kStages * kStageBytes + 2 * kStages * sizeof(uint64_t) + 128;
+constexpr size_t kSmemBytes = (size_t) kStages * kStageBytes + 2 * kStages * sizeof(uint64_t) + kStages * 2 * sizeof(uint32_t) + 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 
@@ -66,21 +68,68 @@ struct DistArgs {
   const double *weights;        // [NC*8] or nullptr
   const uint32_t *chunk_ids;    // [n_chunks] or nullptr (identity)
   const ngsd_tile *tiles;
+  const uint32_t *split_begin;  // [n_splits + 1] chunk-list boundaries of the K splits
+  uint32_t *sched;              // dynamic scheduler: next unit to hand out (zeroed before launch)
   double *partials;             // [n_units][16384]
   uint64_t NC;                  // chunk stride of the packed planes
-  uint32_t n_chunks, n_splits, n_tiles, n_units;
+  uint32_t n_tiles, n_units;
+  uint32_t no_diag;             // development knob: run diagonal tiles through the full-tile path
 };
+
+enum : uint32_t { kFirst = 1u, kLast = 2u, kDiag = 4u, kExit = 8u };
+
+// One K4 step of a full (off-diagonal) tile for one consumer warp: 64 x 32 sub-tile, 12 LDS.64 + 32 DMMA.
+__device__ __forceinline__ void step_full(double (&acc)[64], const double *As, const double *Bs, double w) {
+  double af[8], bf[4];
+#pragma unroll
+  for (int mi = 0; mi < 8; mi++) af[mi] = As[mi * 32];
+#pragma unroll
+  for (int ni = 0; ni < 4; ni++) bf[ni] = Bs[ni * 32] * w;
+#pragma unroll
+  for (int mi = 0; mi < 8; mi++)
+#pragma unroll
+    for (int ni = 0; ni < 4; ni++) dmma884(acc[(mi * 4 + ni) * 2], acc[(mi * 4 + ni) * 2 + 1], af[mi], bf[ni]);
+}
+
+// One chunk (6 K4 steps) of a DIAGONAL tile: only the upper triangle of the 16 x 16 grid of 8x8 blocks is needed
+// (136 of 256).  Warp W owns block-rows W and 15-W (17 blocks, the same for every warp, so the four SMSPs stay
+// balanced): acc[0..31] = row W, columns 0..15; acc[32..63] = row 15-W.  Specialised per warp at compile time:
+// predicated-off DMMAs still cost issue slots on the FP64 tensor pipe, so each warp runs straight-line code with
+// exactly its 17 DMMA + (18 - W) LDS.64 per K4 step.
+template <int W>
+__device__ __forceinline__ void chunk_diag(double (&acc)[64], const double *As, const double *Bs, double w0, double w1) {
+#pragma unroll
+  for (int k4 = 0; k4 < NGSD_K4_PER_CHUNK; k4++) {
+    const double *Ak = As + k4 * 512, *Bk = Bs + k4 * 512;
+    const double w = (k4 & 1) ? w1 : w0;
+    const double a0 = Ak[W * 32], a1 = Ak[(15 - W) * 32];
+    double bf[16];
+#pragma unroll
+    for (int c = W; c < 16; c++) bf[c] = Bk[c * 32] * w;
+#pragma unroll
+    for (int c = W; c < 16; c++) dmma884(acc[c * 2], acc[c * 2 + 1], a0, bf[c]);
+#pragma unroll
+    for (int c = 15 - W; c < 16; c++) dmma884(acc[32 + c * 2], acc[32 + c * 2 + 1], a1, bf[c]);
+  }
+}
+
+template <int W>
+__device__ __forceinline__ void store_diag(const double (&acc)[64], double2 *dst) {
+#pragma unroll
+  for (int c = W; c < 16; c++) dst[c * 32] = make_double2(acc[c * 2], acc[c * 2 + 1]);
+#pragma unroll
+  for (int c = 15 - W; c < 16; c++) dst[(16 + c) * 32] = make_double2(acc[32 + c * 2], acc[32 + c * 2 + 1]);
+}
 
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(kThreads, 1) k_dist_dmma(DistArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
-  double *sA = reinterpret_cast<double *>(smem);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t) kStages * kStageBytes);
   uint64_t *empty = full + kStages;
+  uint32_t *meta = reinterpret_cast<uint32_t *>(empty + kStages);   // [kStages][2] = {unit, flags}
   auto stageA = [&](int s) { return reinterpret_cast<double *>(smem + (size_t) s * kStageBytes); };
   auto stageB = [&](int s) { return reinterpret_cast<double *>(smem + (size_t) s * kStageBytes + NGSD_TILE_BYTES); };
   auto stageW = [&](int s) { return reinterpret_cast<double *>(smem + (size_t) s * kStageBytes + 2 * NGSD_TILE_BYTES); };
-  (void) sA;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -93,18 +142,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_dmma(DistArgs a) {
   uint32_t phase = 0;
 
   if (warp == kConsumerWarps) {
-    // ===== producer =====
+    // ===== producer: one lane pulls units from the global counter and streams their chunks =====
     if (lane == 0) {
-      for (uint32_t u = blockIdx.x; u < a.n_units; u += gridDim.x) {
+      for (;;) {
+        const uint32_t u = atomicAdd(a.sched, 1u);
+        if (u >= a.n_units) break;
         const uint32_t q = u / a.n_tiles, t = u - q * a.n_tiles;
         const ngsd_tile tl = a.tiles[t];
-        const uint32_t c0 = (uint32_t) (((uint64_t) q * a.n_chunks) / a.n_splits);
-        const uint32_t c1 = (uint32_t) (((uint64_t) (q + 1) * a.n_chunks) / a.n_splits);
+        const uint32_t c0 = a.split_begin[q], c1 = a.split_begin[q + 1];
         const double *Ab = a.Apack + (uint64_t) tl.ti * a.NC * NGSD_TILE_DOUBLES;
         const double *Bb = a.Bpack + (uint64_t) tl.tj * a.NC * NGSD_TILE_DOUBLES;
+        const uint32_t fl = (tl.ti == tl.tj && !a.no_diag) ? kDiag : 0u;
         for (uint32_t c = c0; c < c1; c++) {
           const uint64_t chunk = a.chunk_ids ? a.chunk_ids[c] : c;
           mbar_wait(&empty[stage], phase ^ 1);
+          meta[stage * 2] = u;
+          meta[stage * 2 + 1] = fl | (c == c0 ? kFirst : 0u) | (c + 1 == c1 ? kLast : 0u);
           mbar_expect_tx(&full[stage], WEIGHTED ? kStageBytes : 2 * NGSD_TILE_BYTES);
           bulk_g2s(stageA(stage), Ab + chunk * NGSD_TILE_DOUBLES, NGSD_TILE_BYTES, &full[stage]);
           bulk_g2s(stageB(stage), Bb + chunk * NGSD_TILE_DOUBLES, NGSD_TILE_BYTES, &full[stage]);
@@ -112,59 +165,69 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_dmma(DistArgs a) {
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
+      mbar_wait(&empty[stage], phase ^ 1);
+      meta[stage * 2 + 1] = kExit;
+      mbar_arrive(&full[stage]);
     }
     return;
   }
 
   // ===== consumers =====
-  const int wm = warp >> 2, wn = warp & 3;            // 2 x 4 warps; warp tile 64 (rows) x 32 (cols)
-  const int offA = (wm * 8) * 32 + lane;              // row-group wm*8 + mi
-  const int offB = (wn * 4) * 32 + lane;              // col-group wn*4 + ni
-  for (uint32_t u = blockIdx.x; u < a.n_units; u += gridDim.x) {
-    const uint32_t q = u / a.n_tiles;
-    const uint32_t c0 = (uint32_t) (((uint64_t) q * a.n_chunks) / a.n_splits);
-    const uint32_t c1 = (uint32_t) (((uint64_t) (q + 1) * a.n_chunks) / a.n_splits);
-    double acc[8][4][2];
+  const int wm = warp >> 2, wn = warp & 3;            // full tiles: 2 x 4 warps, warp tile 64 (rows) x 32 (cols)
+  double acc[64];
+  for (;;) {
+    mbar_wait(&full[stage], phase);
+    const uint32_t u = meta[stage * 2], fl = meta[stage * 2 + 1];
+    if (fl & kExit) break;
+    if (fl & kFirst) {
 #pragma unroll
-    for (int mi = 0; mi < 8; mi++)
-#pragma unroll
-      for (int ni = 0; ni < 4; ni++) acc[mi][ni][0] = acc[mi][ni][1] = 0.0;
-
-    for (uint32_t c = c0; c < c1; c++) {
-      mbar_wait(&full[stage], phase);
-      const double *As = stageA(stage) + offA;
-      const double *Bs = stageB(stage) + offB;
-      double w0 = 1.0, w1 = 1.0;
-      if (WEIGHTED) {
-        const double *Ws = stageW(stage);
-        w0 = Ws[lane & 3];
-        w1 = Ws[4 + (lane & 3)];
-      }
-#pragma unroll
-      for (int k4 = 0; k4 < NGSD_K4_PER_CHUNK; k4++) {
-        double af[8], bf[4];
-#pragma unroll
-        for (int mi = 0; mi < 8; mi++) af[mi] = As[(k4 * 16 + mi) * 32];
-#pragma unroll
-        for (int ni = 0; ni < 4; ni++) {
-          bf[ni] = Bs[(k4 * 16 + ni) * 32];
-          if (WEIGHTED) bf[ni] *= (k4 & 1) ? w1 : w0;
-        }
-#pragma unroll
-        for (int mi = 0; mi < 8; mi++)
-#pragma unroll
-          for (int ni = 0; ni < 4; ni++) dmma884(acc[mi][ni][0], acc[mi][ni][1], af[mi], bf[ni]);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[stage]);
-      if (++stage == kStages) { stage = 0; phase ^= 1; }
+      for (int k = 0; k < 64; k++) acc[k] = 0.0;
     }
-    // partial tile in fragment order: [warp][mi*4+ni][lane][2]
-    double2 *dst = reinterpret_cast<double2 *>(a.partials + (uint64_t) u * NGSD_TILE_ELEMS) + (warp * 32) * 32 + lane;
+    double w0 = 1.0, w1 = 1.0;
+    if (WEIGHTED) {
+      const double *Ws = stageW(stage);
+      w0 = Ws[lane & 3];
+      w1 = Ws[4 + (lane & 3)];
+    }
+    if (fl & kDiag) {
+      const double *As = stageA(stage) + lane, *Bs = stageB(stage) + lane;
+      switch (warp) {       // warp-uniform: no divergence
+        case 0: chunk_diag<0>(acc, As, Bs, w0, w1); break;
+        case 1: chunk_diag<1>(acc, As, Bs, w0, w1); break;
+        case 2: chunk_diag<2>(acc, As, Bs, w0, w1); break;
+        case 3: chunk_diag<3>(acc, As, Bs, w0, w1); break;
+        case 4: chunk_diag<4>(acc, As, Bs, w0, w1); break;
+        case 5: chunk_diag<5>(acc, As, Bs, w0, w1); break;
+        case 6: chunk_diag<6>(acc, As, Bs, w0, w1); break;
+        default: chunk_diag<7>(acc, As, Bs, w0, w1); break;
+      }
+    } else {
+      const double *As = stageA(stage) + (wm * 8) * 32 + lane, *Bs = stageB(stage) + (wn * 4) * 32 + lane;
 #pragma unroll
-    for (int mi = 0; mi < 8; mi++)
+      for (int k4 = 0; k4 < NGSD_K4_PER_CHUNK; k4++) step_full(acc, As + k4 * 512, Bs + k4 * 512, (k4 & 1) ? w1 : w0);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[stage]);
+    if (++stage == kStages) { stage = 0; phase ^= 1; }
+    if (fl & kLast) {
+      // partial tile in fragment order: [warp][32 accumulator pairs][lane] double2 (decoded in epilogue.cu)
+      double2 *dst = reinterpret_cast<double2 *>(a.partials + (uint64_t) u * NGSD_TILE_ELEMS) + (warp * 32) * 32 + lane;
+      if (fl & kDiag) {
+        switch (warp) {
+          case 0: store_diag<0>(acc, dst); break;
+          case 1: store_diag<1>(acc, dst); break;
+          case 2: store_diag<2>(acc, dst); break;
+          case 3: store_diag<3>(acc, dst); break;
+          case 4: store_diag<4>(acc, dst); break;
+          case 5: store_diag<5>(acc, dst); break;
+          case 6: store_diag<6>(acc, dst); break;
+          default: store_diag<7>(acc, dst); break;
+        }
+      } else {
 #pragma unroll
-      for (int ni = 0; ni < 4; ni++) dst[(mi * 4 + ni) * 32] = make_double2(acc[mi][ni][0], acc[mi][ni][1]);
+        for (int f = 0; f < 32; f++) dst[f * 32] = make_double2(acc[f * 2], acc[f * 2 + 1]);
+      }
+    }
   }
 }
 
@@ -203,12 +266,15 @@ cudaError_t ngsd_launch_dist_dmma(ngsd_ctx *ctx, const ngsd_dist_plan &p) {
   a.weights = p.weighted ? ctx->d_weights : nullptr;
   a.chunk_ids = p.weighted ? ctx->d_chunk_ids : nullptr;
   a.tiles = ctx->d_tiles;
+  a.split_begin = ctx->d_split_begin;
+  a.sched = ctx->d_sched;
   a.partials = ctx->d_partials;
   a.NC = ctx->NC;
-  a.n_chunks = p.n_chunks;
-  a.n_splits = p.n_splits;
   a.n_tiles = ctx->n_tiles;
   a.n_units = p.n_units;
+  a.no_diag = getenv("NGSD_NODIAG") ? 1u : 0u;
+  cudaError_t e = cudaMemsetAsync(ctx->d_sched, 0, sizeof(uint32_t), ctx->stream);
+  if (e != cudaSuccess) return e;
   if (p.weighted)
     k_dist_dmma<true><<<p.grid, kThreads, kSmemBytes, ctx->stream>>>(a);
   else

@@ -1,6 +1,8 @@
 // K4 epilogue: deterministic reduction of the K-split partial tiles + the tail of gen_dist (ngsDist.cpp:372-401):
 //   cnt <- tot_sites override; d = num / (double) cnt; model 0: d, 1: -log(1-d), 2: -log(1-(d*4/3))*3/4;
 // symmetric write of both triangles as gen_dist_slave does (ngsDist.cpp:408-412), 0.0 diagonal (ngsDist.cpp:200).
+#include <stdlib.h>
+
 #include "ngsd_internal.h"
 
 namespace {
@@ -14,40 +16,59 @@ struct EpiArgs {
   uint64_t n_ind, n_pad, const_cnt, tot_sites;
   uint32_t n_splits, n_tiles;
   int evol_model;
+  int no_diag;
 };
 
-// grid (n_tiles, 8); block 256: thread handles 8 double2 slots of one consumer-warp's fragment block
+// grid (n_tiles, 32); block 256: one thread per double2 slot of the tile (8192 slots), splits summed in a fixed order
 __global__ void __launch_bounds__(256) k_epilogue(EpiArgs a) {
   const uint32_t t = blockIdx.x;
   const ngsd_tile tl = a.tiles[t];
-  const int warp = blockIdx.y;                 // consumer warp whose 64x32 sub-tile this block finishes
-  const int wm = warp >> 2, wn = warp & 3;
-  const int lane = threadIdx.x & 31;
-  for (int frag = threadIdx.x >> 5; frag < 32; frag += 8) {
-    const uint64_t e = ((uint64_t) (warp * 32 + frag) * 32 + lane);   // double2 index inside the tile
-    double s0 = 0, s1 = 0;
-    for (uint32_t q = 0; q < a.n_splits; q++) {                        // fixed order: deterministic
-      const double2 v = reinterpret_cast<const double2 *>(a.partials + ((uint64_t) q * a.n_tiles + t) * NGSD_TILE_ELEMS)[e];
-      s0 += v.x;
-      s1 += v.y;
-    }
-    const int mi = frag >> 2, ni = frag & 3;
-    const uint64_t i = (uint64_t) tl.ti * NGSD_TILE + wm * 64 + mi * 8 + (lane >> 2);
-    const uint64_t j0 = (uint64_t) tl.tj * NGSD_TILE + wn * 32 + ni * 8 + 2 * (lane & 3);
+  const uint32_t e = blockIdx.y * 256 + threadIdx.x;     // double2 index inside the tile: (warp*32 + frag)*32 + lane
+  const int lane = e & 31, frag = (e >> 5) & 31, warp = e >> 10;
+  // decode the slot -> (row, first column) inside the tile; layouts written by dist_dmma.cu
+  int row, col0;
+  if (tl.ti == tl.tj && !a.no_diag) {     // diagonal tile: warp owns 8x8 block-rows `warp` (frags 0..15) and 15-warp (frags 16..31)
+    const int R = (frag < 16) ? warp : 15 - warp, c = frag & 15;
+    if (c < R) return;      // below the diagonal: never computed, never stored
+    row = R * 8 + (lane >> 2);
+    col0 = c * 8 + 2 * (lane & 3);
+  } else {                  // full tile: 2 x 4 warps of 64 x 32, frag = mi*4 + ni
+    const int wm = warp >> 2, wn = warp & 3, mi = frag >> 2, ni = frag & 3;
+    row = wm * 64 + mi * 8 + (lane >> 2);
+    col0 = wn * 32 + ni * 8 + 2 * (lane & 3);
+  }
+  const uint64_t i = (uint64_t) tl.ti * NGSD_TILE + row;
+  const uint64_t j0 = (uint64_t) tl.tj * NGSD_TILE + col0;
+  if (i >= a.n_ind || j0 >= a.n_ind) return;   // padding rows / columns
+  const double2 *src = reinterpret_cast<const double2 *>(a.partials + (uint64_t) t * NGSD_TILE_ELEMS) + e;
+  const uint64_t stride = (uint64_t) a.n_tiles * (NGSD_TILE_ELEMS / 2);   // in double2
+  double s0 = 0, s1 = 0;
+  uint32_t q = 0;
+  for (; q + 8 <= a.n_splits; q += 8) {                  // 8 independent loads in flight, adds in split order
+    double2 v[8];
 #pragma unroll
-    for (int c = 0; c < 2; c++) {
-      const uint64_t j = j0 + c;
-      if (i >= j || j >= a.n_ind) continue;
-      const double num = c ? s1 : s0;
-      uint64_t cnt = a.cnt ? (uint64_t) a.cnt[i * a.n_pad + j] : a.const_cnt;
-      if (a.num) a.num[i * a.n_ind + j] = a.num[j * a.n_ind + i] = num;
-      if (a.cntout) a.cntout[i * a.n_ind + j] = a.cntout[j * a.n_ind + i] = cnt;
-      if (a.tot_sites > 0) cnt = a.tot_sites;
-      double d = num / (double) cnt;
-      if (a.evol_model == 1) d = -log(1 - d);
-      else if (a.evol_model == 2) d = -log(1 - (d * 4 / 3)) * 3 / 4;
-      a.out[i * a.n_ind + j] = a.out[j * a.n_ind + i] = d;
-    }
+    for (int k = 0; k < 8; k++) v[k] = src[(uint64_t) (q + k) * stride];
+#pragma unroll
+    for (int k = 0; k < 8; k++) { s0 += v[k].x; s1 += v[k].y; }
+  }
+  for (; q < a.n_splits; q++) {
+    const double2 v = src[(uint64_t) q * stride];
+    s0 += v.x;
+    s1 += v.y;
+  }
+#pragma unroll
+  for (int c = 0; c < 2; c++) {
+    const uint64_t j = j0 + c;
+    if (i >= j || j >= a.n_ind) continue;
+    const double num = c ? s1 : s0;
+    uint64_t cnt = a.cnt ? (uint64_t) a.cnt[i * a.n_pad + j] : a.const_cnt;
+    if (a.num) a.num[i * a.n_ind + j] = a.num[j * a.n_ind + i] = num;
+    if (a.cntout) a.cntout[i * a.n_ind + j] = a.cntout[j * a.n_ind + i] = cnt;
+    if (a.tot_sites > 0) cnt = a.tot_sites;
+    double d = num / (double) cnt;
+    if (a.evol_model == 1) d = -log(1 - d);
+    else if (a.evol_model == 2) d = -log(1 - (d * 4 / 3)) * 3 / 4;
+    a.out[i * a.n_ind + j] = a.out[j * a.n_ind + i] = d;
   }
 }
 
@@ -76,7 +97,8 @@ cudaError_t ngsd_launch_epilogue(ngsd_ctx *ctx, const ngsd_epilogue_args &e) {
   a.n_splits = e.n_splits;
   a.n_tiles = ctx->n_tiles;
   a.evol_model = ctx->cfg.evol_model;
+  a.no_diag = getenv("NGSD_NODIAG") ? 1 : 0;
   k_zero_diag<<<(unsigned) ((ctx->n_ind + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_out, ctx->d_num, ctx->d_cntout, ctx->n_ind);
-  k_epilogue<<<dim3(ctx->n_tiles, 8), 256, 0, ctx->stream>>>(a);
+  k_epilogue<<<dim3(ctx->n_tiles, 32), 256, 0, ctx->stream>>>(a);
   return cudaGetLastError();
 }

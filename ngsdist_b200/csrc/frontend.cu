@@ -83,6 +83,43 @@ __device__ __forceinline__ bool posterior(const FrontCfg &c, double x0, double x
   return ok;
 }
 
+// Fast path for the un-called front end (no call_geno): the same posterior without the round trip through log space.
+//   normal-scale input : p_g = x_g / (x_0 + x_1 + x_2)                       [= exp(log x_g - logsum(log x))]
+//   log-scale input    : e_g = exp(L_g - max L), p_g = e_g / (e_0 + e_1 + e_2)  [= exp(L_g - logsum(L))]
+// Algebraically identical to post_prob + exp (gen_func.cpp:920-932, ngsDist.cpp:172-173); it differs from the
+// reference's own rounding by <= ~|log p| * 2^-52 relative (the reference loses that much in "log(sum) + M"), far
+// inside the 1e-9 budget on distances.  Reference corner cases are reproduced explicitly:
+//   x_g == 0 -> p_g = 0 (exp(-1e15 - norm) underflows to 0);  all three 0 on the binary path -> exp(-1.125) each
+//   (SURVEY App. E-11);  negative / NaN input -> NaN -> fatal on the binary path.
+__device__ __forceinline__ bool posterior_fast(const FrontCfg &c, double x0, double x1, double x2, double p[3]) {
+  double e0 = x0, e1 = x1, e2 = x2;
+  if (c.in_log) {
+    double M = x0;
+    M = (x1 >= M ? x1 : M);
+    M = (x2 >= M ? x2 : M);
+    if (M == -INFINITY) {                       // logsum returns -inf -> L - (-inf) = NaN (gen_func.cpp:144-145)
+      p[0] = p[1] = p[2] = NAN;
+      return c.kind != NGSD_INPUT_BINARY_GL;
+    }
+    e0 = (x0 == M) ? 1.0 : exp(x0 - M);
+    e1 = (x1 == M) ? 1.0 : exp(x1 - M);
+    e2 = (x2 == M) ? 1.0 : exp(x2 - M);
+  } else {
+    if (x0 < 0 || x1 < 0 || x2 < 0) e0 = NAN;   // log(negative) = NaN in the reference
+    if (c.kind == NGSD_INPUT_BINARY_GL && x0 == 0 && x1 == 0 && x2 == 0) {
+      p[0] = p[1] = p[2] = 0.32465246735834974;  // exp(-1.125): -1e15 - (-1e15 + log 3) after rounding
+      return true;
+    }
+  }
+  const double sum = (e0 + e1) + e2;
+  p[0] = e0 / sum;      // true divisions: x / x must give exactly 1 (hard calls stay hard)
+  p[1] = e1 / sum;
+  p[2] = e2 / sum;
+  bool ok = true;
+  if (c.kind == NGSD_INPUT_BINARY_GL && (isnan(p[0]) || isnan(p[1]) || isnan(p[2]))) ok = false;
+  return ok;
+}
+
 // Genotype-code input (read_data.cpp:88-95,98 followed by ngsDist.cpp:172-173): exact one-hot / uniform triples.
 __device__ __forceinline__ bool posterior_from_code(int g, double p[3]) {
   if (g > 2) { p[0] = p[1] = p[2] = 0; return false; }
@@ -96,51 +133,59 @@ __device__ __forceinline__ bool miss_data(const double p[3]) {      // gen_func.
 }
 
 // grid (n_pad/32, ceil(n/64)); block (32 individuals, 16 site groups of 4) = one 64-site mask word per individual.
-__global__ void __launch_bounds__(512) k_frontend(FrontCfg c, const double *__restrict__ raw, const int8_t *__restrict__ codes,
-                                                   uint64_t n_ind, uint64_t site0, uint64_t n, uint64_t NC, uint64_t NW,
-                                                   double *__restrict__ Apack, double *__restrict__ Bpack,
-                                                   uint64_t *__restrict__ mask, int *__restrict__ err) {
+// EXACT = the reference's log-space sequence (needed by call_geno's comparisons); otherwise the fast path above.
+template <bool EXACT>
+__global__ void __launch_bounds__(512, EXACT ? 1 : 2) k_frontend(FrontCfg c, const double *__restrict__ raw, const int8_t *__restrict__ codes,
+                                                      uint64_t n_ind, uint64_t site0, uint64_t n, uint64_t NC, uint64_t NW,
+                                                      double *__restrict__ Apack, double *__restrict__ Bpack,
+                                                      uint64_t *__restrict__ mask, int *__restrict__ err) {
   __shared__ unsigned nib[16][32];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const uint64_t i = (uint64_t) blockIdx.x * 32 + tx;
   const uint64_t word = site0 / 64 + blockIdx.y;
   const uint64_t s_local0 = (uint64_t) blockIdx.y * 64 + ty * 4;   // first of this thread's 4 sites, relative to site0
 
-  double A[3][4], B[3][4];
+  double A[4][3];
+  int code[4] = {-1, -1, -1, -1};
+  // all loads first (12 independent 8-byte loads per thread; a warp reads 768 contiguous bytes per site)
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint64_t sl = s_local0 + q;
+    A[q][0] = A[q][1] = A[q][2] = 0;
+    if (i < n_ind && sl < n) {
+      if (codes) {
+        code[q] = (int) codes[sl * n_ind + i];
+      } else {
+        const double *x = raw + (sl * n_ind + i) * 3;
+        A[q][0] = x[0]; A[q][1] = x[1]; A[q][2] = x[2];
+      }
+    }
+  }
   unsigned bits = 0;
   int bad = 0;
 #pragma unroll
   for (int q = 0; q < 4; q++) {
     const uint64_t sl = s_local0 + q;
-    double p[3] = {0, 0, 0};
     bool present = false;
     if (i < n_ind && sl < n) {
       bool ok;
+      double p[3];
       if (codes) {
-        ok = posterior_from_code((int) codes[sl * n_ind + i], p);
+        ok = posterior_from_code(code[q], p);
         if (!ok) bad |= 2;
       } else {
-        const double *x = raw + (sl * n_ind + i) * 3;
-        ok = posterior(c, x[0], x[1], x[2], p);
+        ok = EXACT ? posterior(c, A[q][0], A[q][1], A[q][2], p) : posterior_fast(c, A[q][0], A[q][1], A[q][2], p);
         if (!ok) bad |= 1;
       }
       present = !miss_data(p);
       if (c.pairwise_del && !present) p[0] = p[1] = p[2] = 0;       // the skip of ngsDist.cpp:335-338, folded into the operands
+      A[q][0] = p[0]; A[q][1] = p[1]; A[q][2] = p[2];
     }
     bits |= (present ? 1u : 0u) << q;
-#pragma unroll
-    for (int g = 0; g < 3; g++) {
-      A[g][q] = p[g];
-      // (score . p)_g ; evaluated as in the reference's inner product order over g2 (ngsDist.cpp:351-353)
-      double b = c.score[3 * g + 0] * p[0];
-      b += c.score[3 * g + 1] * p[1];
-      b += c.score[3 * g + 2] * p[2];
-      B[g][q] = b;
-    }
   }
   if (bad) atomicOr(err, bad);
 
-  // packed stores: 32 bytes per plane per operand
+  // packed stores: 32 bytes per plane per operand; B = score . p evaluated in the reference's g2 order (ngsDist.cpp:351-353)
   const uint64_t rb = i >> 7, r = i & 127;
   const uint64_t sgrp = site0 / 4 + (uint64_t) blockIdx.y * 16 + ty;     // global 4-site group
   const uint64_t chunk = sgrp >> 1, h = sgrp & 1;
@@ -150,10 +195,17 @@ __global__ void __launch_bounds__(512) k_frontend(FrontCfg c, const double *__re
     const uint64_t o = base + (uint64_t) (g * 2 + h) * (16 * 32);
     double2 *pa = reinterpret_cast<double2 *>(Apack + o);
     double2 *pb = reinterpret_cast<double2 *>(Bpack + o);
-    pa[0] = make_double2(A[g][0], A[g][1]);
-    pa[1] = make_double2(A[g][2], A[g][3]);
-    pb[0] = make_double2(B[g][0], B[g][1]);
-    pb[1] = make_double2(B[g][2], B[g][3]);
+    double b[4];
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      b[q] = c.score[3 * g + 0] * A[q][0];
+      b[q] += c.score[3 * g + 1] * A[q][1];
+      b[q] += c.score[3 * g + 2] * A[q][2];
+    }
+    pa[0] = make_double2(A[0][g], A[1][g]);
+    pa[1] = make_double2(A[2][g], A[3][g]);
+    pb[0] = make_double2(b[0], b[1]);
+    pb[1] = make_double2(b[2], b[3]);
   }
 
   nib[ty][tx] = bits;
@@ -217,8 +269,12 @@ cudaError_t ngsd_launch_frontend(ngsd_ctx *ctx, const ngsd_frontend_args &a) {
   c.call_thresh = ctx->cfg.call_thresh;
   for (int k = 0; k < 9; k++) c.score[k] = ctx->cfg.score[k];
   dim3 grid((unsigned) (ctx->n_pad / 32), (unsigned) ((a.n + 63) / 64)), block(32, 16);
-  k_frontend<<<grid, block, 0, ctx->stream>>>(c, a.raw, a.codes, ctx->n_ind, a.site0, a.n, ctx->NC, ctx->NW, ctx->Apack,
-                                              ctx->Bpack, ctx->mask, ctx->d_err);
+  if (c.call_geno)
+    k_frontend<true><<<grid, block, 0, ctx->stream>>>(c, a.raw, a.codes, ctx->n_ind, a.site0, a.n, ctx->NC, ctx->NW, ctx->Apack,
+                                                      ctx->Bpack, ctx->mask, ctx->d_err);
+  else
+    k_frontend<false><<<grid, block, 0, ctx->stream>>>(c, a.raw, a.codes, ctx->n_ind, a.site0, a.n, ctx->NC, ctx->NW, ctx->Apack,
+                                                       ctx->Bpack, ctx->mask, ctx->d_err);
   return cudaGetLastError();
 }
 

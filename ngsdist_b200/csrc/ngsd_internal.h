@@ -57,6 +57,9 @@ struct ngsd_ctx {
   double *d_partials = nullptr; uint64_t partial_slots = 0;
   double *d_weights = nullptr;                 // [NC*8] per-site bootstrap weights
   uint32_t *d_chunk_ids = nullptr;             // [NC] active chunk list
+  uint32_t *d_split_begin = nullptr; uint32_t split_cap = 0;   // K-split boundaries in the chunk list
+  uint32_t *d_sched = nullptr;                 // dynamic unit counter of k_dist_dmma
+  uint32_t n_diag_tiles = 0;
   uint32_t *d_ent_word = nullptr; uint64_t *d_ent_mask = nullptr; uint64_t ent_cap = 0;   // mask-count entries
   uint32_t *d_cnt = nullptr;                   // [n_pad][n_pad] shared-site counts
   double *d_out = nullptr, *d_num = nullptr; uint64_t *d_cntout = nullptr;   // [n_ind][n_ind]

@@ -116,10 +116,10 @@ def test_frontend_posteriors_and_masks(call, thr):
         if call and thr == (0, 0):
             assert np.array_equal(Pg, P), "called genotypes must be bit-exact"
         else:
-            # device log/exp are within 1-2 ulp of glibc; a few ulp after the normalisation
-            assert np.allclose(Pg, P, rtol=1e-14, atol=1e-300)
-            hard = (P == 0) | (P == 1)
-            assert np.array_equal(Pg[hard], P[hard])
+            # un-called path: p = x / sum(x) on the device vs exp(log x - logsum) in the reference; the reference itself
+            # carries ~|log p| * 2^-52 relative error from "log(sum) + M" (frontend.cu: posterior_fast)
+            assert np.allclose(Pg, P, rtol=1e-12, atol=1e-300)
+            assert np.array_equal(Pg == 0, P == 0)   # exact zeros stay exact zeros
 
 
 @pytest.mark.parametrize("n_ind,n_sites,miss", [(130, 1000, 0.1), (300, 4099, 0.05), (257, 515, 0.3)])
