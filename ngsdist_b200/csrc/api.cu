@@ -386,10 +386,7 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
     int rc = ngsd_frontend(ctx);
     if (rc) return rc;
   }
-  if (!ctx->cfg.indep_geno) {
-    ngsd_set_error(ctx, "per pair-site EM path (indep_geno = 0) not available in this build");
-    return NGSD_ERR_ARG;
-  }
+  const bool em_path = !ctx->cfg.indep_geno;   // default --probs: per pair-site em2 (ngsDist.cpp:348-349)
   const bool weighted = block_counts != nullptr;
   uint64_t n_eff = ctx->n_sites;
   if (weighted) {
@@ -456,6 +453,7 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   }
 
   ngsd_dist_plan plan;
+  uint32_t em_splits = 0;
   plan.weighted = weighted;
   plan.n_chunks = (uint32_t) n_chunks;
   plan.grid = ctx->n_sm;
@@ -464,6 +462,11 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   plan.n_splits = (uint32_t) splits.size() - 1;
   plan.n_units = plan.n_splits * ctx->n_tiles;
   plan.grid = (int) std::min<uint64_t>(plan.grid, plan.n_units);
+  if (em_path) {
+    em_splits = ngsd_em_splits(ctx, plan.n_chunks);
+    const uint64_t ld = (ctx->n_ind + 15) / 16 * 16;
+    plan.n_units = (uint32_t) (((uint64_t) em_splits * ld * ld + NGSD_TILE_ELEMS - 1) / NGSD_TILE_ELEMS);   // workspace slots
+  }
   if (splits.size() > ctx->split_cap) {
     cudaFree(ctx->d_split_begin);
     ctx->d_split_begin = nullptr;
@@ -496,19 +499,27 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
     launches += n_entries ? 1 : 0;
   }
   tick(ctx, 3);
-  if (plan.n_chunks > 0) {
-    NGSD_CUDA(ctx, ngsd_launch_dist_dmma(ctx, plan));
+  if (em_path) {
+    NGSD_CUDA(ctx, ngsd_launch_dist_em(ctx, plan.n_chunks, em_splits, weighted));
+    launches++;
+    tick(ctx, 4);
+    NGSD_CUDA(ctx, ngsd_launch_epilogue_em(ctx, em_splits, n_eff, ctx->cfg.pairwise_del != 0));
     launches++;
   } else {
-    NGSD_CUDA(ctx, cudaMemsetAsync(ctx->d_partials, 0, (uint64_t) plan.n_units * NGSD_TILE_ELEMS * sizeof(double), ctx->stream));
+    if (plan.n_chunks > 0) {
+      NGSD_CUDA(ctx, ngsd_launch_dist_dmma(ctx, plan));
+      launches++;
+    } else {
+      NGSD_CUDA(ctx, cudaMemsetAsync(ctx->d_partials, 0, (uint64_t) plan.n_units * NGSD_TILE_ELEMS * sizeof(double), ctx->stream));
+    }
+    tick(ctx, 4);
+    ngsd_epilogue_args ea;
+    ea.n_splits = plan.n_splits;
+    ea.const_cnt = n_eff;
+    ea.use_cnt = ctx->cfg.pairwise_del != 0;
+    NGSD_CUDA(ctx, ngsd_launch_epilogue(ctx, ea));
+    launches += 2;
   }
-  tick(ctx, 4);
-  ngsd_epilogue_args ea;
-  ea.n_splits = plan.n_splits;
-  ea.const_cnt = n_eff;
-  ea.use_cnt = ctx->cfg.pairwise_del != 0;
-  NGSD_CUDA(ctx, ngsd_launch_epilogue(ctx, ea));
-  launches += 2;
   tick(ctx, 5);
   const uint64_t n2 = ctx->n_ind * ctx->n_ind;
   if (out) NGSD_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, n2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -522,7 +533,7 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[5]); ctx->timing.total_ms = ms;
   ctx->timing.launches = launches;
   ctx->timing.dist_ctas = plan.grid;
-  ctx->timing.dist_dmma = (uint64_t) plan.n_chunks * NGSD_K4_PER_CHUNK * ((uint64_t) (ctx->n_tiles - ctx->n_diag_tiles) * 256ull + (uint64_t) ctx->n_diag_tiles * 136ull);
+  ctx->timing.dist_dmma = em_path ? 0 : (uint64_t) plan.n_chunks * NGSD_K4_PER_CHUNK * ((uint64_t) (ctx->n_tiles - ctx->n_diag_tiles) * 256ull + (uint64_t) ctx->n_diag_tiles * 136ull);
   ctx->timing.active_sites = active_sites;
   return NGSD_OK;
 }

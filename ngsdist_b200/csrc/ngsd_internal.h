@@ -107,3 +107,7 @@ struct ngsd_epilogue_args {
 };
 cudaError_t ngsd_launch_epilogue(ngsd_ctx *ctx, const ngsd_epilogue_args &a);
 size_t ngsd_dist_smem_bytes();
+// K2b: per pair-site EM path (indep_geno == 0)
+uint32_t ngsd_em_splits(const ngsd_ctx *ctx, uint32_t n_chunks);
+cudaError_t ngsd_launch_dist_em(ngsd_ctx *ctx, uint32_t n_chunks, uint32_t n_splits, bool weighted);
+cudaError_t ngsd_launch_epilogue_em(ngsd_ctx *ctx, uint32_t n_splits, uint64_t const_cnt, bool use_cnt);
