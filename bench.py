@@ -243,6 +243,14 @@ def main():
 
     if rank == 0:
         peak = nb.probe_fp64_tflops(local)
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                tr = json.load(fh)["k_dist_dmma_c2"]
+            if (n_ind, n_sites) == (N_IND, N_SITES):
+                traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        except Exception:
+            pass
         alg_flops = 6.0 * units_step                   # 3 FMA per pair-site
         achieved = alg_flops / (dist_ms * 1e-3) * 1e-12
         executed = tim.dist_dmma * 512.0 / (dist_ms * 1e-3) * 1e-12
@@ -258,7 +266,8 @@ def main():
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
             "gpu_launches": n_launch,
             "roofline": {"bound": "tensor", "kernel": "k_dist_dmma (FP64 DMMA.8x8x4 contraction)", "achieved": achieved, "peak": peak,
-                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
+                         "traffic_note": "DRAM bytes read+written by one k_dist_dmma launch (ncu --set full, profiles/r01_ncu_summary.md); operands are 2.4 GB",
                          "peak_source": "live DMMA.8x8x4 issue-rate probe in this run (MEASURED_PEAKS.json has no FP64 figure; cuBLAS Dgemm measured 35.5)",
                          "executed_tflops": executed, "executed_frac": executed / peak, "kernel_ms": dist_ms,
                          "algorithmic_flops_per_launch": alg_flops,
