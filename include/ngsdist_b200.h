@@ -118,6 +118,23 @@ NGSD_API int ngsd_frontend(ngsd_ctx *ctx);
 NGSD_API int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_blocks, uint64_t block_size,
                    double *out, double *num_opt, uint64_t *cnt_opt);
 
+/* ---- multi-GPU support (one context per GPU / process) -------------------------------------------------
+ * Bootstrap replicates shard by simply calling ngsd_distances for different replicates on different contexts.
+ *
+ * Output-triangle tiles: after ngsd_set_tile_shard(rank, world) the context computes only the 128 x 128 upper-triangle
+ * tiles dealt to `rank` (round-robin over the tile list); every entry it does not own is written as 0 in out / num /
+ * cnt, so an element-wise SUM over the ranks assembles the full matrices exactly (x + 0 == x).  Not available for the
+ * per pair-site EM path.
+ *
+ * Sites: each rank creates its context for its own contiguous, block-aligned site range, calls ngsd_distances with
+ * out == NULL (raw sums stay on the device), all-reduces the buffers returned by ngsd_device_results (num: FP64 sum,
+ * cnt: uint64 sum -- e.g. ncclAllReduce over NVLink) and then calls ngsd_finish, which applies the tail of gen_dist
+ * (ngsDist.cpp:372-401: tot_sites override, division, evolutionary model) to the reduced sums: the epilogue is
+ * non-linear, so it must run after the reduction. */
+NGSD_API int ngsd_set_tile_shard(ngsd_ctx *ctx, uint32_t rank, uint32_t world);
+NGSD_API int ngsd_device_results(ngsd_ctx *ctx, double **out_dev, double **num_dev, uint64_t **cnt_dev);   /* n_ind x n_ind each */
+NGSD_API int ngsd_finish(ngsd_ctx *ctx, double *out_host);
+
 /* Host-side helper with the reference's RNG semantics (gsl_rng_taus; ngsDist.cpp:179-180, gen_func.cpp:117-119):
  * state[3] is seeded by ngsd_taus_seed and advanced by n_blocks draws per call of ngsd_boot_block_counts, which
  * fills counts[n_blocks] for one replicate exactly as rnd_map_data would have re-pointed the blocks. */

@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     "ngsd_abi_version", "ngsd_default_cfg", "ngsd_create", "ngsd_destroy", "ngsd_last_error", "ngsd_push_sites",
     "ngsd_push_sites_device", "ngsd_push_genotypes", "ngsd_frontend", "ngsd_distances", "ngsd_taus_seed", "ngsd_taus_get",
     "ngsd_boot_block_counts", "ngsd_get_posteriors", "ngsd_synth_raw_device", "ngsd_get_timing", "ngsd_stream",
-    "ngsd_probe_fp64_tflops", "ngsd_host_alloc", "ngsd_host_free",
+    "ngsd_probe_fp64_tflops", "ngsd_host_alloc", "ngsd_host_free", "ngsd_set_tile_shard", "ngsd_device_results", "ngsd_finish",
 ]
 
 
@@ -100,8 +100,12 @@ def lib():
     L.ngsd_host_alloc.restype = vp
     L.ngsd_host_free.argtypes = [vp]
     L.ngsd_host_free.restype = None
+    L.ngsd_set_tile_shard.argtypes = [vp, C.c_uint32, C.c_uint32]
+    L.ngsd_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
+    L.ngsd_finish.argtypes = [vp, vp]
     for name in ("ngsd_create", "ngsd_destroy", "ngsd_push_sites", "ngsd_push_sites_device", "ngsd_push_genotypes", "ngsd_frontend",
-                 "ngsd_distances", "ngsd_get_posteriors", "ngsd_synth_raw_device", "ngsd_get_timing", "ngsd_probe_fp64_tflops"):
+                 "ngsd_distances", "ngsd_get_posteriors", "ngsd_synth_raw_device", "ngsd_get_timing", "ngsd_probe_fp64_tflops",
+                 "ngsd_set_tile_shard", "ngsd_device_results", "ngsd_finish"):
         getattr(L, name).restype = i32
     _lib = L
     return L
@@ -286,6 +290,32 @@ class NgsDistB200:
                 counts, bs = self.next_boot_counts()
                 res.append(self.distances(counts, bs, want_num=want_num, want_cnt=want_cnt))
         return res
+
+    # -- multi-GPU (see multi.py) --
+    def set_tile_shard(self, rank, world):
+        self._check(lib().ngsd_set_tile_shard(self._h, rank, world))
+
+    def device_results(self):
+        """Device addresses of the n_ind x n_ind result buffers (dist f64, num f64, cnt u64) of the last ngsd_distances."""
+        o, n, c = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(lib().ngsd_device_results(self._h, C.byref(o), C.byref(n), C.byref(c)))
+        return o.value, n.value, c.value
+
+    def partial_sums(self, block_counts=None, block_size=1):
+        """Raw sums of this context's sites; results stay on the device (site-sharded runs)."""
+        if block_counts is not None:
+            block_counts = np.ascontiguousarray(block_counts, dtype=np.uint32)
+            nb_ = len(block_counts)
+        else:
+            nb_ = 0
+        self._check(lib().ngsd_distances(self._h, _ptr(block_counts), nb_, block_size, None, None, None))
+
+    def finish(self, out=None):
+        n = self.p.n_ind
+        if out is None:
+            out = np.empty((n, n), dtype=np.float64)
+        self._check(lib().ngsd_finish(self._h, _ptr(out)))
+        return out
 
     # -- measurement --
     def timing(self):

@@ -452,6 +452,20 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
     }
   }
 
+  if (ctx->n_tiles == 0) {   // a tile shard that owns nothing: all-zero contribution
+    int rc0 = ensure_dist_buffers(ctx, 1);
+    if (rc0) return rc0;
+    const uint64_t n2z = ctx->n_ind * ctx->n_ind;
+    NGSD_CUDA(ctx, cudaMemsetAsync(ctx->d_out, 0, n2z * sizeof(double), ctx->stream));
+    NGSD_CUDA(ctx, cudaMemsetAsync(ctx->d_num, 0, n2z * sizeof(double), ctx->stream));
+    NGSD_CUDA(ctx, cudaMemsetAsync(ctx->d_cntout, 0, n2z * sizeof(uint64_t), ctx->stream));
+    if (out) NGSD_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, n2z * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (num_opt) NGSD_CUDA(ctx, cudaMemcpyAsync(num_opt, ctx->d_num, n2z * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (cnt_opt) NGSD_CUDA(ctx, cudaMemcpyAsync(cnt_opt, ctx->d_cntout, n2z * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->timing = ngsd_timing();
+    return NGSD_OK;
+  }
   ngsd_dist_plan plan;
   uint32_t em_splits = 0;
   plan.weighted = weighted;
@@ -535,6 +549,45 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   ctx->timing.dist_ctas = plan.grid;
   ctx->timing.dist_dmma = em_path ? 0 : (uint64_t) plan.n_chunks * NGSD_K4_PER_CHUNK * ((uint64_t) (ctx->n_tiles - ctx->n_diag_tiles) * 256ull + (uint64_t) ctx->n_diag_tiles * 136ull);
   ctx->timing.active_sites = active_sites;
+  return NGSD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- multi-GPU ----
+
+int ngsd_set_tile_shard(ngsd_ctx *ctx, uint32_t rank, uint32_t world) {
+  if (!ctx) return NGSD_ERR_ARG;
+  if (world == 0 || rank >= world) { ngsd_set_error(ctx, "invalid tile shard %u of %u", rank, world); return NGSD_ERR_ARG; }
+  if (!ctx->cfg.indep_geno && world > 1) { ngsd_set_error(ctx, "tile sharding is not available on the per pair-site EM path"); return NGSD_ERR_ARG; }
+  NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<ngsd_tile> all = make_tiles((uint32_t) ctx->RB), mine;
+  for (size_t t = 0; t < all.size(); t++)
+    if (t % world == rank) mine.push_back(all[t]);
+  NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->n_tiles = (uint32_t) mine.size();
+  ctx->n_diag_tiles = 0;
+  for (auto &t : mine) ctx->n_diag_tiles += (t.ti == t.tj);
+  if (!mine.empty()) NGSD_CUDA(ctx, cudaMemcpy(ctx->d_tiles, mine.data(), mine.size() * sizeof(ngsd_tile), cudaMemcpyHostToDevice));
+  ctx->shard_rank = rank;
+  ctx->shard_world = world;
+  return NGSD_OK;
+}
+
+int ngsd_device_results(ngsd_ctx *ctx, double **out_dev, double **num_dev, uint64_t **cnt_dev) {
+  if (!ctx) return NGSD_ERR_ARG;
+  if (!ctx->d_out) { ngsd_set_error(ctx, "no results yet: call ngsd_distances first"); return NGSD_ERR_STATE; }
+  if (out_dev) *out_dev = ctx->d_out;
+  if (num_dev) *num_dev = ctx->d_num;
+  if (cnt_dev) *cnt_dev = ctx->d_cntout;
+  return NGSD_OK;
+}
+
+int ngsd_finish(ngsd_ctx *ctx, double *out_host) {
+  if (!ctx) return NGSD_ERR_ARG;
+  if (!ctx->d_out) { ngsd_set_error(ctx, "no results yet: call ngsd_distances first"); return NGSD_ERR_STATE; }
+  NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
+  NGSD_CUDA(ctx, ngsd_launch_finish(ctx));
+  if (out_host) NGSD_CUDA(ctx, cudaMemcpyAsync(out_host, ctx->d_out, ctx->n_ind * ctx->n_ind * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return NGSD_OK;
 }
 

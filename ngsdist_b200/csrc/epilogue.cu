@@ -80,7 +80,29 @@ __global__ void k_zero_diag(double *out, double *num, uint64_t *cnt, uint64_t n)
   if (cnt) cnt[i * n + i] = 0;
 }
 
+// ngsd_finish: the tail of gen_dist on already reduced raw sums (site-sharded runs): out = model(num / cnt)
+__global__ void k_finish(const double *__restrict__ num, const uint64_t *__restrict__ cnt, double *__restrict__ out, uint64_t n,
+                         uint64_t tot_sites, int evol_model) {
+  const uint64_t idx = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n) return;
+  const uint64_t i = idx / n, j = idx % n;
+  if (i == j) { out[idx] = 0.0; return; }
+  uint64_t c = cnt[idx];
+  if (tot_sites > 0) c = tot_sites;
+  double d = num[idx] / (double) c;
+  if (evol_model == 1) d = -log(1 - d);
+  else if (evol_model == 2) d = -log(1 - (d * 4 / 3)) * 3 / 4;
+  out[idx] = d;
+}
+
 }  // namespace
+
+cudaError_t ngsd_launch_finish(ngsd_ctx *ctx) {
+  const uint64_t n2 = ctx->n_ind * ctx->n_ind;
+  k_finish<<<(unsigned) ((n2 + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_num, ctx->d_cntout, ctx->d_out, ctx->n_ind, ctx->cfg.tot_sites,
+                                                                 ctx->cfg.evol_model);
+  return cudaGetLastError();
+}
 
 cudaError_t ngsd_launch_epilogue(ngsd_ctx *ctx, const ngsd_epilogue_args &e) {
   EpiArgs a;
@@ -98,6 +120,13 @@ cudaError_t ngsd_launch_epilogue(ngsd_ctx *ctx, const ngsd_epilogue_args &e) {
   a.n_tiles = ctx->n_tiles;
   a.evol_model = ctx->cfg.evol_model;
   a.no_diag = getenv("NGSD_NODIAG") ? 1 : 0;
+  if (ctx->shard_world > 1) {   // entries of tiles owned by other ranks must read as 0 (ngsd_set_tile_shard)
+    const uint64_t n2 = ctx->n_ind * ctx->n_ind;
+    cudaError_t e = cudaMemsetAsync(ctx->d_out, 0, n2 * sizeof(double), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_num, 0, n2 * sizeof(double), ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(ctx->d_cntout, 0, n2 * sizeof(uint64_t), ctx->stream);
+    if (e != cudaSuccess) return e;
+  }
   k_zero_diag<<<(unsigned) ((ctx->n_ind + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_out, ctx->d_num, ctx->d_cntout, ctx->n_ind);
   k_epilogue<<<dim3(ctx->n_tiles, 32), 256, 0, ctx->stream>>>(a);
   return cudaGetLastError();

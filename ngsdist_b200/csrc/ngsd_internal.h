@@ -60,6 +60,7 @@ struct ngsd_ctx {
   uint32_t *d_split_begin = nullptr; uint32_t split_cap = 0;   // K-split boundaries in the chunk list
   uint32_t *d_sched = nullptr;                 // dynamic unit counter of k_dist_dmma
   uint32_t n_diag_tiles = 0;
+  uint32_t shard_rank = 0, shard_world = 1;   // output-tile sharding
   uint32_t *d_ent_word = nullptr; uint64_t *d_ent_mask = nullptr; uint64_t ent_cap = 0;   // mask-count entries
   uint32_t *d_cnt = nullptr;                   // [n_pad][n_pad] shared-site counts
   double *d_out = nullptr, *d_num = nullptr; uint64_t *d_cntout = nullptr;   // [n_ind][n_ind]
@@ -110,4 +111,5 @@ size_t ngsd_dist_smem_bytes();
 // K2b: per pair-site EM path (indep_geno == 0)
 uint32_t ngsd_em_splits(const ngsd_ctx *ctx, uint32_t n_chunks);
 cudaError_t ngsd_launch_dist_em(ngsd_ctx *ctx, uint32_t n_chunks, uint32_t n_splits, bool weighted);
+cudaError_t ngsd_launch_finish(ngsd_ctx *ctx);
 cudaError_t ngsd_launch_epilogue_em(ngsd_ctx *ctx, uint32_t n_splits, uint64_t const_cnt, bool use_cnt);
