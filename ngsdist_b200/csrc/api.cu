@@ -155,6 +155,9 @@ int ngsd_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
   ctx->n_sm = prop.multiProcessorCount;
   CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+  CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+  CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  CREATE_CUDA(cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   for (auto &e : ctx->ev) CREATE_CUDA(cudaEventCreate(&e));
   for (int b = 0; b < 2; b++) {
     CREATE_CUDA(cudaEventCreateWithFlags(&ctx->stage_free[b], cudaEventDisableTiming));
@@ -189,10 +192,11 @@ int ngsd_destroy(ngsd_ctx *ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
+  if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
   cudaFree(ctx->Apack); cudaFree(ctx->Bpack); cudaFree(ctx->mask); cudaFree(ctx->d_err);
   cudaFree(ctx->stage_dev[0]); cudaFree(ctx->stage_dev[1]);
   cudaFree(ctx->d_tiles); cudaFree(ctx->d_partials); cudaFree(ctx->d_weights); cudaFree(ctx->d_chunk_ids);
-  cudaFree(ctx->d_ent_word); cudaFree(ctx->d_ent_mask); cudaFree(ctx->d_cnt); cudaFree(ctx->d_split_begin); cudaFree(ctx->d_sched);
+  cudaFree(ctx->d_ent_word); cudaFree(ctx->d_ent_mask); cudaFree(ctx->d_cnt); cudaFree(ctx->d_split_begin); cudaFree(ctx->d_split_scale); cudaFree(ctx->d_sched);
   cudaFree(ctx->d_out); cudaFree(ctx->d_num); cudaFree(ctx->d_cntout);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -202,6 +206,9 @@ int ngsd_destroy(ngsd_ctx *ctx) {
   }
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+  if (ctx->aux_stream) cudaStreamDestroy(ctx->aux_stream);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
   delete ctx;
   return NGSD_OK;
 }
@@ -400,6 +407,9 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
 
   // ---- host-side bootstrap bookkeeping: per-site weights, active chunk list, level-mask entries ----
   uint64_t n_chunks = NCu, n_entries = 0, active_sites = n_eff;
+  bool uniform_scale = false;
+  std::vector<uint32_t> class_end;      // (uniform_scale) end position of each weight class in the sorted chunk list
+  std::vector<double> class_weight;
   uint32_t maxw = 1;
   if (weighted)
     for (uint64_t b = 0; b < n_blocks; b++) maxw = std::max(maxw, block_counts[b]);
@@ -426,6 +436,23 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
       bool any = false;
       for (int k = 0; k < NGSD_SC; k++) any |= h_w[c * NGSD_SC + k] != 0.0;
       if (any) h_c[n_chunks++] = (uint32_t) c;
+    }
+    // Blocks that are whole chunks (block_size % 8 == 0): every chunk has ONE weight.  Order the chunk list by weight
+    // class (stable), let every K split lie inside one class and carry the weight as a per-split scale: the inner loop
+    // of k_dist_dmma then needs no per-site multiplies at all (DMMA and DMUL share one pipe).
+    uniform_scale = (block_size % NGSD_SC == 0) && !em_path;
+    if (uniform_scale) {
+      std::vector<uint32_t> sorted;
+      sorted.reserve(n_chunks);
+      class_end.clear();
+      class_weight.clear();
+      for (uint32_t v = 1; v <= maxw; v++) {
+        const size_t before = sorted.size();
+        for (uint64_t k = 0; k < n_chunks; k++)
+          if (h_w[(uint64_t) h_c[k] * NGSD_SC] == (double) v) sorted.push_back(h_c[k]);
+        if (sorted.size() > before) { class_end.push_back((uint32_t) sorted.size()); class_weight.push_back((double) v); }
+      }
+      memcpy(h_c, sorted.data(), n_chunks * sizeof(uint32_t));
     }
   }
   if (ctx->cfg.pairwise_del) {
@@ -473,6 +500,26 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   plan.grid = ctx->n_sm;
   const double cost_tiles = (double) (ctx->n_tiles - ctx->n_diag_tiles) + ctx->n_diag_tiles * (136.0 / 256.0);
   std::vector<uint32_t> splits = plan_splits(plan.n_chunks, ctx->n_tiles, cost_tiles, plan.grid);
+  std::vector<double> scales;
+  plan.uniform_scale = uniform_scale;
+  if (uniform_scale) {   // cut the splits at the class boundaries and record each split's weight
+    std::vector<uint32_t> cut;
+    size_t k = 0;
+    cut.push_back(0);
+    for (size_t q = 1; q < splits.size(); q++) {
+      while (k < class_end.size() && class_end[k] < splits[q]) {
+        if (class_end[k] > cut.back()) cut.push_back(class_end[k]);
+        k++;
+      }
+      if (splits[q] > cut.back()) cut.push_back(splits[q]);
+    }
+    splits.swap(cut);
+    k = 0;
+    for (size_t q = 0; q + 1 < splits.size(); q++) {
+      while (k < class_end.size() && class_end[k] <= splits[q]) k++;
+      scales.push_back(k < class_weight.size() ? class_weight[k] : 1.0);
+    }
+  }
   plan.n_splits = (uint32_t) splits.size() - 1;
   plan.n_units = plan.n_splits * ctx->n_tiles;
   plan.grid = (int) std::min<uint64_t>(plan.grid, plan.n_units);
@@ -486,6 +533,9 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
     ctx->d_split_begin = nullptr;
     ctx->split_cap = 0;
     NGSD_CUDA(ctx, dev_alloc(&ctx->d_split_begin, splits.size() + 64));
+    cudaFree(ctx->d_split_scale);
+    ctx->d_split_scale = nullptr;
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_split_scale, splits.size() + 64));
     ctx->split_cap = (uint32_t) splits.size() + 64;
   }
   rc = ensure_dist_buffers(ctx, plan.n_units);
@@ -498,8 +548,10 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   ctx->timing = ngsd_timing();
   // (pageable source: the copy is staged before the call returns, so `splits` may go out of scope afterwards)
   NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_split_begin, splits.data(), splits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (uniform_scale)
+    NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_split_scale, scales.data(), scales.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (weighted) {
-    NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_weights, h_w, bytes_w, cudaMemcpyHostToDevice, ctx->stream));
+    if (!uniform_scale) NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_weights, h_w, bytes_w, cudaMemcpyHostToDevice, ctx->stream));
     NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_chunk_ids, h_c, n_chunks * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   }
   if (n_entries) {
@@ -507,30 +559,40 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
     NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_ent_mask, h_em, n_entries * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
   }
   int launches = 0;
+  const bool do_count = ctx->cfg.pairwise_del != 0;
   tick(ctx, 2);
-  if (ctx->cfg.pairwise_del) {
-    NGSD_CUDA(ctx, ngsd_launch_mask_count(ctx, n_entries));
-    launches += n_entries ? 1 : 0;
-  }
+  if (do_count) NGSD_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));   // entry lists are on the device
   tick(ctx, 3);
+  // K2 / K2b first, so that its persistent CTAs own every SM; K3 is then launched on the auxiliary stream and its
+  // (small) CTAs co-reside with them: integer AND+POPC in the shadow of the FP64 contraction.
   if (em_path) {
     NGSD_CUDA(ctx, ngsd_launch_dist_em(ctx, plan.n_chunks, em_splits, weighted));
     launches++;
-    tick(ctx, 4);
-    NGSD_CUDA(ctx, ngsd_launch_epilogue_em(ctx, em_splits, n_eff, ctx->cfg.pairwise_del != 0));
+  } else if (plan.n_chunks > 0) {
+    NGSD_CUDA(ctx, ngsd_launch_dist_dmma(ctx, plan));
     launches++;
   } else {
-    if (plan.n_chunks > 0) {
-      NGSD_CUDA(ctx, ngsd_launch_dist_dmma(ctx, plan));
-      launches++;
-    } else {
-      NGSD_CUDA(ctx, cudaMemsetAsync(ctx->d_partials, 0, (uint64_t) plan.n_units * NGSD_TILE_ELEMS * sizeof(double), ctx->stream));
-    }
-    tick(ctx, 4);
+    NGSD_CUDA(ctx, cudaMemsetAsync(ctx->d_partials, 0, (uint64_t) plan.n_units * NGSD_TILE_ELEMS * sizeof(double), ctx->stream));
+  }
+  tick(ctx, 4);
+  if (do_count) {
+    NGSD_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    NGSD_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->aux_stream));
+    NGSD_CUDA(ctx, ngsd_launch_mask_count(ctx, n_entries, ctx->aux_stream));
+    NGSD_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->aux_stream));
+    NGSD_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    NGSD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    launches += n_entries ? 1 : 0;
+  }
+  tick(ctx, 8);
+  if (em_path) {
+    NGSD_CUDA(ctx, ngsd_launch_epilogue_em(ctx, em_splits, n_eff, do_count));
+    launches++;
+  } else {
     ngsd_epilogue_args ea;
     ea.n_splits = plan.n_splits;
     ea.const_cnt = n_eff;
-    ea.use_cnt = ctx->cfg.pairwise_del != 0;
+    ea.use_cnt = do_count;
     NGSD_CUDA(ctx, ngsd_launch_epilogue(ctx, ea));
     launches += 2;
   }
@@ -541,9 +603,10 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   if (cnt_opt) NGSD_CUDA(ctx, cudaMemcpyAsync(cnt_opt, ctx->d_cntout, n2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   float ms;
-  cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]); ctx->timing.count_ms = ms;
+  ctx->timing.count_ms = 0;
+  if (do_count) { cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ctx->timing.count_ms = ms; }   // overlaps dist_ms
   cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->timing.dist_ms = ms;
-  cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]); ctx->timing.epilogue_ms = ms;
+  cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[5]); ctx->timing.epilogue_ms = ms;
   cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[5]); ctx->timing.total_ms = ms;
   ctx->timing.launches = launches;
   ctx->timing.dist_ctas = plan.grid;

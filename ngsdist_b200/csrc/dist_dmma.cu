@@ -69,6 +69,7 @@ struct DistArgs {
   const uint32_t *chunk_ids;    // [n_chunks] or nullptr (identity)
   const ngsd_tile *tiles;
   const uint32_t *split_begin;  // [n_splits + 1] chunk-list boundaries of the K splits
+  const double *split_scale;    // [n_splits] weight common to all chunks of the split, or nullptr (= 1)
   uint32_t *sched;              // dynamic scheduler: next unit to hand out (zeroed before launch)
   double *partials;             // [n_units][16384]
   uint64_t NC;                  // chunk stride of the packed planes
@@ -212,6 +213,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_dmma(DistArgs a) {
     if (fl & kLast) {
       // partial tile in fragment order: [warp][32 accumulator pairs][lane] double2 (decoded in epilogue.cu)
       double2 *dst = reinterpret_cast<double2 *>(a.partials + (uint64_t) u * NGSD_TILE_ELEMS) + (warp * 32) * 32 + lane;
+      if (a.split_scale) {      // bootstrap multiplicity shared by every chunk of this split (block_size % 8 == 0)
+        const double sc = a.split_scale[u / a.n_tiles];
+        if (sc != 1.0) {
+#pragma unroll
+          for (int k = 0; k < 64; k++) acc[k] *= sc;
+        }
+      }
       if (fl & kDiag) {
         switch (warp) {
           case 0: store_diag<0>(acc, dst); break;
@@ -258,15 +266,21 @@ cudaError_t ngsd_launch_dist_dmma(ngsd_ctx *ctx, const ngsd_dist_plan &p) {
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(k_dist_dmma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBytes);
     if (e != cudaSuccess) return e;
+    // full shared-memory carveout, so that the small K3 CTAs (8 KiB) can co-reside with the 193 KiB pipeline ring
+    e = cudaFuncSetAttribute(k_dist_dmma<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(k_dist_dmma<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+    if (e != cudaSuccess) return e;
     attr_set[ctx->device & 63] = true;
   }
   DistArgs a;
   a.Apack = ctx->Apack;
   a.Bpack = ctx->Bpack;
-  a.weights = p.weighted ? ctx->d_weights : nullptr;
+  a.weights = (p.weighted && !p.uniform_scale) ? ctx->d_weights : nullptr;
   a.chunk_ids = p.weighted ? ctx->d_chunk_ids : nullptr;
   a.tiles = ctx->d_tiles;
   a.split_begin = ctx->d_split_begin;
+  a.split_scale = p.uniform_scale ? ctx->d_split_scale : nullptr;
   a.sched = ctx->d_sched;
   a.partials = ctx->d_partials;
   a.NC = ctx->NC;
@@ -275,7 +289,7 @@ cudaError_t ngsd_launch_dist_dmma(ngsd_ctx *ctx, const ngsd_dist_plan &p) {
   a.no_diag = getenv("NGSD_NODIAG") ? 1u : 0u;
   cudaError_t e = cudaMemsetAsync(ctx->d_sched, 0, sizeof(uint32_t), ctx->stream);
   if (e != cudaSuccess) return e;
-  if (p.weighted)
+  if (p.weighted && !p.uniform_scale)
     k_dist_dmma<true><<<p.grid, kThreads, kSmemBytes, ctx->stream>>>(a);
   else
     k_dist_dmma<false><<<p.grid, kThreads, kSmemBytes, ctx->stream>>>(a);

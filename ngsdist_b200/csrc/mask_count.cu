@@ -8,7 +8,7 @@
 
 namespace {
 
-constexpr int kEB = 16;   // entries per shared-memory batch
+constexpr int kEB = 8;   // entries per shared-memory batch
 
 struct CountArgs {
   const uint64_t *mask;       // [RB][NW][128]
@@ -20,27 +20,32 @@ struct CountArgs {
   uint32_t n_splits;
 };
 
-// grid (n_tiles, n_splits); block 256 = 16 x 16 threads, each 8 x 8 pairs (rows rr*16+ty, cols cc*16+tx)
-__global__ void __launch_bounds__(256) k_mask_count(CountArgs a) {
-  __shared__ uint64_t sa[kEB][128];
-  __shared__ uint64_t sb[kEB][128];
-  const ngsd_tile tl = a.tiles[blockIdx.x];
+// grid (4 * n_tiles, n_splits): a CTA owns the 64 x 64 quadrant `blockIdx.x & 3` of tile `blockIdx.x >> 2`.
+// block 128 = 8 x 16 threads, each 8 x 4 pairs (rows r*8+ty, cols c*16+tx).  Sized (4 warps x 64 registers, 8 KiB
+// shared memory) so that a CTA fits on an SM NEXT TO the persistent k_dist_dmma CTA (9 warps x 168 registers): the
+// counts run on the XU/ALU pipes in the shadow of the FP64 tensor contraction (api.cu launches K3 on a second stream
+// right after K2).
+__global__ void __launch_bounds__(128, 8) k_mask_count(CountArgs a) {
+  __shared__ uint64_t sa[kEB][64];
+  __shared__ uint64_t sb[kEB][64];
+  const ngsd_tile tl = a.tiles[blockIdx.x >> 2];
+  const int qr = (blockIdx.x >> 1) & 1, qc = blockIdx.x & 1;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const uint64_t e0 = (a.n_entries * blockIdx.y) / a.n_splits, e1 = (a.n_entries * (blockIdx.y + 1)) / a.n_splits;
-  const uint64_t *ma = a.mask + (uint64_t) tl.ti * a.NW * 128;
-  const uint64_t *mb = a.mask + (uint64_t) tl.tj * a.NW * 128;
-  uint32_t acc[8][8];
+  const uint64_t *ma = a.mask + (uint64_t) tl.ti * a.NW * 128 + qr * 64;
+  const uint64_t *mb = a.mask + (uint64_t) tl.tj * a.NW * 128 + qc * 64;
+  uint32_t acc[8][4];
 #pragma unroll
   for (int r = 0; r < 8; r++)
 #pragma unroll
-    for (int c = 0; c < 8; c++) acc[r][c] = 0;
+    for (int c = 0; c < 4; c++) acc[r][c] = 0;
 
   for (uint64_t eb = e0; eb < e1; eb += kEB) {
     const int nb = (int) ((e1 - eb) < kEB ? (e1 - eb) : kEB);
     __syncthreads();
 #pragma unroll
-    for (int k = 0; k < kEB * 128 / 256; k++) {
-      const int idx = k * 256 + tid, e = idx >> 7, r = idx & 127;
+    for (int k = 0; k < kEB * 64 / 128; k++) {
+      const int idx = k * 128 + tid, e = idx >> 6, r = idx & 63;
       uint64_t va = 0, vb = 0;
       if (e < nb) {
         const uint64_t w = a.ent_word[eb + e];
@@ -53,32 +58,35 @@ __global__ void __launch_bounds__(256) k_mask_count(CountArgs a) {
     __syncthreads();
 #pragma unroll 2
     for (int e = 0; e < kEB; e++) {
-      uint64_t av[8], bv[8];
+      uint64_t bv[4];
 #pragma unroll
-      for (int r = 0; r < 8; r++) av[r] = sa[e][r * 16 + ty];
+      for (int c = 0; c < 4; c++) bv[c] = sb[e][c * 16 + tx];
 #pragma unroll
-      for (int c = 0; c < 8; c++) bv[c] = sb[e][c * 16 + tx];
+      for (int r = 0; r < 8; r++) {
+        const uint64_t av = sa[e][r * 8 + ty];
 #pragma unroll
-      for (int r = 0; r < 8; r++)
-#pragma unroll
-        for (int c = 0; c < 8; c++) acc[r][c] += __popcll(av[r] & bv[c]);
+        for (int c = 0; c < 4; c++) acc[r][c] += __popcll(av & bv[c]);
+      }
     }
   }
 #pragma unroll
   for (int r = 0; r < 8; r++)
 #pragma unroll
-    for (int c = 0; c < 8; c++) {
-      const uint64_t i = (uint64_t) tl.ti * 128 + r * 16 + ty, j = (uint64_t) tl.tj * 128 + c * 16 + tx;
+    for (int c = 0; c < 4; c++) {
+      const uint64_t i = (uint64_t) tl.ti * 128 + qr * 64 + r * 8 + ty, j = (uint64_t) tl.tj * 128 + qc * 64 + c * 16 + tx;
       if (acc[r][c]) atomicAdd(&a.cnt[i * a.n_pad + j], acc[r][c]);
     }
 }
 
 }  // namespace
 
-cudaError_t ngsd_launch_mask_count(ngsd_ctx *ctx, uint64_t n_entries) {
-  cudaError_t e = cudaMemsetAsync(ctx->d_cnt, 0, ctx->n_pad * ctx->n_pad * sizeof(uint32_t), ctx->stream);
+cudaError_t ngsd_launch_mask_count(ngsd_ctx *ctx, uint64_t n_entries, cudaStream_t stream) {
+  cudaError_t e = cudaMemsetAsync(ctx->d_cnt, 0, ctx->n_pad * ctx->n_pad * sizeof(uint32_t), stream);
   if (e != cudaSuccess) return e;
   if (n_entries == 0) return cudaSuccess;
+  // same shared-memory carveout as k_dist_dmma, otherwise the SMs would have to drain before K3 could be placed on them
+  e = cudaFuncSetAttribute(k_mask_count, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+  if (e != cudaSuccess) return e;
   CountArgs a;
   a.mask = ctx->mask;
   a.ent_word = ctx->d_ent_word;
@@ -88,10 +96,10 @@ cudaError_t ngsd_launch_mask_count(ngsd_ctx *ctx, uint64_t n_entries) {
   a.NW = ctx->NW;
   a.n_pad = ctx->n_pad;
   a.n_entries = n_entries;
-  uint64_t want = (uint64_t) (4 * ctx->n_sm + ctx->n_tiles - 1) / ctx->n_tiles;
+  uint64_t want = (uint64_t) (8 * ctx->n_sm + 4 * ctx->n_tiles - 1) / (4 * ctx->n_tiles);
   uint64_t maxs = (n_entries + kEB - 1) / kEB;
   a.n_splits = (uint32_t) (want < 1 ? 1 : (want > maxs ? maxs : want));
   if (a.n_splits > 65535) a.n_splits = 65535;
-  k_mask_count<<<dim3(ctx->n_tiles, a.n_splits), 256, 0, ctx->stream>>>(a);
+  k_mask_count<<<dim3(4 * ctx->n_tiles, a.n_splits), 128, 0, stream>>>(a);
   return cudaGetLastError();
 }

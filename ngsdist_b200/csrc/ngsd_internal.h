@@ -39,6 +39,8 @@ struct ngsd_ctx {
   int n_sm = 0;
   cudaStream_t stream = nullptr;      // compute stream (all kernels)
   cudaStream_t copy_stream = nullptr; // H2D staging
+  cudaStream_t aux_stream = nullptr;  // K3 mask count, concurrent with K2
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   uint64_t n_ind = 0, n_pad = 0, RB = 0, n_sites = 0, NC = 0, NW = 0;
   double *Apack = nullptr, *Bpack = nullptr;   // [RB][NC][3072]
   uint64_t *mask = nullptr;                    // [RB][NW][128] presence bits (1 = data present)
@@ -57,7 +59,8 @@ struct ngsd_ctx {
   double *d_partials = nullptr; uint64_t partial_slots = 0;
   double *d_weights = nullptr;                 // [NC*8] per-site bootstrap weights
   uint32_t *d_chunk_ids = nullptr;             // [NC] active chunk list
-  uint32_t *d_split_begin = nullptr; uint32_t split_cap = 0;   // K-split boundaries in the chunk list
+  uint32_t *d_split_begin = nullptr; uint32_t split_cap = 0;
+  double *d_split_scale = nullptr;   // K-split boundaries in the chunk list
   uint32_t *d_sched = nullptr;                 // dynamic unit counter of k_dist_dmma
   uint32_t n_diag_tiles = 0;
   uint32_t shard_rank = 0, shard_world = 1;   // output-tile sharding
@@ -66,7 +69,7 @@ struct ngsd_ctx {
   double *d_out = nullptr, *d_num = nullptr; uint64_t *d_cntout = nullptr;   // [n_ind][n_ind]
   void *h_pin = nullptr; uint64_t h_pin_bytes = 0;    // pinned scratch for weights / lists / results
   // timing
-  cudaEvent_t ev[8] = {};
+  cudaEvent_t ev[10] = {};
   ngsd_timing timing = {};
   char err[512] = {0};
 };
@@ -97,10 +100,11 @@ struct ngsd_dist_plan {
   uint32_t n_splits;        // S
   uint32_t n_units;         // S * n_tiles
   bool weighted;
+  bool uniform_scale;       // weighted, but every chunk has one weight: splits carry it, no per-site scaling in the loop
   int grid;
 };
 cudaError_t ngsd_launch_dist_dmma(ngsd_ctx *ctx, const ngsd_dist_plan &p);
-cudaError_t ngsd_launch_mask_count(ngsd_ctx *ctx, uint64_t n_entries);
+cudaError_t ngsd_launch_mask_count(ngsd_ctx *ctx, uint64_t n_entries, cudaStream_t stream);
 struct ngsd_epilogue_args {
   uint32_t n_splits;
   uint64_t const_cnt;       // used when !pairwise_del
