@@ -1,0 +1,406 @@
+// ngsDist drop-in command line on top of libngsdist_b200.so.
+//
+// Same flags, input formats and `.dist` layout as the reference's main() (ngsDist.cpp:29-320, parse_args.cpp:52-221):
+// this file is the host side that stays C++ -- option parsing, the readers' tokenising rules, labels, the host RNG
+// stream and the writer -- and it hands RAW values to the CUDA hot path through the C ABI (include/ngsdist_b200.h).
+// Written from the behaviour documented in SURVEY.md §3/App. E; no reference source is reused.
+//
+// Differences on purpose (documented in DESIGN.md): text lines may be longer than the reference's 500 000-character
+// buffer; input is streamed in chunks (the whole data set is never held on the host); an empty text line consumes a
+// site like the reference does but yields a missing site (1/3,1/3,1/3) instead of the reference's accidental (0,0,0);
+// --verbose >= 5 per-site dumps are not produced; additive flag --device N selects the GPU.
+#include <getopt.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <time.h>
+#include <zlib.h>
+
+#include <string>
+#include <vector>
+
+#include "../../../include/ngsdist_b200.h"
+
+static const char *kVersion = "1.0.10-b200";
+
+struct Pars {
+  const char *in_geno = nullptr;
+  bool in_bin = false, in_probs = false, in_logscale = false;
+  uint64_t n_ind = 0, n_sites = 0, tot_sites = 0;
+  const char *in_labels = nullptr; bool in_labels_header = false;
+  const char *in_pos = nullptr; bool in_pos_header = false;
+  bool call_geno = false; double N_thresh = 0, call_thresh = 0;
+  bool pairwise_del = false;
+  double score[9] = {0, 0.5, 1, 0.5, 0, 0.5, 1, 0.5, 0};
+  uint64_t evol_model = 1;
+  bool indep_geno = false;
+  uint64_t n_boot_rep = 0, boot_block_size = 1;
+  const char *out = nullptr;
+  unsigned n_threads = 1, verbose = 1, seed = 0;
+  int device = 0;
+};
+
+// error(): same shape as the reference's (shared/gen_func.cpp:12-18): banner on stderr, perror, exit(-1)
+[[noreturn]] static void die(const char *func, const char *msg) {
+  fflush(stdout);
+  fprintf(stderr, "\n=====\nERROR: [%s] %s\n=====\n\n", func, msg);
+  perror("\t");
+  fflush(stderr);
+  exit(-1);
+}
+
+static const char *kModels[] = {"Raw p-distance", "Log transf. p-distance", "JC69", "K80", "F81", "HKY85/F84", "TN93"};
+
+static void parse_args(Pars *p, int argc, char **argv) {
+  static struct option lopts[] = {
+      {"geno", required_argument, nullptr, 'g'},       {"probs", no_argument, nullptr, 'p'},
+      {"log_scale", no_argument, nullptr, 'l'},        {"n_ind", required_argument, nullptr, 'n'},
+      {"n_sites", required_argument, nullptr, 's'},    {"tot_sites", required_argument, nullptr, 'S'},
+      {"labels", required_argument, nullptr, 'L'},     {"labelsH", required_argument, nullptr, 'H'},
+      {"pos", required_argument, nullptr, 'a'},        {"posH", required_argument, nullptr, 'A'},
+      {"call_geno", no_argument, nullptr, 'c'},        {"N_thresh", required_argument, nullptr, 'N'},
+      {"call_thresh", required_argument, nullptr, 'C'}, {"pairwise_del", no_argument, nullptr, 'D'},
+      {"avg_nuc_dist", no_argument, nullptr, 'd'},     {"evol_model", required_argument, nullptr, 'm'},
+      {"indep_geno", no_argument, nullptr, 'I'},       {"n_boot_rep", required_argument, nullptr, 'b'},
+      {"boot_block_size", required_argument, nullptr, 'B'}, {"out", required_argument, nullptr, 'o'},
+      {"n_threads", required_argument, nullptr, 'x'},  {"verbose", required_argument, nullptr, 'V'},
+      {"seed", required_argument, nullptr, 'r'},       {"device", required_argument, nullptr, 1000},
+      {nullptr, 0, nullptr, 0}};
+  p->seed = (unsigned) time(nullptr);
+  int c;
+  while ((c = getopt_long_only(argc, argv, "g:pln:s:S:a:A:L:H:cN:C:Ddm:Ib:B:o:x:V:r:", lopts, nullptr)) != -1) {
+    switch (c) {
+      case 'g': p->in_geno = optarg; break;
+      case 'p': p->in_probs = true; break;
+      case 'l': p->in_logscale = true; p->in_probs = true; break;
+      case 'n': p->n_ind = (uint64_t) atol(optarg); break;
+      case 's': p->n_sites = (uint64_t) atol(optarg); break;
+      case 'S': p->tot_sites = (uint64_t) atol(optarg); break;
+      case 'L': p->in_labels = optarg; p->in_labels_header = false; break;
+      case 'H': p->in_labels = optarg; p->in_labels_header = true; break;
+      case 'a': p->in_pos = optarg; p->in_pos_header = false; break;
+      case 'A': p->in_pos = optarg; p->in_pos_header = true; break;
+      case 'c': p->call_geno = true; break;
+      case 'N': p->N_thresh = atof(optarg); p->call_geno = true; break;
+      case 'C': p->call_thresh = atof(optarg); p->call_geno = true; break;
+      case 'D': p->pairwise_del = true; break;
+      case 'd': p->score[4] = 0.5; break;
+      case 'm': p->evol_model = (uint64_t) atol(optarg); break;
+      case 'I': p->indep_geno = true; break;
+      case 'b': p->n_boot_rep = (uint64_t) atol(optarg); break;
+      case 'B': p->boot_block_size = (uint64_t) atol(optarg); break;
+      case 'o': p->out = optarg; break;
+      case 'x': p->n_threads = (unsigned) atoi(optarg); break;
+      case 'V': p->verbose = (unsigned) atoi(optarg); break;
+      case 'r': p->seed = (unsigned) atoi(optarg); break;
+      case 1000: p->device = atoi(optarg); break;
+      default: exit(-1);
+    }
+  }
+  if (p->verbose >= 1) {
+    fprintf(stderr, "==> Input Arguments:\n");
+    fprintf(stderr,
+            "\tgeno: %s\n\tprobs: %s\n\tlog_scale: %s\n\tn_ind: %lu\n\tn_sites: %lu\n\ttot_sites: %lu\n\tlabels: %s (%s header)\n"
+            "\tpositions: %s (%s header)\n\tcall_geno: %s\n\tN_thresh: %f\n\tcall_thresh: %f\n\tpairwise_del: %s\n\tavg_nuc_dist: %s\n"
+            "\tevol_model: %s\n\tgeno_indep: %s\n\tn_boot_rep: %lu\n\tboot_block_size: %lu\n\tout: %s\n\tn_threads: %d\n\tverbose: %d\n"
+            "\tseed: %d\n\tversion: %s (CUDA sm_100a, device %d)\n\n",
+            p->in_geno, p->in_probs ? "true" : "false", p->in_logscale ? "true" : "false", p->n_ind, p->n_sites, p->tot_sites,
+            p->in_labels, p->in_labels_header ? "WITH" : "WITHOUT", p->in_pos, p->in_pos_header ? "WITH" : "WITHOUT",
+            p->call_geno ? "true" : "false", p->N_thresh, p->call_thresh, p->pairwise_del ? "true" : "false",
+            p->score[4] == 0.5 ? "true" : "false", p->evol_model <= 6 ? kModels[p->evol_model] : "?", p->indep_geno ? "true" : "false",
+            p->n_boot_rep, p->boot_block_size, p->out, p->n_threads, p->verbose, p->seed, kVersion, p->device);
+  }
+  if (p->verbose > 4)
+    fprintf(stderr, "==> Verbose values greater than 4 for debugging purpose only. Expect large amounts of info on screen\n");
+  // the checks of parse_args.cpp:203-220, same order and messages
+  if (p->in_geno == nullptr) die("parse_cmd_args", "genotype input file (--geno) missing!");
+  if (p->n_ind == 0) die("parse_cmd_args", "number of individuals (--n_ind) missing!");
+  if (p->n_sites == 0) die("parse_cmd_args", "number of sites (--n_sites) missing!");
+  if (p->tot_sites > 0 && p->pairwise_del)
+    die("parse_cmd_args", "cannot specify total number of sites (--tot_sites) with pairwise deletion (--pairwise_del)!");
+  if (p->call_geno && !p->in_probs) die("parse_cmd_args", "can only call genotypes from likelihoods/probabilities!");
+  if (p->evol_model > 6) die("parse_cmd_args", "invalid correction method specified!");
+  if (p->evol_model > 2 && p->in_pos == nullptr)
+    die("parse_cmd_args", "use of more complex evolutionary models requires position information!");
+  if (p->out == nullptr) die("parse_cmd_args", "output prefix (--out) missing!");
+  if (p->n_threads < 1) die("parse_cmd_args", "number of threads cannot be less than 1!");
+}
+
+// ---- line-oriented gz reading (labels, positions, text genotypes) --------------------------------------------
+
+static gzFile open_gz(const char *name, const char *mode) {
+  gzFile fh = strcmp(name, "-") == 0 ? gzdopen(fileno(stdin), mode) : gzopen(name, mode);
+  if (fh) gzbuffer(fh, 1 << 20);
+  return fh;
+}
+
+// one line of any length, trailing "\n" / "\r\n" removed; false at end of file
+static bool read_line(gzFile fh, std::string &line) {
+  line.clear();
+  char buf[65536];
+  bool got = false;
+  while (gzgets(fh, buf, sizeof(buf)) != nullptr) {
+    got = true;
+    line += buf;
+    if (!line.empty() && line.back() == '\n') break;
+  }
+  if (!got) return false;
+  while (!line.empty() && (line.back() == '\n' || line.back() == '\r')) line.pop_back();
+  return true;
+}
+
+// numeric tokens of a line: separators are blanks and tabs, a token counts only if it parses completely as a double
+// (shared/gen_func.cpp:390-417)
+static void numeric_fields(const std::string &line, std::vector<double> &out) {
+  out.clear();
+  const char *s = line.c_str();
+  while (*s) {
+    while (*s == ' ' || *s == '\t') s++;
+    if (!*s) break;
+    const char *e = s;
+    while (*e && *e != ' ' && *e != '\t') e++;
+    char *endp = nullptr;
+    std::string tok(s, e - s);
+    double v = strtod(tok.c_str(), &endp);
+    if (endp && *endp == '\0' && endp != tok.c_str()) out.push_back(v);
+    s = e;
+  }
+}
+
+static std::vector<std::string> read_labels(const Pars &p) {
+  std::vector<std::string> lab;
+  if (!p.in_labels) {
+    for (uint64_t i = 0; i < p.n_ind; i++) lab.push_back("Ind_" + std::to_string(i));   // ngsDist.cpp:118-124
+    return lab;
+  }
+  if (p.verbose >= 1) fprintf(stderr, "==> Reading labels\n");
+  gzFile fh = open_gz(p.in_labels, "r");
+  if (!fh) die("read_file", "cannot open file!");
+  std::string line;
+  uint64_t skip = p.in_labels_header ? 1 : 0;
+  while (read_line(fh, line)) {
+    if (line.empty() || line[0] == '#') continue;          // shared/gen_func.cpp:258-261
+    if (skip) { skip--; continue; }
+    size_t tab = line.find('\t');                            // cut at the first tab (ngsDist.cpp:111-116)
+    lab.push_back(tab == std::string::npos ? line : line.substr(0, tab));
+  }
+  gzclose(fh);
+  if (lab.size() != p.n_ind) die("main", "invalid LABELS file!");
+  return lab;
+}
+
+static void check_positions(const Pars &p) {   // only validated, never used (models 3-6 are rejected), ngsDist.cpp:133-149
+  if (!p.in_pos) return;
+  if (p.verbose >= 1) fprintf(stderr, "==> Reading positions file\n");
+  gzFile fh = open_gz(p.in_pos, "r");
+  if (!fh) die("read_file", "cannot open file!");
+  std::string line;
+  uint64_t skip = p.in_pos_header ? 1 : 0, rows = 0, cols = 0;
+  while (read_line(fh, line)) {
+    if (line.empty() || line[0] == '#') continue;
+    if (skip) { skip--; continue; }
+    uint64_t n = 1;
+    for (char ch : line) n += (ch == '\t');
+    if (cols == 0) cols = n;
+    if (cols != n) die("read_split", "invalid number of fields in file!");
+    rows++;
+  }
+  gzclose(fh);
+  if (rows != p.n_sites || cols < 2) die("main", "invalid POS file!");
+}
+
+// ---- writer (ngsDist.cpp:282-287; "%.10f" as gen_func.cpp:479-496) ------------------------------------------------
+
+static void write_matrix(FILE *fh, const std::vector<std::string> &lab, const double *d, uint64_t n) {
+  fprintf(fh, "\n%lu\n", n);
+  std::string row;
+  char num[64];
+  for (uint64_t i = 0; i < n; i++) {
+    row.assign(lab[i]);
+    for (uint64_t j = 0; j < n; j++) {
+      int len = snprintf(num, sizeof(num), "\t%.10f", d[i * n + j]);
+      row.append(num, len);
+    }
+    row.push_back('\n');
+    fwrite(row.data(), 1, row.size(), fh);
+  }
+}
+
+int main(int argc, char **argv) {
+  Pars p;
+  parse_args(&p, argc, argv);
+  const uint64_t n_comb = (uint64_t) ((pow((double) p.n_ind, 2) - p.n_ind) / 2);
+  if (p.verbose >= 1) fprintf(stderr, "==> Analysis will be run in %lu combinations\n", n_comb);
+  // forcing rules of ngsDist.cpp:55-65
+  if (!p.in_probs && !p.indep_geno) {
+    fprintf(stderr, "==> Using faster algorithm (assuming independence of genotypes) since input are genotypes!\n");
+    p.indep_geno = true;
+  } else if (p.call_geno && !p.indep_geno) {
+    fprintf(stderr, "==> Using faster algorithm (assuming independence of genotypes) since calling genotypes!\n");
+    p.indep_geno = true;
+  } else if (p.indep_geno && p.verbose >= 1) {
+    fprintf(stderr, "==> Using faster algorithm (assuming independence of genotypes)!\n");
+  }
+  // input kind (ngsDist.cpp:73-95)
+  if (strcmp(p.in_geno, "-") == 0) {
+    if (p.verbose >= 1) fprintf(stderr, "==> Reading from STDIN (BINARY)\n");
+    p.in_bin = true;
+  } else {
+    struct stat st;
+    if (stat(p.in_geno, &st) != 0) die("main", "cannot check GENO file size!");
+    const char *dot = strrchr(p.in_geno, '.');
+    if (dot && strcmp(dot, ".gz") == 0) {
+      if (p.verbose >= 1) fprintf(stderr, "==> GZIP input file (never BINARY)\n");
+      p.in_bin = false;
+    } else {
+      if (p.verbose >= 1) fprintf(stderr, "==> BINARY input file\n");
+      p.in_bin = true;
+      p.in_probs = true;
+      if (p.n_sites != (uint64_t) st.st_size / sizeof(double) / p.n_ind / 3) die("main", "invalid/corrupt genotype input file!");
+    }
+  }
+  std::vector<std::string> labels = read_labels(p);
+  if (p.verbose >= 4)
+    for (auto &l : labels) fprintf(stderr, "%s\n", l.c_str());
+  check_positions(p);
+
+  // ---- context ----
+  ngsd_cfg cfg;
+  ngsd_default_cfg(&cfg);
+  cfg.n_ind = p.n_ind; cfg.n_sites = p.n_sites; cfg.tot_sites = p.tot_sites;
+  memcpy(cfg.score, p.score, sizeof(cfg.score));
+  cfg.evol_model = (int32_t) p.evol_model;
+  cfg.pairwise_del = p.pairwise_del; cfg.indep_geno = p.indep_geno; cfg.call_geno = p.call_geno;
+  cfg.N_thresh = p.N_thresh; cfg.call_thresh = p.call_thresh; cfg.input_is_log = p.in_logscale;
+  const bool codes_input = !p.in_probs && !p.in_bin;
+  cfg.input_kind = codes_input ? NGSD_INPUT_GENOTYPES : (p.in_bin ? NGSD_INPUT_BINARY_GL : NGSD_INPUT_TEXT_GL);
+  cfg.device = p.device;
+  ngsd_ctx *ctx = nullptr;
+  if (ngsd_create(&cfg, &ctx)) die(cfg.evol_model > 2 ? "gen_dist" : "main", ngsd_last_error(nullptr));
+
+  // ---- read + front end, chunk by chunk (replaces read_geno + ngsDist.cpp:161-174) ----
+  if (p.verbose >= 1) fprintf(stderr, "==> Reading genotype data\n");
+  gzFile fh = open_gz(p.in_geno, p.in_bin ? "rb" : "r");
+  if (!fh) die("read_geno", "cannot open GENO file!");
+  const uint64_t per_site = p.n_ind * 3;
+  uint64_t chunk = ((uint64_t) 32 << 20) / (per_site * sizeof(double)) / 64 * 64;
+  if (chunk < 64) chunk = 64;
+  double *raw = codes_input ? nullptr : (double *) ngsd_host_alloc(chunk * per_site * sizeof(double));
+  std::vector<int8_t> codes(codes_input ? chunk * p.n_ind : 0);
+  if (!codes_input && !raw) die("main", "cannot allocate pinned host buffer");
+  std::string line;
+  std::vector<double> fields;
+  const uint64_t n_geno = p.in_probs ? 3 : 1;
+  uint64_t s_first_data = 0;   // becomes 1 once the first data line was seen (the header rule only applies before that)
+  for (uint64_t s0 = 0; s0 < p.n_sites; s0 += chunk) {
+    const uint64_t n = (p.n_sites - s0 < chunk) ? p.n_sites - s0 : chunk;
+    if (p.in_bin) {
+      const uint64_t bytes = n * per_site * sizeof(double);
+      uint64_t got = 0;
+      while (got < bytes) {
+        const unsigned want = (unsigned) ((bytes - got > (1u << 30)) ? (1u << 30) : bytes - got);
+        int r = gzread(fh, (char *) raw + got, want);
+        if (r <= 0) {
+          if (gzeof(fh)) die("read_geno", "GENO file at premature EOF. Check GENO file and number of sites!");
+          die("read_geno", "cannot read binary GENO file. Check GENO file and number of sites!");
+        }
+        got += (uint64_t) r;
+      }
+    } else {
+      for (uint64_t s = 0; s < n; s++) {
+        for (;;) {
+          if (!read_line(fh, line)) {
+            if (gzeof(fh)) die("read_geno", "GENO file at premature EOF. Check GENO file and number of sites!");
+            die("read_geno", "cannot read GZip GENO file. Check GENO file and number of sites!");
+          }
+          if (line.empty()) { fields.clear(); break; }        // consumes a site (read_data.cpp:58-59)
+          numeric_fields(line, fields);
+          if (fields.empty() || (s_first_data == 0 && s0 + s == 0 && fields.size() < p.n_ind * n_geno)) {
+            fprintf(stderr, "> Header found! Skipping line...\n");
+            continue;                                           // header: does not consume a site
+          }
+          break;
+        }
+        if (line.empty()) {
+          fprintf(stderr, "> Empty line at site %lu: treated as missing data for every individual\n", s0 + s);
+          for (uint64_t i = 0; i < p.n_ind; i++) {
+            if (codes_input) codes[s * p.n_ind + i] = -1;
+            else raw[(s * p.n_ind + i) * 3 + 0] = raw[(s * p.n_ind + i) * 3 + 1] = raw[(s * p.n_ind + i) * 3 + 2] = p.in_logscale ? log(1.0 / 3) : 1.0 / 3;
+          }
+          continue;
+        }
+        s_first_data = 1;
+        if (fields.size() < p.n_ind * n_geno) die("read_geno", "wrong GENO file format. Less fields than expected!");
+        const double *ptr = fields.data() + (fields.size() - p.n_ind * n_geno);   // last n_ind*n_geno numeric columns
+        if (codes_input) {
+          for (uint64_t i = 0; i < p.n_ind; i++) {
+            int g = (int) ptr[i];
+            if (g > 2) die("read_geno", "wrong GENO file format. Genotypes must be coded as {-1,0,1,2} !");
+            codes[s * p.n_ind + i] = (int8_t) (g < 0 ? -1 : g);
+          }
+        } else {
+          memcpy(raw + s * per_site, ptr, per_site * sizeof(double));
+        }
+      }
+    }
+    int rc = codes_input ? ngsd_push_genotypes(ctx, codes.data(), s0, n) : ngsd_push_sites(ctx, raw, s0, n);
+    if (rc) die("read_geno", ngsd_last_error(ctx));
+  }
+  {  // the file must be at EOF (read_data.cpp:106-109)
+    char extra;
+    int r = gzread(fh, &extra, 1);
+    if (!(r <= 0 && gzeof(fh))) die("read_geno", "GENO file not at EOF. Check GENO file and number of sites!");
+  }
+  gzclose(fh);
+  if (raw) ngsd_host_free(raw);
+  if (ngsd_frontend(ctx)) die("read_geno", ngsd_last_error(ctx));
+
+  if (p.verbose >= 2) fprintf(stderr, "==> Setting seed for random number generator\n");
+  uint32_t rng[3];
+  ngsd_taus_seed(rng, p.seed);                                        // gsl_rng_taus + gsl_rng_set (ngsDist.cpp:179-180)
+
+  FILE *out_fh = fopen(p.out, "w");
+  if (!out_fh) die("main", "cannot open output file!");
+  static char obuf[1 << 22];
+  setvbuf(out_fh, obuf, _IOFBF, sizeof(obuf));
+
+  std::vector<double> dist(p.n_ind * p.n_ind), num;
+  std::vector<uint64_t> cnt;
+  if (p.verbose >= 3) { num.resize(p.n_ind * p.n_ind); cnt.resize(p.n_ind * p.n_ind); }
+  std::vector<uint32_t> counts;
+  uint64_t n_sites = p.n_sites;
+  for (uint64_t rep = 0; rep <= p.n_boot_rep; rep++) {
+    if (p.verbose >= 1) {
+      if (rep == 0) fprintf(stderr, "==> Analyzing full dataset...\n");
+      else fprintf(stderr, "==> Bootstrap replicate # %lu ...\n", rep);
+    }
+    int rc;
+    if (rep == 0) {
+      rc = ngsd_distances(ctx, nullptr, 0, 1, dist.data(), num.empty() ? nullptr : num.data(), cnt.empty() ? nullptr : cnt.data());
+    } else {
+      n_sites -= n_sites % p.boot_block_size;                         // persistent truncation (ngsDist.cpp:236)
+      const uint64_t n_blocks = n_sites / p.boot_block_size;
+      counts.resize(n_blocks);
+      ngsd_boot_block_counts(rng, n_blocks, counts.data());           // the draws of rnd_map_data (ngsDist.cpp:421-423)
+      rc = ngsd_distances(ctx, counts.data(), n_blocks, p.boot_block_size, dist.data(), num.empty() ? nullptr : num.data(),
+                          cnt.empty() ? nullptr : cnt.data());
+    }
+    if (rc) die("gen_dist", ngsd_last_error(ctx));
+    if (p.verbose >= 3)
+      for (uint64_t i1 = 0; i1 < p.n_ind; i1++)
+        for (uint64_t i2 = i1 + 1; i2 < p.n_ind; i2++)
+          fprintf(stderr, "\tDistance of %f from %lu valid sites (%f) between %s (ind %lu) and %s (ind %lu)!\n", num[i1 * p.n_ind + i2],
+                  cnt[i1 * p.n_ind + i2], num[i1 * p.n_ind + i2] / (double) cnt[i1 * p.n_ind + i2], labels[i1].c_str(), i1,
+                  labels[i2].c_str(), i2);
+    if (p.verbose >= 2) fprintf(stderr, "> Printing distance matrix\n");
+    write_matrix(out_fh, labels, dist.data(), p.n_ind);
+  }
+  fclose(out_fh);
+  if (p.verbose >= 1) fprintf(stderr, "==> Freeing memory...\n");
+  ngsd_destroy(ctx);
+  if (p.verbose >= 1) fprintf(stderr, "Done!\n");
+  return 0;
+}

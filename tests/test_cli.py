@@ -1,0 +1,101 @@
+"""The drop-in command line (ngsdist_b200/bin/ngsDist): same flags, inputs and .dist layout as the reference.
+
+CPU part: argument validation reproduces parse_args.cpp:203-220 (message + exit status 255) before any CUDA call.
+GPU part: every golden case is run through the binary and compared with the reference's own .dist text.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from util import GOLDEN, golden_text, manifest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "ngsdist_b200", "bin", "ngsDist")
+MAN = manifest()
+
+
+def run_cli(args, **kw):
+    return subprocess.run([CLI] + args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, **kw)
+
+
+def test_cli_is_built():
+    assert os.path.exists(CLI), "run __graft_entry__.build()"
+
+
+@pytest.mark.parametrize("args,msg", [
+    ([], "genotype input file (--geno) missing!"),
+    (["--geno", "x.bin"], "number of individuals (--n_ind) missing!"),
+    (["--geno", "x.bin", "--n_ind", "3"], "number of sites (--n_sites) missing!"),
+    (["--geno", "x.bin", "--n_ind", "3", "--n_sites", "4", "--tot_sites", "9", "--pairwise_del", "--out", "o"], "cannot specify total number of sites"),
+    (["--geno", "x.gz", "--n_ind", "3", "--n_sites", "4", "--call_geno", "--out", "o"], "can only call genotypes from likelihoods/probabilities!"),
+    (["--geno", "x.bin", "--n_ind", "3", "--n_sites", "4", "--evol_model", "9", "--out", "o"], "invalid correction method specified!"),
+    (["--geno", "x.bin", "--n_ind", "3", "--n_sites", "4", "--evol_model", "3", "--out", "o"], "requires position information!"),
+    (["--geno", "x.bin", "--n_ind", "3", "--n_sites", "4"], "output prefix (--out) missing!"),
+    (["--geno", "x.bin", "--n_ind", "3", "--n_sites", "4", "--out", "o", "--n_threads", "0"], "number of threads cannot be less than 1!"),
+    # single-dash long options and unique prefixes are accepted (getopt_long_only), then the size check fires
+    (["-geno", os.path.join(GOLDEN, "g7x53.bin"), "-n_ind", "7", "-n_sites", "50", "-out", "o", "-verb", "0"], "invalid/corrupt genotype input file!"),
+])
+def test_cli_argument_errors(args, msg):
+    r = run_cli(args + ([] if "-verb" in args else ["--verbose", "0"]))
+    assert r.returncode == 255
+    assert "ERROR: [" in r.stderr and msg in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", MAN["binary"] + MAN["text"], ids=lambda c: c["name"])
+def test_cli_reproduces_reference_dist_files(case, tmp_path):
+    out = str(tmp_path / "out.dist")
+    args = ["--geno", os.path.join(GOLDEN, case["input"]), "--n_ind", str(case["n_ind"]), "--n_sites", str(case["n_sites"]),
+            "--out", out, "--n_threads", "4", "--verbose", "0"] + case["flags"]
+    r = run_cli(args)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got_text = open(out).read()
+    want_text = golden_text(case["name"])
+    got = [m for _, m in oracle.parse_dist(out, case["n_ind"])]
+    ref_path = str(tmp_path / "ref.dist")
+    open(ref_path, "w").write(want_text)
+    want = [m for _, m in oracle.parse_dist(ref_path, case["n_ind"])]
+    assert len(got) == len(want)
+    # identical layout: same lines, labels, column counts
+    assert [l.split("\t")[0] for l in got_text.split("\n")] == [l.split("\t")[0] for l in want_text.split("\n")]
+    for g, w in zip(got, want):
+        fin = np.isfinite(w)
+        assert np.array_equal(np.isnan(g), np.isnan(w)) and np.array_equal(np.isinf(g), np.isinf(w))
+        assert np.abs(g[fin] - w[fin]).max() <= 1.1e-10      # at most one unit in the 10th printed decimal
+    if case["name"] in ("txt_geno_pdel_boot", "call", "txt_geno"):
+        # called / genotype input: exact sums (multiples of 0.5 or the same u = 1/3 terms) -> byte-identical text expected
+        if case["name"] == "txt_geno_pdel_boot":
+            assert got_text == want_text
+
+
+@pytest.mark.gpu
+def test_cli_labels_stdin_and_nan_spelling(tmp_path):
+    n_ind, n_sites = 5, 64
+    raw = oracle.synth_raw(3, 0.0, n_ind, n_sites)
+    raw[:32, 0, :] = 1 / 3
+    raw[32:, 1, :] = 1 / 3                      # individuals 0 and 1 never share a site -> cnt == 0 -> -nan / nan
+    geno = tmp_path / "in.bin"
+    raw.tofile(geno)
+    labels = tmp_path / "labels.txt"
+    labels.write_text("# comment\nheader\nA\tx\nB\nC\nD\nE\n")
+    out = tmp_path / "o.dist"
+    flags = ["--probs", "--indep_geno", "--pairwise_del", "--evol_model", "0"]
+    r = run_cli(["--geno", str(geno), "--n_ind", "5", "--n_sites", "64", "--labelsH", str(labels), "--out", str(out), "--verbose", "0"] + flags)
+    assert r.returncode == 0, r.stderr
+    ref, ref_text = oracle.run_reference(None, flags + ["--labelsH", str(labels)], geno_path=str(geno), n_ind=n_ind, n_sites=n_sites) \
+        if oracle.have_ref() else (None, None)
+    text = out.read_text()
+    assert text.split("\n")[2].startswith("A\t0.0000000000\t-nan\t")
+    if ref_text is not None:
+        assert [l.split("\t")[0] for l in text.split("\n")] == [l.split("\t")[0] for l in ref_text.split("\n")]
+        assert text.count("nan") == ref_text.count("nan") and text.count("-nan") == ref_text.count("-nan")
+    # binary from stdin ("-")
+    out2 = tmp_path / "o2.dist"
+    with open(geno, "rb") as fh:
+        r = subprocess.run([CLI, "--geno", "-", "--probs", "--n_ind", "5", "--n_sites", "64", "--labelsH", str(labels), "--out", str(out2),
+                            "--verbose", "0"] + flags[1:], stdin=fh, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stderr
+    assert out2.read_text() == text
