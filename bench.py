@@ -251,9 +251,14 @@ def main():
                 traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
         except Exception:
             pass
-        alg_flops = 6.0 * units_step                   # 3 FMA per pair-site
-        achieved = alg_flops / (dist_ms * 1e-3) * 1e-12
+        # SURVEY §8(d) accounting rule: (i) roofline.achieved = FP64 tensor FLOP/s EXECUTED by the kernel (DMMA.8x8x4 count
+        # x 512, including diagonal-tile waste) against the measured DMMA peak; (ii) `useful` = nominal pair-sites/s x 6 FLOP
+        # (3 FMA per pair-site, ngsDist.cpp:351-353) against the same peak.  Without --pairwise_del the kernel uses the
+        # sum-to-one reduction (2 FMA per pair-site), so (ii) may exceed (i) and even 1.0; it is never the roofline fraction.
+        alg_flops = 6.0 * units_step
+        useful = alg_flops / (dist_ms * 1e-3) * 1e-12
         executed = tim.dist_dmma * 512.0 / (dist_ms * 1e-3) * 1e-12
+        achieved = executed
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": W,
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
@@ -269,8 +274,10 @@ def main():
                          "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
                          "traffic_note": "DRAM bytes read+written by one k_dist_dmma launch (ncu --set full, profiles/r01_ncu_summary.md); operands are 2.4 GB",
                          "peak_source": "live DMMA.8x8x4 issue-rate probe in this run (MEASURED_PEAKS.json has no FP64 figure; cuBLAS Dgemm measured 35.5)",
-                         "executed_tflops": executed, "executed_frac": executed / peak, "kernel_ms": dist_ms,
+                         "executed_flops_per_launch": tim.dist_dmma * 512.0, "kernel_ms": dist_ms,
+                         "useful_tflops_at_6flop_per_pair_site": useful, "useful_frac": useful / peak,
                          "algorithmic_flops_per_launch": alg_flops,
+                         "note": "achieved = executed DMMA FLOP/s; the 2-plane (sum-to-one) contraction does 4 FLOP per pair-site",
                          "step_share": {"dist_ms": dist_ms, "epilogue_ms": statistics.mean(t_epi), "step_ms": ms_total / args.steps}},
         }
         if world == 1 and not args.no_cpu_baseline:

@@ -66,7 +66,8 @@ typedef struct {
   int32_t input_is_log;      /* params.in_logscale as given on the command line                     */
   int32_t input_kind;        /* ngsd_input_kind                                                      */
   int32_t device;            /* CUDA device ordinal this context owns                                */
-  int32_t reserved;          /* must be 0                                                            */
+  int32_t reserved;          /* flags: bit 0 = keep all three operand planes (disables the sum-to-one reduction that is
+                                used when indep_geno && !pairwise_del; for inspection through ngsd_get_posteriors)  */
 } ngsd_cfg;
 
 typedef struct ngsd_ctx ngsd_ctx;

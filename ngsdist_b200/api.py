@@ -139,6 +139,7 @@ class Params:
     boot_block_size: int = 1
     seed: int = 12345
     in_text: bool = False      # text reader semantics (no -inf clamp) instead of the binary reader's
+    keep_planes: bool = False  # ngsd_cfg.reserved bit 0: keep all three operand planes (exact ngsd_get_posteriors)
 
     def resolved(self):
         """Apply the parse-time implications and main()'s forcing rules (parse_args.cpp:91-94,123-130; ngsDist.cpp:55-62)."""
@@ -190,6 +191,7 @@ class NgsDistB200:
         cfg.input_is_log = int(p.in_logscale)
         cfg.input_kind = 2 if not p.in_probs else (1 if p.in_text else 0)
         cfg.device = device
+        cfg.reserved = 1 if p.keep_planes else 0
         self._h = C.c_void_p()
         rc = L.ngsd_create(C.byref(cfg), C.byref(self._h))
         if rc:

@@ -117,7 +117,7 @@ int ngsd_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
     ngsd_set_error(nullptr, "missing data threshold must be smaller than calling genotype threshold!");
     return NGSD_ERR_THRESH;
   }
-  if (cfg->input_kind < 0 || cfg->input_kind > 2 || cfg->reserved != 0) { ngsd_set_error(nullptr, "invalid input_kind / reserved"); return NGSD_ERR_ARG; }
+  if (cfg->input_kind < 0 || cfg->input_kind > 2 || (cfg->reserved & ~1)) { ngsd_set_error(nullptr, "invalid input_kind / flags"); return NGSD_ERR_ARG; }
   if ((cfg->input_kind == NGSD_INPUT_GENOTYPES || cfg->call_geno) && !cfg->indep_geno) {
     ngsd_set_error(nullptr, "indep_geno must be set for genotype input / call_geno (ngsDist.cpp:55-62)");
     return NGSD_ERR_ARG;
@@ -168,12 +168,20 @@ int ngsd_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
   ctx->n_pad = (cfg->n_ind + NGSD_TILE - 1) / NGSD_TILE * NGSD_TILE;
   ctx->RB = ctx->n_pad / NGSD_TILE;
   ctx->NW = (cfg->n_sites + 63) / 64;
-  ctx->NC = ctx->NW * 8;
+  // sum-to-one reduction (2 operand planes) whenever no individual-site is masked out of the contraction
+  ctx->planes = (cfg->indep_geno && !cfg->pairwise_del && !(cfg->reserved & 1)) ? 2 : 3;
+  ctx->sc = ctx->planes == 3 ? NGSD_SC : NGSD_SC2;
+  ctx->NC = ctx->planes == 3 ? ctx->NW * 8 : (ctx->NW * 16 + 2) / 3;
   ctx->pushed.assign(ctx->NW, 0);
   const uint64_t plane = ctx->RB * ctx->NC * NGSD_TILE_DOUBLES;
   CREATE_CUDA(dev_alloc(&ctx->Apack, plane));
   CREATE_CUDA(dev_alloc(&ctx->Bpack, plane));
   CREATE_CUDA(dev_alloc(&ctx->mask, ctx->RB * ctx->NW * 128));
+  if (ctx->planes == 2) {
+    ctx->ldc = ctx->NW * 64;
+    CREATE_CUDA(dev_alloc(&ctx->Cplane, ctx->n_pad * ctx->ldc));
+    CREATE_CUDA(dev_alloc(&ctx->d_cvec, ctx->n_pad));
+  }
   CREATE_CUDA(dev_alloc(&ctx->d_err, 1));
   CREATE_CUDA(dev_alloc(&ctx->d_sched, 1));
   CREATE_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
@@ -193,7 +201,7 @@ int ngsd_destroy(ngsd_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
-  cudaFree(ctx->Apack); cudaFree(ctx->Bpack); cudaFree(ctx->mask); cudaFree(ctx->d_err);
+  cudaFree(ctx->Apack); cudaFree(ctx->Bpack); cudaFree(ctx->mask); cudaFree(ctx->d_err); cudaFree(ctx->Cplane); cudaFree(ctx->d_cvec);
   cudaFree(ctx->stage_dev[0]); cudaFree(ctx->stage_dev[1]);
   cudaFree(ctx->d_tiles); cudaFree(ctx->d_partials); cudaFree(ctx->d_weights); cudaFree(ctx->d_chunk_ids);
   cudaFree(ctx->d_ent_word); cudaFree(ctx->d_ent_mask); cudaFree(ctx->d_cnt); cudaFree(ctx->d_split_begin); cudaFree(ctx->d_split_scale); cudaFree(ctx->d_sched);
@@ -357,7 +365,7 @@ static int ensure_dist_buffers(ngsd_ctx *ctx, uint64_t slots) {
     NGSD_CUDA(ctx, dev_alloc(&ctx->d_out, n2));
     NGSD_CUDA(ctx, dev_alloc(&ctx->d_num, n2));
     NGSD_CUDA(ctx, dev_alloc(&ctx->d_cntout, n2));
-    NGSD_CUDA(ctx, dev_alloc(&ctx->d_weights, ctx->NC * NGSD_SC));
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_weights, ctx->NC * NGSD_SC_MAX));
     NGSD_CUDA(ctx, dev_alloc(&ctx->d_chunk_ids, ctx->NC));
     if (ctx->cfg.pairwise_del) NGSD_CUDA(ctx, dev_alloc(&ctx->d_cnt, ctx->n_pad * ctx->n_pad));
   }
@@ -403,7 +411,8 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
     }
     n_eff = n_blocks * block_size;
   }
-  const uint64_t NCu = (ctx->n_sites + NGSD_SC - 1) / NGSD_SC;   // chunks that hold data
+  const uint64_t SC = (uint64_t) ctx->sc;
+  const uint64_t NCu = (ctx->n_sites + SC - 1) / SC;   // chunks that hold data
 
   // ---- host-side bootstrap bookkeeping: per-site weights, active chunk list, level-mask entries ----
   uint64_t n_chunks = NCu, n_entries = 0, active_sites = n_eff;
@@ -414,7 +423,7 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   if (weighted)
     for (uint64_t b = 0; b < n_blocks; b++) maxw = std::max(maxw, block_counts[b]);
   const uint64_t ent_max = ctx->cfg.pairwise_del ? ctx->NW * (weighted ? maxw : 1) : 0;
-  const uint64_t bytes_w = ctx->NC * NGSD_SC * sizeof(double), bytes_c = ctx->NC * sizeof(uint32_t);
+  const uint64_t bytes_w = ctx->NC * SC * sizeof(double), bytes_c = ctx->NC * sizeof(uint32_t);
   const uint64_t bytes_e = ent_max * (sizeof(uint32_t) + sizeof(uint64_t));
   int rc = ensure_pinned(ctx, bytes_w + bytes_c + bytes_e + 64);
   if (rc) return rc;
@@ -434,13 +443,13 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
     n_chunks = 0;
     for (uint64_t c = 0; c < NCu; c++) {
       bool any = false;
-      for (int k = 0; k < NGSD_SC; k++) any |= h_w[c * NGSD_SC + k] != 0.0;
+      for (uint64_t k = 0; k < SC; k++) any |= h_w[c * SC + k] != 0.0;
       if (any) h_c[n_chunks++] = (uint32_t) c;
     }
     // Blocks that are whole chunks (block_size % 8 == 0): every chunk has ONE weight.  Order the chunk list by weight
     // class (stable), let every K split lie inside one class and carry the weight as a per-split scale: the inner loop
     // of k_dist_dmma then needs no per-site multiplies at all (DMMA and DMUL share one pipe).
-    uniform_scale = (block_size % NGSD_SC == 0) && !em_path;
+    uniform_scale = (block_size % SC == 0) && !em_path;
     if (uniform_scale) {
       std::vector<uint32_t> sorted;
       sorted.reserve(n_chunks);
@@ -449,7 +458,7 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
       for (uint32_t v = 1; v <= maxw; v++) {
         const size_t before = sorted.size();
         for (uint64_t k = 0; k < n_chunks; k++)
-          if (h_w[(uint64_t) h_c[k] * NGSD_SC] == (double) v) sorted.push_back(h_c[k]);
+          if (h_w[(uint64_t) h_c[k] * SC] == (double) v) sorted.push_back(h_c[k]);
         if (sorted.size() > before) { class_end.push_back((uint32_t) sorted.size()); class_weight.push_back((double) v); }
       }
       memcpy(h_c, sorted.data(), n_chunks * sizeof(uint32_t));
@@ -551,7 +560,8 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   if (uniform_scale)
     NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_split_scale, scales.data(), scales.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (weighted) {
-    if (!uniform_scale) NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_weights, h_w, bytes_w, cudaMemcpyHostToDevice, ctx->stream));
+    if (!uniform_scale || ctx->planes == 2)   // per-site weights: scaled B fragments and/or the weighted c-vector
+      NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_weights, h_w, bytes_w, cudaMemcpyHostToDevice, ctx->stream));
     NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_chunk_ids, h_c, n_chunks * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   }
   if (n_entries) {
@@ -585,6 +595,10 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
     launches += n_entries ? 1 : 0;
   }
   tick(ctx, 8);
+  if (!em_path && ctx->planes == 2) {
+    NGSD_CUDA(ctx, ngsd_launch_cvec(ctx, weighted, n_eff));
+    launches++;
+  }
   if (em_path) {
     NGSD_CUDA(ctx, ngsd_launch_epilogue_em(ctx, em_splits, n_eff, do_count));
     launches++;

@@ -23,7 +23,7 @@ namespace {
 constexpr int kStages = 4;
 constexpr int kConsumerWarps = 8;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;
-constexpr int kStageBytes = 2 * NGSD_TILE_BYTES + 64;   // A + B + 8 weights
+constexpr int kStageBytes = 2 * NGSD_TILE_BYTES + 128;  // A + B + up to 12 per-site weights
 constexpr size_t kSmemBytes = (size_t) kStages * kStageBytes + 2 * kStages * sizeof(uint64_t) + kStages * 2 * sizeof(uint32_t) + 128;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
@@ -97,12 +97,12 @@ __device__ __forceinline__ void step_full(double (&acc)[64], const double *As, c
 // balanced): acc[0..31] = row W, columns 0..15; acc[32..63] = row 15-W.  Specialised per warp at compile time:
 // predicated-off DMMAs still cost issue slots on the FP64 tensor pipe, so each warp runs straight-line code with
 // exactly its 17 DMMA + (18 - W) LDS.64 per K4 step.
-template <int W>
-__device__ __forceinline__ void chunk_diag(double (&acc)[64], const double *As, const double *Bs, double w0, double w1) {
+template <int W, int PLANES>
+__device__ __forceinline__ void chunk_diag(double (&acc)[64], const double *As, const double *Bs, const double (&wv)[3]) {
 #pragma unroll
   for (int k4 = 0; k4 < NGSD_K4_PER_CHUNK; k4++) {
     const double *Ak = As + k4 * 512, *Bk = Bs + k4 * 512;
-    const double w = (k4 & 1) ? w1 : w0;
+    const double w = wv[PLANES == 3 ? (k4 & 1) : (k4 % 3)];
     const double a0 = Ak[W * 32], a1 = Ak[(15 - W) * 32];
     double bf[16];
 #pragma unroll
@@ -122,7 +122,9 @@ __device__ __forceinline__ void store_diag(const double (&acc)[64], double2 *dst
   for (int c = 15 - W; c < 16; c++) dst[(16 + c) * 32] = make_double2(acc[32 + c * 2], acc[32 + c * 2 + 1]);
 }
 
-template <bool WEIGHTED>
+// PLANES = 3: chunk of 8 sites, k4-group = g*2 + h;  PLANES = 2: chunk of 12 sites, k4-group = g*3 + h (ngsd_internal.h).
+// The only place the two differ inside the kernel is which per-site weight a k4-group takes.
+template <bool WEIGHTED, int PLANES>
 __global__ void __launch_bounds__(kThreads, 1) k_dist_dmma(DistArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t) kStages * kStageBytes);
@@ -159,10 +161,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_dmma(DistArgs a) {
           mbar_wait(&empty[stage], phase ^ 1);
           meta[stage * 2] = u;
           meta[stage * 2 + 1] = fl | (c == c0 ? kFirst : 0u) | (c + 1 == c1 ? kLast : 0u);
-          mbar_expect_tx(&full[stage], WEIGHTED ? kStageBytes : 2 * NGSD_TILE_BYTES);
+          constexpr int kSites = PLANES == 3 ? NGSD_SC : NGSD_SC2;
+          mbar_expect_tx(&full[stage], 2 * NGSD_TILE_BYTES + (WEIGHTED ? kSites * 8 : 0));
           bulk_g2s(stageA(stage), Ab + chunk * NGSD_TILE_DOUBLES, NGSD_TILE_BYTES, &full[stage]);
           bulk_g2s(stageB(stage), Bb + chunk * NGSD_TILE_DOUBLES, NGSD_TILE_BYTES, &full[stage]);
-          if (WEIGHTED) bulk_g2s(stageW(stage), a.weights + chunk * NGSD_SC, 64, &full[stage]);
+          if (WEIGHTED) bulk_g2s(stageW(stage), a.weights + chunk * kSites, kSites * 8, &full[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -184,28 +187,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_dmma(DistArgs a) {
 #pragma unroll
       for (int k = 0; k < 64; k++) acc[k] = 0.0;
     }
-    double w0 = 1.0, w1 = 1.0;
+    double wv[3] = {1.0, 1.0, 1.0};              // weight of this lane's site in each 4-site group of the chunk
     if (WEIGHTED) {
       const double *Ws = stageW(stage);
-      w0 = Ws[lane & 3];
-      w1 = Ws[4 + (lane & 3)];
+      wv[0] = Ws[lane & 3];
+      wv[1] = Ws[4 + (lane & 3)];
+      if (PLANES == 2) wv[2] = Ws[8 + (lane & 3)];
     }
+    const double w0 = wv[0], w1 = wv[1];
+    (void) w0; (void) w1;
     if (fl & kDiag) {
       const double *As = stageA(stage) + lane, *Bs = stageB(stage) + lane;
       switch (warp) {       // warp-uniform: no divergence
-        case 0: chunk_diag<0>(acc, As, Bs, w0, w1); break;
-        case 1: chunk_diag<1>(acc, As, Bs, w0, w1); break;
-        case 2: chunk_diag<2>(acc, As, Bs, w0, w1); break;
-        case 3: chunk_diag<3>(acc, As, Bs, w0, w1); break;
-        case 4: chunk_diag<4>(acc, As, Bs, w0, w1); break;
-        case 5: chunk_diag<5>(acc, As, Bs, w0, w1); break;
-        case 6: chunk_diag<6>(acc, As, Bs, w0, w1); break;
-        default: chunk_diag<7>(acc, As, Bs, w0, w1); break;
+        case 0: chunk_diag<0, PLANES>(acc, As, Bs, wv); break;
+        case 1: chunk_diag<1, PLANES>(acc, As, Bs, wv); break;
+        case 2: chunk_diag<2, PLANES>(acc, As, Bs, wv); break;
+        case 3: chunk_diag<3, PLANES>(acc, As, Bs, wv); break;
+        case 4: chunk_diag<4, PLANES>(acc, As, Bs, wv); break;
+        case 5: chunk_diag<5, PLANES>(acc, As, Bs, wv); break;
+        case 6: chunk_diag<6, PLANES>(acc, As, Bs, wv); break;
+        default: chunk_diag<7, PLANES>(acc, As, Bs, wv); break;
       }
     } else {
       const double *As = stageA(stage) + (wm * 8) * 32 + lane, *Bs = stageB(stage) + (wn * 4) * 32 + lane;
 #pragma unroll
-      for (int k4 = 0; k4 < NGSD_K4_PER_CHUNK; k4++) step_full(acc, As + k4 * 512, Bs + k4 * 512, (k4 & 1) ? w1 : w0);
+      for (int k4 = 0; k4 < NGSD_K4_PER_CHUNK; k4++) step_full(acc, As + k4 * 512, Bs + k4 * 512, wv[PLANES == 3 ? (k4 & 1) : (k4 % 3)]);
     }
     __syncwarp();
     if (lane == 0) mbar_arrive(&empty[stage]);
@@ -262,15 +268,13 @@ size_t ngsd_dist_smem_bytes() { return kSmemBytes; }
 cudaError_t ngsd_launch_dist_dmma(ngsd_ctx *ctx, const ngsd_dist_plan &p) {
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
-    cudaError_t e = cudaFuncSetAttribute(k_dist_dmma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBytes);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_dist_dmma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBytes);
-    if (e != cudaSuccess) return e;
-    // full shared-memory carveout, so that the small K3 CTAs (8 KiB) can co-reside with the 193 KiB pipeline ring
-    e = cudaFuncSetAttribute(k_dist_dmma<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(k_dist_dmma<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-    if (e != cudaSuccess) return e;
+    const void *fns[3] = {(const void *) k_dist_dmma<false, 3>, (const void *) k_dist_dmma<true, 3>, (const void *) k_dist_dmma<true, 2>};
+    for (const void *f : fns) {
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBytes);
+      if (e != cudaSuccess) return e;
+      e = cudaFuncSetAttribute(f, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+      if (e != cudaSuccess) return e;
+    }
     attr_set[ctx->device & 63] = true;
   }
   DistArgs a;
@@ -289,10 +293,14 @@ cudaError_t ngsd_launch_dist_dmma(ngsd_ctx *ctx, const ngsd_dist_plan &p) {
   a.no_diag = getenv("NGSD_NODIAG") ? 1u : 0u;
   cudaError_t e = cudaMemsetAsync(ctx->d_sched, 0, sizeof(uint32_t), ctx->stream);
   if (e != cudaSuccess) return e;
-  if (p.weighted && !p.uniform_scale)
-    k_dist_dmma<true><<<p.grid, kThreads, kSmemBytes, ctx->stream>>>(a);
-  else
-    k_dist_dmma<false><<<p.grid, kThreads, kSmemBytes, ctx->stream>>>(a);
+  if (p.weighted && !p.uniform_scale) {
+    if (ctx->planes == 3)
+      k_dist_dmma<true, 3><<<p.grid, kThreads, kSmemBytes, ctx->stream>>>(a);
+    else
+      k_dist_dmma<true, 2><<<p.grid, kThreads, kSmemBytes, ctx->stream>>>(a);
+  } else {
+    k_dist_dmma<false, 3><<<p.grid, kThreads, kSmemBytes, ctx->stream>>>(a);   // unweighted: plane count is irrelevant
+  }
   return cudaGetLastError();
 }
 

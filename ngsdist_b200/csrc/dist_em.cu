@@ -21,6 +21,7 @@ namespace {
 
 constexpr int kGroupChunks = 4;                 // chunks (of 8 sites) staged per shared-memory group
 constexpr int kGroupSites = kGroupChunks * NGSD_SC;
+constexpr int kRound = 4;                       // EM steps between two finish rounds
 constexpr double kExpTol = 1.0010005001667084;  // e^0.001 (tole of ngsDist.cpp:349)
 
 struct EmArgs {
@@ -77,14 +78,15 @@ __global__ void __launch_bounds__(256) k_dist_em(EmArgs a) {
       }
     }
     __syncthreads();
-    if (!live) continue;
 
-    // ---- flattened EM: one trip = one EM step of this thread's current site ----
+    // ---- EM over the group's sites.  Lanes walk their sites at their own pace; to keep divergence cheap the warp
+    // alternates kRound predicated EM steps (lanes whose site has converged idle) with ONE finish round in which
+    // every converged lane adds its term and fetches its next site. ----
     int s = -1, t = 1;
     double a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;     // alpha, beta of the current site
     double p0 = 0, p1 = 0, p2 = 0, q0 = 0, q1 = 0, q2 = 0;     // alpha^t, beta^t
     double Sprev = 9.0, Scur = 1.0;
-    bool active = true;
+    bool active = live, done = false;
     auto next_site = [&]() {
       for (;;) {
         if (++s >= ns) { active = false; return; }
@@ -96,11 +98,22 @@ __global__ void __launch_bounds__(256) k_dist_em(EmArgs a) {
       p0 = a0; p1 = a1; p2 = a2; q0 = b0; q1 = b1; q2 = b2;
       t = 1; Sprev = 9.0; Scur = (a0 + a1 + a2) * (b0 + b1 + b2);
     };
-    next_site();
-    while (active) {
-      const double n0 = p0 * a0, n1 = p1 * a1, n2 = p2 * a2, m0 = q0 * b0, m1 = q1 * b1, m2 = q2 * b2;
-      const double Snext = (n0 + n1 + n2) * (m0 + m1 + m2);
-      if (Snext * Sprev < kExpTol * (Scur * Scur) || t >= 50) {
+    if (active) next_site();
+    while (__any_sync(0xffffffffu, active)) {
+#pragma unroll
+      for (int r = 0; r < kRound; r++) {
+        if (active && !done) {
+          const double n0 = p0 * a0, n1 = p1 * a1, n2 = p2 * a2, m0 = q0 * b0, m1 = q1 * b1, m2 = q2 * b2;
+          const double Snext = (n0 + n1 + n2) * (m0 + m1 + m2);
+          if (Snext * Sprev < kExpTol * (Scur * Scur) || t >= 50) {
+            done = true;
+          } else {
+            p0 = n0; p1 = n1; p2 = n2; q0 = m0; q1 = m1; q2 = m2;
+            Sprev = Scur; Scur = Snext; t++;
+          }
+        }
+      }
+      if (active && done) {
         // sum(score o sfs_T), sfs_T = (p (x) q) / (S_a(T) S_b(T)); row-major (g1, g2) order as ngsDist.cpp:351-353
         double d = D00 * (p0 * q0);
         d += D01 * (p0 * q1); d += D02 * (p0 * q2);
@@ -108,10 +121,8 @@ __global__ void __launch_bounds__(256) k_dist_em(EmArgs a) {
         d += D20 * (p2 * q0); d += D21 * (p2 * q1); d += D22 * (p2 * q2);
         d /= Scur;
         acc += WEIGHTED ? s_w[s] * d : d;
+        done = false;
         next_site();
-      } else {
-        p0 = n0; p1 = n1; p2 = n2; q0 = m0; q1 = m1; q2 = m2;
-        Sprev = Scur; Scur = Snext; t++;
       }
     }
   }

@@ -11,6 +11,7 @@ struct EpiArgs {
   const double *partials;     // [n_splits][n_tiles][16384] fragment order (dist_dmma.cu)
   const ngsd_tile *tiles;
   const uint32_t *cnt;        // [n_pad][n_pad] or nullptr
+  const double *cvec;         // [n_pad] 2-plane mode: weighted row sums of the B_2 plane, added for column j; or nullptr
   double *out, *num;          // [n_ind][n_ind]
   uint64_t *cntout;
   uint64_t n_ind, n_pad, const_cnt, tot_sites;
@@ -60,7 +61,7 @@ __global__ void __launch_bounds__(256) k_epilogue(EpiArgs a) {
   for (int c = 0; c < 2; c++) {
     const uint64_t j = j0 + c;
     if (i >= j || j >= a.n_ind) continue;
-    const double num = c ? s1 : s0;
+    const double num = (c ? s1 : s0) + (a.cvec ? a.cvec[j] : 0.0);
     uint64_t cnt = a.cnt ? (uint64_t) a.cnt[i * a.n_pad + j] : a.const_cnt;
     if (a.num) a.num[i * a.n_ind + j] = a.num[j * a.n_ind + i] = num;
     if (a.cntout) a.cntout[i * a.n_ind + j] = a.cntout[j * a.n_ind + i] = cnt;
@@ -95,7 +96,28 @@ __global__ void k_finish(const double *__restrict__ num, const uint64_t *__restr
   out[idx] = d;
 }
 
+// 2-plane mode: c_j = sum_s w_s * C[j][s] (C = B_2 plane); one block per individual, fixed-order tree reduction
+__global__ void __launch_bounds__(256) k_cvec(const double *__restrict__ C, uint64_t ldc, const double *__restrict__ w, uint64_t n_eff,
+                                             double *__restrict__ cvec) {
+  __shared__ double red[256];
+  const double *row = C + (uint64_t) blockIdx.x * ldc;
+  double s = 0;
+  for (uint64_t k = threadIdx.x; k < n_eff; k += 256) s += w ? w[k] * row[k] : row[k];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if ((int) threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) cvec[blockIdx.x] = red[0];
+}
+
 }  // namespace
+
+cudaError_t ngsd_launch_cvec(ngsd_ctx *ctx, bool weighted, uint64_t n_eff) {
+  k_cvec<<<(unsigned) ctx->n_pad, 256, 0, ctx->stream>>>(ctx->Cplane, ctx->ldc, weighted ? ctx->d_weights : nullptr, n_eff, ctx->d_cvec);
+  return cudaGetLastError();
+}
 
 cudaError_t ngsd_launch_finish(ngsd_ctx *ctx) {
   const uint64_t n2 = ctx->n_ind * ctx->n_ind;
@@ -109,6 +131,7 @@ cudaError_t ngsd_launch_epilogue(ngsd_ctx *ctx, const ngsd_epilogue_args &e) {
   a.partials = ctx->d_partials;
   a.tiles = ctx->d_tiles;
   a.cnt = e.use_cnt ? ctx->d_cnt : nullptr;
+  a.cvec = ctx->planes == 2 ? ctx->d_cvec : nullptr;
   a.out = ctx->d_out;
   a.num = ctx->d_num;
   a.cntout = ctx->d_cntout;

@@ -22,6 +22,7 @@ struct FrontCfg {
   int in_log;
   int call_geno;
   int pairwise_del;
+  int planes;        // 3, or 2 (sum-to-one reduction, see ngsd_internal.h)
   double N_thresh, call_thresh;
   double score[9];
 };
@@ -138,6 +139,7 @@ template <bool EXACT>
 __global__ void __launch_bounds__(512, EXACT ? 1 : 2) k_frontend(FrontCfg c, const double *__restrict__ raw, const int8_t *__restrict__ codes,
                                                       uint64_t n_ind, uint64_t site0, uint64_t n, uint64_t NC, uint64_t NW,
                                                       double *__restrict__ Apack, double *__restrict__ Bpack,
+                                                      double *__restrict__ Cplane, uint64_t ldc,
                                                       uint64_t *__restrict__ mask, int *__restrict__ err) {
   __shared__ unsigned nib[16][32];
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -188,24 +190,46 @@ __global__ void __launch_bounds__(512, EXACT ? 1 : 2) k_frontend(FrontCfg c, con
   // packed stores: 32 bytes per plane per operand; B = score . p evaluated in the reference's g2 order (ngsDist.cpp:351-353)
   const uint64_t rb = i >> 7, r = i & 127;
   const uint64_t sgrp = site0 / 4 + (uint64_t) blockIdx.y * 16 + ty;     // global 4-site group
-  const uint64_t chunk = sgrp >> 1, h = sgrp & 1;
-  const uint64_t base = (rb * NC + chunk) * NGSD_TILE_DOUBLES + (r >> 3) * 32 + (r & 7) * 4;
+  double Bv[3][4];
 #pragma unroll
-  for (int g = 0; g < 3; g++) {
-    const uint64_t o = base + (uint64_t) (g * 2 + h) * (16 * 32);
-    double2 *pa = reinterpret_cast<double2 *>(Apack + o);
-    double2 *pb = reinterpret_cast<double2 *>(Bpack + o);
-    double b[4];
+  for (int g = 0; g < 3; g++)
 #pragma unroll
     for (int q = 0; q < 4; q++) {
-      b[q] = c.score[3 * g + 0] * A[q][0];
-      b[q] += c.score[3 * g + 1] * A[q][1];
-      b[q] += c.score[3 * g + 2] * A[q][2];
+      double b = c.score[3 * g + 0] * A[q][0];
+      b += c.score[3 * g + 1] * A[q][1];
+      b += c.score[3 * g + 2] * A[q][2];
+      Bv[g][q] = b;
     }
-    pa[0] = make_double2(A[0][g], A[1][g]);
-    pa[1] = make_double2(A[2][g], A[3][g]);
-    pb[0] = make_double2(b[0], b[1]);
-    pb[1] = make_double2(b[2], b[3]);
+  if (c.planes == 3) {
+    const uint64_t chunk = sgrp >> 1, h = sgrp & 1;
+    const uint64_t base = (rb * NC + chunk) * NGSD_TILE_DOUBLES + (r >> 3) * 32 + (r & 7) * 4;
+#pragma unroll
+    for (int g = 0; g < 3; g++) {
+      const uint64_t o = base + (uint64_t) (g * 2 + h) * (16 * 32);
+      double2 *pa = reinterpret_cast<double2 *>(Apack + o);
+      double2 *pb = reinterpret_cast<double2 *>(Bpack + o);
+      pa[0] = make_double2(A[0][g], A[1][g]);
+      pa[1] = make_double2(A[2][g], A[3][g]);
+      pb[0] = make_double2(Bv[g][0], Bv[g][1]);
+      pb[1] = make_double2(Bv[g][2], Bv[g][3]);
+    }
+  } else {
+    // two planes: A = (p0, p1), B = (B0 - B2, B1 - B2), C = B2; chunk of 12 sites, k4-group = g*3 + h
+    const uint64_t chunk = sgrp / 3, h = sgrp % 3;
+    const uint64_t base = (rb * NC + chunk) * NGSD_TILE_DOUBLES + (r >> 3) * 32 + (r & 7) * 4;
+#pragma unroll
+    for (int g = 0; g < 2; g++) {
+      const uint64_t o = base + (uint64_t) (g * 3 + h) * (16 * 32);
+      double2 *pa = reinterpret_cast<double2 *>(Apack + o);
+      double2 *pb = reinterpret_cast<double2 *>(Bpack + o);
+      pa[0] = make_double2(A[0][g], A[1][g]);
+      pa[1] = make_double2(A[2][g], A[3][g]);
+      pb[0] = make_double2(Bv[g][0] - Bv[2][0], Bv[g][1] - Bv[2][1]);
+      pb[1] = make_double2(Bv[g][2] - Bv[2][2], Bv[g][3] - Bv[2][3]);
+    }
+    double2 *pc = reinterpret_cast<double2 *>(Cplane + i * ldc + sgrp * 4);
+    pc[0] = make_double2(Bv[2][0], Bv[2][1]);
+    pc[1] = make_double2(Bv[2][2], Bv[2][3]);
   }
 
   nib[ty][tx] = bits;
@@ -220,14 +244,23 @@ __global__ void __launch_bounds__(512, EXACT ? 1 : 2) k_frontend(FrontCfg c, con
 
 // Inspection: packed A planes + mask -> [ind][site][3] / [ind][site]
 __global__ void k_unpack(const double *__restrict__ Apack, const uint64_t *__restrict__ mask, uint64_t n_ind, uint64_t n_sites,
-                         uint64_t NC, uint64_t NW, double *__restrict__ P, uint8_t *__restrict__ miss) {
+                         uint64_t NC, uint64_t NW, int planes, double *__restrict__ P, uint8_t *__restrict__ miss) {
   const uint64_t idx = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_ind * n_sites) return;
   const uint64_t i = idx / n_sites, s = idx % n_sites;
-  const uint64_t rb = i >> 7, r = i & 127, chunk = s >> 3, h = (s >> 2) & 1, q = s & 3;
-  const uint64_t base = (rb * NC + chunk) * NGSD_TILE_DOUBLES + (r >> 3) * 32 + (r & 7) * 4 + q;
-  if (P)
-    for (int g = 0; g < 3; g++) P[idx * 3 + g] = Apack[base + (uint64_t) (g * 2 + h) * 512];
+  const uint64_t rb = i >> 7, r = i & 127, sgrp = s >> 2, q = s & 3;
+  if (P) {
+    if (planes == 3) {
+      const uint64_t chunk = sgrp >> 1, h = sgrp & 1;
+      const uint64_t base = (rb * NC + chunk) * NGSD_TILE_DOUBLES + (r >> 3) * 32 + (r & 7) * 4 + q;
+      for (int g = 0; g < 3; g++) P[idx * 3 + g] = Apack[base + (uint64_t) (g * 2 + h) * 512];
+    } else {
+      const uint64_t chunk = sgrp / 3, h = sgrp % 3;
+      const uint64_t base = (rb * NC + chunk) * NGSD_TILE_DOUBLES + (r >> 3) * 32 + (r & 7) * 4 + q;
+      const double p0 = Apack[base + (uint64_t) (0 * 3 + h) * 512], p1 = Apack[base + (uint64_t) (1 * 3 + h) * 512];
+      P[idx * 3 + 0] = p0; P[idx * 3 + 1] = p1; P[idx * 3 + 2] = 1.0 - p0 - p1;   // the identity the 2-plane mode relies on
+    }
+  }
   if (miss) miss[idx] = !((mask[(rb * NW + (s >> 6)) * 128 + r] >> (s & 63)) & 1);
 }
 
@@ -265,23 +298,24 @@ cudaError_t ngsd_launch_frontend(ngsd_ctx *ctx, const ngsd_frontend_args &a) {
   c.in_log = ctx->cfg.input_is_log;
   c.call_geno = ctx->cfg.call_geno;
   c.pairwise_del = ctx->cfg.pairwise_del;
+  c.planes = ctx->planes;
   c.N_thresh = ctx->cfg.N_thresh;
   c.call_thresh = ctx->cfg.call_thresh;
   for (int k = 0; k < 9; k++) c.score[k] = ctx->cfg.score[k];
   dim3 grid((unsigned) (ctx->n_pad / 32), (unsigned) ((a.n + 63) / 64)), block(32, 16);
   if (c.call_geno)
     k_frontend<true><<<grid, block, 0, ctx->stream>>>(c, a.raw, a.codes, ctx->n_ind, a.site0, a.n, ctx->NC, ctx->NW, ctx->Apack,
-                                                      ctx->Bpack, ctx->mask, ctx->d_err);
+                                                      ctx->Bpack, ctx->Cplane, ctx->ldc, ctx->mask, ctx->d_err);
   else
     k_frontend<false><<<grid, block, 0, ctx->stream>>>(c, a.raw, a.codes, ctx->n_ind, a.site0, a.n, ctx->NC, ctx->NW, ctx->Apack,
-                                                       ctx->Bpack, ctx->mask, ctx->d_err);
+                                                       ctx->Bpack, ctx->Cplane, ctx->ldc, ctx->mask, ctx->d_err);
   return cudaGetLastError();
 }
 
 cudaError_t ngsd_launch_unpack(ngsd_ctx *ctx, double *P_dev, uint8_t *miss_dev) {
   const uint64_t tot = ctx->n_ind * ctx->n_sites;
   k_unpack<<<(unsigned) ((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->Apack, ctx->mask, ctx->n_ind, ctx->n_sites, ctx->NC,
-                                                                    ctx->NW, P_dev, miss_dev);
+                                                                    ctx->NW, ctx->planes, P_dev, miss_dev);
   return cudaGetLastError();
 }
 

@@ -23,9 +23,17 @@
 //   producer stages a whole pipeline step with ONE cp.async.bulk (TMA) copy per operand.
 //   A planes hold p_g (zeroed where --pairwise_del drops the individual-site),
 //   B planes hold (score . p)_g, also zeroed there; bootstrap weights scale B fragments in registers.
+//
+// Two-plane mode (planes == 2; used when nothing masks individual-sites: indep_geno && !pairwise_del).  Posteriors sum to
+// one, so  sum_g p_g B_g = B_2 + p_0 (B_0 - B_2) + p_1 (B_1 - B_2):  the contraction needs only K = 2 per site,
+//   A planes = (p_0, p_1), B planes = (B_0 - B_2, B_1 - B_2), chunk = 12 sites (k4-group = g*3 + h, h = 0..2: the tile
+//   stays 6 k4-groups = 24 KiB), plus the plane C[ind][site] = B_2 whose (weighted) row sums c_j are added in the epilogue.
+//   One third fewer DMMAs and 8 bytes less per individual-site; exact for one-hot posteriors, ~1e-16 absolute otherwise.
 // ---------------------------------------------------------------------------------------------
 constexpr int NGSD_TILE = 128;                 // individuals per row block / CTA tile edge
-constexpr int NGSD_SC = 8;                     // sites per chunk (= one pipeline stage)
+constexpr int NGSD_SC = 8;                     // sites per chunk (= one pipeline stage), 3-plane mode
+constexpr int NGSD_SC2 = 12;                   // sites per chunk, 2-plane mode
+constexpr int NGSD_SC_MAX = 12;
 constexpr int NGSD_K4_PER_CHUNK = 6;           // 3 planes x 2 halves
 constexpr int NGSD_TILE_DOUBLES = NGSD_K4_PER_CHUNK * 16 * 32;   // 3072 doubles = 24 KiB
 constexpr int NGSD_TILE_BYTES = NGSD_TILE_DOUBLES * 8;
@@ -42,6 +50,10 @@ struct ngsd_ctx {
   cudaStream_t aux_stream = nullptr;  // K3 mask count, concurrent with K2
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   uint64_t n_ind = 0, n_pad = 0, RB = 0, n_sites = 0, NC = 0, NW = 0;
+  int planes = 3, sc = NGSD_SC;                // operand planes per site (3, or 2 with the sum-to-one reduction) / sites per chunk
+  double *Cplane = nullptr;                    // [n_pad][ldc] B_2 plane (2-plane mode)
+  uint64_t ldc = 0;
+  double *d_cvec = nullptr;                    // [n_pad] weighted row sums of Cplane for the current matrix
   double *Apack = nullptr, *Bpack = nullptr;   // [RB][NC][3072]
   uint64_t *mask = nullptr;                    // [RB][NW][128] presence bits (1 = data present)
   int *d_err = nullptr;                        // device error flags (bit0 NaN, bit1 bad genotype code)
@@ -116,4 +128,5 @@ size_t ngsd_dist_smem_bytes();
 uint32_t ngsd_em_splits(const ngsd_ctx *ctx, uint32_t n_chunks);
 cudaError_t ngsd_launch_dist_em(ngsd_ctx *ctx, uint32_t n_chunks, uint32_t n_splits, bool weighted);
 cudaError_t ngsd_launch_finish(ngsd_ctx *ctx);
+cudaError_t ngsd_launch_cvec(ngsd_ctx *ctx, bool weighted, uint64_t n_eff);
 cudaError_t ngsd_launch_epilogue_em(ngsd_ctx *ctx, uint32_t n_splits, uint64_t const_cnt, bool use_cnt);

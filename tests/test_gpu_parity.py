@@ -107,7 +107,8 @@ def test_frontend_posteriors_and_masks(call, thr):
         n_sites, n_ind, _ = r.shape
         P = oracle.frontend(r, call_geno=call, N_thresh=thr[0], call_thresh=thr[1])
         m = oracle.miss_mask(P)
-        p = nb().Params(n_ind=n_ind, n_sites=n_sites, indep_geno=True, call_geno=call, N_thresh=thr[0], call_thresh=thr[1])
+        p = nb().Params(n_ind=n_ind, n_sites=n_sites, indep_geno=True, call_geno=call, N_thresh=thr[0], call_thresh=thr[1],
+                        keep_planes=True)   # all three planes kept so that the posteriors can be read back exactly
         with nb().NgsDistB200(p) as g:
             g.push_sites(r)
             g.frontend()
@@ -145,6 +146,28 @@ def test_multi_tile_shapes_with_bootstrap(n_ind, n_sites, miss, mode):
             dg = r["num"] / np.maximum(r["cnt"], 1)
         assert_close(r["num"], o["num"], "rep %d num" % rep)
         assert_close(r["dist"], o["dist"], "rep %d dist" % rep)
+
+
+def test_two_plane_mode_matches_three_plane_mode():
+    """indep_geno && !pairwise_del uses the sum-to-one reduction (2 operand planes + c-vector); keep_planes forces the
+    plain 3-plane contraction.  Both must agree to rounding, and the read-back third plane is 1 - p0 - p1."""
+    raw = oracle.synth_raw(21, 0.1, 300, 2500)
+    res = {}
+    for keep in (False, True):
+        p = nb().Params(n_ind=300, n_sites=2500, indep_geno=True, evol_model=0, keep_planes=keep, n_boot_rep=2, boot_block_size=7, seed=5)
+        with nb().NgsDistB200(p) as g:
+            g.push_sites(raw)
+            res[keep] = g.run(want_num=True, want_cnt=True)
+            if not keep:
+                P2, _ = g.posteriors()
+    o = oracle.run_job(raw, indep=True, evol_model=0, n_boot_rep=2, boot_block_size=7, seed=5)
+    for a, b, c in zip(res[False], res[True], o):
+        assert np.array_equal(a["cnt"], b["cnt"]) and np.array_equal(a["cnt"], c["cnt"])
+        assert_close(a["num"], b["num"], "2 vs 3 planes")
+        assert_close(a["num"], c["num"], "2 planes vs oracle")
+        assert_close(a["dist"], c["dist"], "2 planes vs oracle")
+    P = oracle.frontend(raw)
+    assert np.abs(P2 - P).max() < 1e-14
 
 
 def test_called_pairwise_del_model0_is_bit_exact():
