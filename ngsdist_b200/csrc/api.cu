@@ -534,7 +534,7 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   plan.grid = (int) std::min<uint64_t>(plan.grid, plan.n_units);
   if (em_path) {
     em_splits = ngsd_em_splits(ctx, plan.n_chunks);
-    const uint64_t ld = (ctx->n_ind + 15) / 16 * 16;
+    const uint64_t ld = ngsd_em_ld(ctx);
     plan.n_units = (uint32_t) (((uint64_t) em_splits * ld * ld + NGSD_TILE_ELEMS - 1) / NGSD_TILE_ELEMS);   // workspace slots
   }
   if (splits.size() > ctx->split_cap) {

@@ -4,13 +4,27 @@
 // sum(score o sfs_T).  That is not bilinear in (p_i, p_j), so it cannot be a GEMM; it runs on the FP64
 // CUDA cores.
 //
-// Closed form used here (validated there on 6e6 pair-sites and here against the oracle): with a uniform
-// start, after t EM steps sfs_t = (a^t / S_a(t)) (x) (b^t / S_b(t)) with element-wise powers and S_x(t) = sum_g x_g^t,
-// and the reference's log-likelihood after step t is log( S(t+1) / S(t) ), S = S_a * S_b, S(0) = 9.  It stops at the
-// first T >= 1 with |log r_T - log r_{T-1}| < 0.001  <=>  S(T+1) * S(T-1) < e^0.001 * S(T)^2  (the ratio is >= 1 by
-// log-convexity of power sums), else at T = 50.  Powers are taken of a / max(a), b / max(b) so nothing underflows;
-// the table and the test are scale invariant.  One thread owns one pair and walks its sites at its own pace: every
-// loop trip is ONE EM step of the thread's current site, so lanes with different T do not wait for each other.
+// Closed form (validated there on 6e6 pair-sites and here against the oracle): with a uniform start,
+// after t EM steps sfs_t = (a^t / S_a(t)) (x) (b^t / S_b(t)) with element-wise powers and S_x(t) = sum_g x_g^t, and the
+// reference's log-likelihood after step t is log(S(t+1) / S(t)), S = S_a * S_b, S(0) = 9.  It stops at the first
+// T in 1..49 with |log r_T - log r_{T-1}| < 0.001  <=>  rho_a(T) * rho_b(T) < e^0.001, where
+//     rho_x(t) = S_x(t+1) * S_x(t-1) / S_x(t)^2   (>= 1 by log-convexity of power sums),
+// else at T = 50.  Everything that depends on ONE individual is therefore separable from the pair:
+//     rho_x(t), t = 1..49          the stopping sequence
+//     ahat_x(t) = x^t / S_x(t)      the individual's factor of sfs_t
+// and the pair-site term is  ahat_i(T)^T . score . ahat_j(T)  with T = first t whose rho product is below e^0.001.
+//
+// Kernel structure: one CTA owns a 64 x 64 tile of pairs and a range of sites.  Per site it alternates
+//   build : 128 individual-sites x 50 EM steps -> shared-memory tables (rho for rows and columns; ahat for the rows;
+//           u = score . ahat folded with the sum-to-one identity for the columns), 2 threads per individual-site;
+//   pairs : every thread finds T for its 16 pairs by bisection on the rho tables -- valid because rho_i * rho_j is
+//           non-increasing beyond t* = the last step at which either sequence still rises (recorded by the build; the
+//           steps up to t* are scanned linearly, which is rare: t* = 0 for > 96 % of Dirichlet individual-sites) --
+//           and adds  u2 + ahat0 * (u0 - u2) + ahat1 * (u1 - u2)  (3 operands per side, 2 FMA).
+// A warp works on ONE row and 32 columns at a time, so row-table reads are broadcasts / few distinct addresses and
+// column-table reads ([t][column] layout) are conflict-free whatever t each lane is at.  ~50 FP64 instructions per
+// pair-site instead of ~200 for the direct iteration, and no data-dependent trip counts in the common case.
+// Powers are taken of x / max(x) so nothing underflows; rho and ahat are scale invariant.
 #include <stdlib.h>
 
 #include <algorithm>
@@ -19,115 +33,231 @@
 
 namespace {
 
-constexpr int kGroupChunks = 4;                 // chunks (of 8 sites) staged per shared-memory group
-constexpr int kGroupSites = kGroupChunks * NGSD_SC;
-constexpr int kRound = 4;                       // EM steps between two finish rounds
+constexpr int kEdge = 64;                       // pairs tile: 64 rows x 64 columns
+constexpr int kIter = 50;                       // maxIter of em2 (ngsDist.cpp:349)
+constexpr int kThreads = 512;                   // 16 warps: the kernel is bound by FP64 / shared-memory latency
+constexpr int kRowLd = 51;                      // row-table stride (odd: conflict-free build stores)
 constexpr double kExpTol = 1.0010005001667084;  // e^0.001 (tole of ngsDist.cpp:349)
+constexpr double kRise = 1e-13;                 // a rho step counts as "rising" above rounding noise only
+
+// shared-memory layout (in doubles)
+constexpr int kRhoRow = 0;                              // [64][51]     rho_row[r * 51 + t]        t = 1..49 (slot 50: scratch)
+constexpr int kRhoCol = kRhoRow + kEdge * kRowLd;       // [50][64]     rho_col[t * 64 + c]        t = 1..49
+constexpr int kAhat = kRhoCol + kIter * kEdge;          // [2][64][51]  ahat_g of row r at step t: [(g * 64 + r) * 51 + t - 1]
+constexpr int kU = kAhat + 2 * kEdge * kRowLd;          // [50][3][64]  (u2, u0 - u2, u1 - u2) of column c: [((t - 1) * 3 + k) * 64 + c]
+constexpr int kRaw = kU + kIter * 3 * kEdge;            // [2][6][256]  staged posteriors of one 8-site chunk (rows, columns)
+constexpr int kWgt = kRaw + 2 * 6 * 256;                // [8]          bootstrap weights of the chunk
+constexpr int kDoubles = kWgt + 8;
+constexpr size_t kSmemBytes = (size_t) kDoubles * 8 + 3 * 128 * sizeof(int);   // + tstar[2][128] (alternating) + valid[128]
 
 struct EmArgs {
-  const double *Apack;          // packed posterior planes (A operand of dist_dmma)
+  const double *Apack;          // packed posterior planes (A operand of dist_dmma, 3-plane layout)
   const double *weights;        // [NC*8] per-site bootstrap weights or nullptr
   const uint32_t *chunk_ids;    // active chunk list or nullptr (identity)
-  double *partials;             // [n_splits][n16*16][n16*16]
-  uint64_t NC;
-  uint32_t n_chunks, n_splits, n16;
-  double score[9];
+  double *partials;             // [n_splits][ld][ld]
+  uint64_t NC, n_sites, ld;
+  uint32_t n_chunks, n_splits, n64, n_tiles;
+  double E[9];                  // rows: score[2][:], score[0][:] - score[2][:], score[1][:] - score[2][:]
 };
 
-// grid (n16 [tj], n16 [ti], n_splits); block 256 = 16 x 16 pairs
-template <bool WEIGHTED>
-__global__ void __launch_bounds__(256) k_dist_em(EmArgs a) {
-  const uint32_t tj = blockIdx.x, ti = blockIdx.y;
-  if (tj < ti) return;
-  __shared__ double s_row[16 * 3 * kGroupSites];     // [(r*3+g)*64 + s]   alpha = a / max(a); 0 marks "skip"
-  __shared__ double s_col[kGroupSites * 3 * 16];     // [(s*3+g)*16 + c]   beta
-  __shared__ double s_w[kGroupSites];
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const uint64_t i = (uint64_t) ti * 16 + ty, j = (uint64_t) tj * 16 + tx;
-  const bool live = i < j;                             // upper triangle only
-  const uint32_t c0 = (uint32_t) (((uint64_t) blockIdx.z * a.n_chunks) / a.n_splits);
-  const uint32_t c1 = (uint32_t) (((uint64_t) (blockIdx.z + 1) * a.n_chunks) / a.n_splits);
-  const double D00 = a.score[0], D01 = a.score[1], D02 = a.score[2], D10 = a.score[3], D11 = a.score[4], D12 = a.score[5],
-               D20 = a.score[6], D21 = a.score[7], D22 = a.score[8];
-  double acc = 0.0;
+// 1 / s for s in [1, 3]: MUFU.RCP64H seed (>= 20 bits) + two Newton steps (error ~1 ulp); no slow path needed.
+__device__ __forceinline__ double fast_rcp(double s) {
+  double x;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(s));
+  double e = fma(-s, x, 1.0);
+  x = fma(x, e, x);
+  e = fma(-s, x, 1.0);
+  return fma(x, e, x);
+}
 
-  for (uint32_t cg = c0; cg < c1; cg += kGroupChunks) {
-    const int nch = (int) min((uint32_t) kGroupChunks, c1 - cg);
-    const int ns = nch * NGSD_SC;
-    __syncthreads();
-    // ---- stage + normalise: 32 individuals (16 rows, 16 cols) x ns sites; thread -> (ind, site) ----
-    for (int e = tid; e < 32 * kGroupSites; e += 256) {
-      const int s = e % kGroupSites, ind = e / kGroupSites;         // ind 0..15 rows, 16..31 cols
-      double v0 = 0, v1 = 0, v2 = 0;
-      if (s < ns) {
-        const uint64_t chunk = a.chunk_ids ? a.chunk_ids[cg + (s >> 3)] : (uint64_t) (cg + (s >> 3));
-        const uint64_t gi = (ind < 16) ? (uint64_t) ti * 16 + ind : (uint64_t) tj * 16 + (ind - 16);
-        const uint64_t rb = gi >> 7, r = gi & 127;
-        const int q = s & 7;
-        const double *src = a.Apack + (rb * a.NC + chunk) * NGSD_TILE_DOUBLES + (uint64_t) ((q >> 2) * 16 + (r >> 3)) * 32 + (r & 7) * 4 + (q & 3);
-        v0 = src[0]; v1 = src[2 * 512]; v2 = src[4 * 512];          // planes g = 0,1,2 -> k4-group g*2 + h
-        const double m = fmax(v0, fmax(v1, v2));
-        if (m > 0) { v0 /= m; v1 /= m; v2 /= m; } else { v0 = v1 = v2 = 0; }   // all-zero = padded or pairwise-deleted
-        if (WEIGHTED && ind == 0) s_w[s] = a.weights[chunk * NGSD_SC + q];
-      }
-      if (ind < 16) {
-        s_row[(ind * 3 + 0) * kGroupSites + s] = v0; s_row[(ind * 3 + 1) * kGroupSites + s] = v1; s_row[(ind * 3 + 2) * kGroupSites + s] = v2;
-      } else {
-        const int c = ind - 16;
-        s_col[(s * 3 + 0) * 16 + c] = v0; s_col[(s * 3 + 1) * 16 + c] = v1; s_col[(s * 3 + 2) * 16 + c] = v2;
-      }
-    }
-    __syncthreads();
+struct Pow3 { double v0, v1, v2; };
+__device__ __forceinline__ Pow3 mul3(const Pow3 &a, const Pow3 &b) { return {a.v0 * b.v0, a.v1 * b.v1, a.v2 * b.v2}; }
+__device__ __forceinline__ double sum3(const Pow3 &a) { return (a.v0 + a.v1) + a.v2; }
 
-    // ---- EM over the group's sites.  Lanes walk their sites at their own pace; to keep divergence cheap the warp
-    // alternates kRound predicated EM steps (lanes whose site has converged idle) with ONE finish round in which
-    // every converged lane adds its term and fetches its next site. ----
-    int s = -1, t = 1;
-    double a0 = 0, a1 = 0, a2 = 0, b0 = 0, b1 = 0, b2 = 0;     // alpha, beta of the current site
-    double p0 = 0, p1 = 0, p2 = 0, q0 = 0, q1 = 0, q2 = 0;     // alpha^t, beta^t
-    double Sprev = 9.0, Scur = 1.0;
-    bool active = live, done = false;
-    auto next_site = [&]() {
-      for (;;) {
-        if (++s >= ns) { active = false; return; }
-        a0 = s_row[(ty * 3 + 0) * kGroupSites + s]; a1 = s_row[(ty * 3 + 1) * kGroupSites + s]; a2 = s_row[(ty * 3 + 2) * kGroupSites + s];
-        b0 = s_col[(s * 3 + 0) * 16 + tx]; b1 = s_col[(s * 3 + 1) * 16 + tx]; b2 = s_col[(s * 3 + 2) * 16 + tx];
-        const bool valid = (a0 + a1 + a2 > 0) && (b0 + b1 + b2 > 0) && (!WEIGHTED || s_w[s] != 0.0);
-        if (valid) break;
-      }
-      p0 = a0; p1 = a1; p2 = a2; q0 = b0; q1 = b1; q2 = b2;
-      t = 1; Sprev = 9.0; Scur = (a0 + a1 + a2) * (b0 + b1 + b2);
-    };
-    if (active) next_site();
-    while (__any_sync(0xffffffffu, active)) {
+// EM steps T0 .. T0+N-1 of one individual-site (SIDE 0 = row of the tile, 1 = column).  Everything indexed by t is a
+// compile-time constant, so the table stores are base + immediate.
+template <int SIDE, int T0, int N>
+__device__ __forceinline__ int build_steps(const Pow3 &x, double *rho_t, double *tab, const double (&E)[9]) {
+  // state at step t: p = x^t, Sc = S(t), Sp = S(t-1), rp = rho(t-1)
+  Pow3 p;
+  double Sp, Sc, rp;
+  if (T0 == 1) {
+    p = x; Sp = 3.0; Sc = sum3(x); rp = INFINITY;
+  } else {
+    // x^(T0-2) by square-and-multiply (T0 - 2 = 12, 25, 37), then two more steps
+    const Pow3 x2 = mul3(x, x), x4 = mul3(x2, x2), x8 = mul3(x4, x4);
+    Pow3 b;
+    if (T0 - 2 == 12) b = mul3(x8, x4);
+    else if (T0 - 2 == 25) { const Pow3 x16 = mul3(x8, x8); b = mul3(mul3(x16, x8), x); }
+    else { const Pow3 x16 = mul3(x8, x8), x32 = mul3(x16, x16); b = mul3(mul3(x32, x4), x); }
+    const double Sm2 = sum3(b);
+    const Pow3 pm1 = mul3(b, x);
+    Sp = sum3(pm1);
+    p = mul3(pm1, x);
+    Sc = sum3(p);
+    const double ip = fast_rcp(Sp);
+    rp = ((Sc * Sm2) * ip) * ip;                                      // rho(T0 - 1)
+  }
+  int tstar = 0;
 #pragma unroll
-      for (int r = 0; r < kRound; r++) {
-        if (active && !done) {
-          const double n0 = p0 * a0, n1 = p1 * a1, n2 = p2 * a2, m0 = q0 * b0, m1 = q1 * b1, m2 = q2 * b2;
-          const double Snext = (n0 + n1 + n2) * (m0 + m1 + m2);
-          if (Snext * Sprev < kExpTol * (Scur * Scur) || t >= 50) {
-            done = true;
+  for (int k = 0; k < N; k++) {
+    const int t = T0 + k;
+    const Pow3 n = mul3(p, x);
+    const double Sn = sum3(n);
+    const double inv = fast_rcp(Sc);
+    const double rho = ((Sn * Sp) * inv) * inv;
+    if (t < kIter) {
+      if (rho - rp > kRise) tstar = t;
+      rho_t[SIDE == 0 ? t : t * kEdge] = rho;
+    }
+    if (SIDE == 0) {
+      tab[t - 1] = p.v0 * inv;
+      tab[kEdge * kRowLd + t - 1] = p.v1 * inv;
+    } else {
+      tab[((t - 1) * 3 + 0) * kEdge] = (E[0] * p.v0 + E[1] * p.v1 + E[2] * p.v2) * inv;
+      tab[((t - 1) * 3 + 1) * kEdge] = (E[3] * p.v0 + E[4] * p.v1 + E[5] * p.v2) * inv;
+      tab[((t - 1) * 3 + 2) * kEdge] = (E[6] * p.v0 + E[7] * p.v1 + E[8] * p.v2) * inv;
+    }
+    p = n; Sp = Sc; Sc = Sn; rp = rho;
+  }
+  return tstar;
+}
+
+// grid = n_splits * n_tiles (split-major); block 512
+template <bool WEIGHTED>
+__global__ void __launch_bounds__(kThreads, 1) k_dist_em(EmArgs a) {
+  extern __shared__ __align__(16) double sm[];
+  double *rho_row = sm + kRhoRow, *rho_col = sm + kRhoCol, *ahat = sm + kAhat, *ucol = sm + kU, *raw = sm + kRaw, *wgt = sm + kWgt;
+  int *tsb = reinterpret_cast<int *>(sm + kDoubles), *valid = tsb + 256;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t q = blockIdx.x / a.n_tiles;
+  uint32_t t_lin = blockIdx.x - q * a.n_tiles, ti = 0;
+  while (t_lin >= a.n64 - ti) { t_lin -= a.n64 - ti; ti++; }
+  const uint32_t tj = ti + t_lin;
+  const bool diag = ti == tj;
+  const uint32_t c0 = (uint32_t) (((uint64_t) q * a.n_chunks) / a.n_splits);
+  const uint32_t c1 = (uint32_t) (((uint64_t) (q + 1) * a.n_chunks) / a.n_splits);
+
+  // build role: warp -> (quarter of the EM steps, side, 32 individuals); rotated so that every SM sub-partition
+  // (warp & 3) gets row and column warps alike (column warps do more arithmetic).
+  const int b_qtr = warp >> 2, b_role = ((warp & 3) + b_qtr) & 3, b_side = b_role >> 1, b_k = (b_role & 1) * 32 + lane;
+  double E[9];
+#pragma unroll
+  for (int k = 0; k < 9; k++) E[k] = a.E[k];
+
+  double acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; k++) acc[k] = 0.0;
+  if (tid < 256) tsb[tid] = 0;
+  int par = 0;                                               // which tstar array the current site uses
+
+  for (uint32_t c = c0; c < c1; c++) {
+    const uint64_t chunk = a.chunk_ids ? a.chunk_ids[c] : (uint64_t) c;
+    __syncthreads();                                          // everyone is done with the previous chunk's weights
+    // ---- stage the chunk: 2 sides x 6 k4-groups x (64 individuals x 4 sites) = 12 contiguous 2 KiB segments ----
+#pragma unroll
+    for (int h = 0; h < 6; h++) {
+      const int seg = h * 2 + (tid >> 8);
+      const uint64_t gi0 = (uint64_t) (seg < 6 ? ti : tj) * kEdge;
+      const double *src = a.Apack + ((gi0 >> 7) * a.NC + chunk) * NGSD_TILE_DOUBLES + (seg % 6) * 512 + ((gi0 & 127) >> 3) * 32;
+      raw[seg * 256 + (tid & 255)] = src[tid & 255];
+    }
+    if (WEIGHTED && tid < NGSD_SC) wgt[tid] = a.weights[chunk * NGSD_SC + tid];
+    __syncthreads();
+
+    for (int s8 = 0; s8 < NGSD_SC; s8++) {
+      if (chunk * NGSD_SC + s8 >= a.n_sites) break;          // padding sites of the last chunk (CTA-uniform)
+      const double w = WEIGHTED ? wgt[s8] : 1.0;
+      if (WEIGHTED && w == 0.0) continue;                     // block not drawn in this replicate (CTA-uniform)
+      int *ts = tsb + par * 128;
+
+      // ================= build: tables of this site's 128 individual-sites =================
+      {
+        const double *rw = raw + (b_side * 6 + (s8 >> 2)) * 256 + b_k * 4 + (s8 & 3);
+        Pow3 x = {rw[0], rw[2 * 256], rw[4 * 256]};                        // planes g = 0,1,2 -> k4-group g*2 + h
+        const double m = fmax(x.v0, fmax(x.v1, x.v2));
+        const bool ok = m > 0;                                             // all-zero = padded or pairwise-deleted
+        if (ok) {
+          x.v0 /= m; x.v1 /= m; x.v2 /= m;                                 // true divisions: the largest becomes exactly 1
+          int tstar;
+          if (b_side == 0) {
+            double *rt = rho_row + b_k * kRowLd, *tab = ahat + b_k * kRowLd;
+            if (b_qtr == 0) tstar = build_steps<0, 1, 13>(x, rt, tab, E);
+            else if (b_qtr == 1) tstar = build_steps<0, 14, 13>(x, rt, tab, E);
+            else if (b_qtr == 2) tstar = build_steps<0, 27, 12>(x, rt, tab, E);
+            else tstar = build_steps<0, 39, 12>(x, rt, tab, E);
           } else {
-            p0 = n0; p1 = n1; p2 = n2; q0 = m0; q1 = m1; q2 = m2;
-            Sprev = Scur; Scur = Snext; t++;
+            double *rt = rho_col + b_k, *tab = ucol + b_k;
+            if (b_qtr == 0) tstar = build_steps<1, 1, 13>(x, rt, tab, E);
+            else if (b_qtr == 1) tstar = build_steps<1, 14, 13>(x, rt, tab, E);
+            else if (b_qtr == 2) tstar = build_steps<1, 27, 12>(x, rt, tab, E);
+            else tstar = build_steps<1, 39, 12>(x, rt, tab, E);
+          }
+          if (tstar) atomicMax(&ts[b_side * 64 + b_k], tstar);
+        }
+        if (b_qtr == 0) valid[b_side * 64 + b_k] = ok ? 1 : 0;
+      }
+      __syncthreads();
+
+      // ================= pairs: T by bisection, then the 2-FMA term =================
+      if (tid < 128) tsb[(par ^ 1) * 128 + tid] = 0;         // the next site's tstar accumulators
+      int tcol[2];
+      bool vcol[2];
+#pragma unroll
+      for (int h = 0; h < 2; h++) { tcol[h] = ts[64 + h * 32 + lane]; vcol[h] = valid[64 + h * 32 + lane] != 0; }
+#pragma unroll
+      for (int k2 = 0; k2 < 2; k2++) {
+        int pos[4], tfix[4];
+        bool ok[4];
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int r = warp + 16 * (k2 * 2 + (e >> 1)), cc = (e & 1) * 32 + lane;
+          ok[e] = (!diag || cc > r) && vcol[e & 1] && valid[r] != 0;
+          const int tm = max(ts[r], tcol[e & 1]);
+          pos[e] = ok[e] ? tm + 1 : kIter;
+          tfix[e] = 0;
+          if (ok[e] && tm > 0) {                        // rare: scan the non-monotone prefix 1..tm
+            for (int t = 1; t <= tm; t++)
+              if (rho_row[r * kRowLd + t] * rho_col[t * kEdge + cc] < kExpTol) { tfix[e] = t; pos[e] = kIter; break; }
           }
         }
+        // first t in [pos, 49] whose rho product is below e^0.001, else 50 (branch-free; all t < pos are known to be above)
+#pragma unroll
+        for (int s = 32; s >= 1; s >>= 1) {
+#pragma unroll
+          for (int e = 0; e < 4; e++) {
+            const int r = warp + 16 * (k2 * 2 + (e >> 1)), cc = (e & 1) * 32 + lane;
+            const int idx = pos[e] + s - 1, idc = min(idx, kIter);
+            const double pr = rho_row[r * kRowLd + idc] * rho_col[idc * kEdge + cc];
+            const bool adv = (idx < kIter) && !(pr < kExpTol);
+            pos[e] = adv ? pos[e] + s : pos[e];
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const int r = warp + 16 * (k2 * 2 + (e >> 1)), cc = (e & 1) * 32 + lane;
+          const int T1 = (tfix[e] ? tfix[e] : pos[e]) - 1;
+          const double a0 = ahat[r * kRowLd + T1], a1 = ahat[(kEdge + r) * kRowLd + T1];
+          const double *u = ucol + (T1 * 3) * kEdge + cc;
+          double d = fma(a1, u[2 * kEdge], fma(a0, u[kEdge], u[0]));
+          if (WEIGHTED) d *= w;
+          if (ok[e]) acc[k2 * 4 + e] += d;
+        }
       }
-      if (active && done) {
-        // sum(score o sfs_T), sfs_T = (p (x) q) / (S_a(T) S_b(T)); row-major (g1, g2) order as ngsDist.cpp:351-353
-        double d = D00 * (p0 * q0);
-        d += D01 * (p0 * q1); d += D02 * (p0 * q2);
-        d += D10 * (p1 * q0); d += D11 * (p1 * q1); d += D12 * (p1 * q2);
-        d += D20 * (p2 * q0); d += D21 * (p2 * q1); d += D22 * (p2 * q2);
-        d /= Scur;
-        acc += WEIGHTED ? s_w[s] * d : d;
-        done = false;
-        next_site();
-      }
+      par ^= 1;
+      __syncthreads();
     }
   }
-  const uint64_t ld = (uint64_t) a.n16 * 16;
-  a.partials[((uint64_t) blockIdx.z * ld + i) * ld + j] = live ? acc : 0.0;
+
+#pragma unroll
+  for (int k2 = 0; k2 < 2; k2++)
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+      const int r = warp + 16 * (k2 * 2 + (e >> 1)), cc = (e & 1) * 32 + lane;
+      const uint64_t i = (uint64_t) ti * kEdge + r, j = (uint64_t) tj * kEdge + cc;
+      a.partials[((uint64_t) q * a.ld + i) * a.ld + j] = (i < j) ? acc[k2 * 4 + e] : 0.0;
+    }
 }
 
 struct EmEpiArgs {
@@ -163,33 +293,55 @@ __global__ void __launch_bounds__(256) k_epilogue_em(EmEpiArgs a) {
   a.out[i * a.n_ind + j] = a.out[j * a.n_ind + i] = d;
 }
 
+uint64_t em_n64(const ngsd_ctx *ctx) { return (ctx->n_ind + kEdge - 1) / kEdge; }
+
 }  // namespace
 
+uint64_t ngsd_em_ld(const ngsd_ctx *ctx) { return em_n64(ctx) * kEdge; }
+
 uint32_t ngsd_em_splits(const ngsd_ctx *ctx, uint32_t n_chunks) {
-  const uint64_t n16 = (ctx->n_ind + 15) / 16, tiles = n16 * (n16 + 1) / 2;
-  uint64_t want = ((uint64_t) 24 * ctx->n_sm + tiles - 1) / tiles;            // >= ~3 waves of 8 CTAs per SM
-  const uint64_t maxs = std::max<uint64_t>(1, n_chunks / kGroupChunks);
-  const uint64_t cap_mem = std::max<uint64_t>(1, ((uint64_t) 2 << 30) / (n16 * 16 * n16 * 16 * 8));
+  const uint64_t n64 = em_n64(ctx), tiles = n64 * (n64 + 1) / 2, ld = n64 * kEdge;
+  uint64_t want = ((uint64_t) 8 * ctx->n_sm + tiles - 1) / tiles;             // ~8 units per SM: short tail, 1 CTA per SM
+  const uint64_t maxs = std::max<uint64_t>(1, n_chunks / 2);
+  const uint64_t cap_mem = std::max<uint64_t>(1, ((uint64_t) 2 << 30) / (ld * ld * 8));
   want = std::max<uint64_t>(1, std::min(std::min(want, maxs), cap_mem));
   return (uint32_t) std::min<uint64_t>(want, 65535);
 }
 
 cudaError_t ngsd_launch_dist_em(ngsd_ctx *ctx, uint32_t n_chunks, uint32_t n_splits, bool weighted) {
+  static bool attr_set[64] = {};
+  if (!attr_set[ctx->device & 63]) {
+    const void *fns[2] = {(const void *) k_dist_em<false>, (const void *) k_dist_em<true>};
+    for (const void *f : fns) {
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBytes);
+      if (e != cudaSuccess) return e;
+    }
+    attr_set[ctx->device & 63] = true;
+  }
   EmArgs a;
   a.Apack = ctx->Apack;
   a.weights = weighted ? ctx->d_weights : nullptr;
   a.chunk_ids = weighted ? ctx->d_chunk_ids : nullptr;
   a.partials = ctx->d_partials;
   a.NC = ctx->NC;
+  a.n_sites = ctx->n_sites;
   a.n_chunks = n_chunks;
   a.n_splits = n_splits;
-  a.n16 = (uint32_t) ((ctx->n_ind + 15) / 16);
-  for (int k = 0; k < 9; k++) a.score[k] = ctx->cfg.score[k];
-  dim3 grid(a.n16, a.n16, n_splits);
+  a.n64 = (uint32_t) em_n64(ctx);
+  a.n_tiles = a.n64 * (a.n64 + 1) / 2;
+  a.ld = (uint64_t) a.n64 * kEdge;
+  const double *D = ctx->cfg.score;
+  for (int k = 0; k < 3; k++) {
+    a.E[0 + k] = D[6 + k];
+    a.E[3 + k] = D[0 + k] - D[6 + k];
+    a.E[6 + k] = D[3 + k] - D[6 + k];
+  }
+  const uint64_t grid = (uint64_t) n_splits * a.n_tiles;
+  if (grid == 0 || grid > 0x7fffffffull) return cudaErrorInvalidConfiguration;
   if (weighted)
-    k_dist_em<true><<<grid, 256, 0, ctx->stream>>>(a);
+    k_dist_em<true><<<(unsigned) grid, kThreads, kSmemBytes, ctx->stream>>>(a);
   else
-    k_dist_em<false><<<grid, 256, 0, ctx->stream>>>(a);
+    k_dist_em<false><<<(unsigned) grid, kThreads, kSmemBytes, ctx->stream>>>(a);
   return cudaGetLastError();
 }
 
@@ -202,12 +354,12 @@ cudaError_t ngsd_launch_epilogue_em(ngsd_ctx *ctx, uint32_t n_splits, uint64_t c
   a.cntout = ctx->d_cntout;
   a.n_ind = ctx->n_ind;
   a.n_pad = ctx->n_pad;
-  const uint32_t n16 = (uint32_t) ((ctx->n_ind + 15) / 16);
-  a.ld = (uint64_t) n16 * 16;
+  a.ld = ngsd_em_ld(ctx);
   a.const_cnt = const_cnt;
   a.tot_sites = ctx->cfg.tot_sites;
   a.n_splits = n_splits;
   a.evol_model = ctx->cfg.evol_model;
+  const uint32_t n16 = (uint32_t) ((ctx->n_ind + 15) / 16);
   k_epilogue_em<<<dim3(n16, n16), 256, 0, ctx->stream>>>(a);
   return cudaGetLastError();
 }

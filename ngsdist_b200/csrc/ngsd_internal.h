@@ -126,6 +126,7 @@ cudaError_t ngsd_launch_epilogue(ngsd_ctx *ctx, const ngsd_epilogue_args &a);
 size_t ngsd_dist_smem_bytes();
 // K2b: per pair-site EM path (indep_geno == 0)
 uint32_t ngsd_em_splits(const ngsd_ctx *ctx, uint32_t n_chunks);
+uint64_t ngsd_em_ld(const ngsd_ctx *ctx);     // leading dimension of the EM partials (64-row tiles)
 cudaError_t ngsd_launch_dist_em(ngsd_ctx *ctx, uint32_t n_chunks, uint32_t n_splits, bool weighted);
 cudaError_t ngsd_launch_finish(ngsd_ctx *ctx);
 cudaError_t ngsd_launch_cvec(ngsd_ctx *ctx, bool weighted, uint64_t n_eff);
