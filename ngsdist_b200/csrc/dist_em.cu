@@ -40,12 +40,13 @@ constexpr int kRowLd = 51;                      // row-table stride (odd: confli
 constexpr double kExpTol = 1.0010005001667084;  // e^0.001 (tole of ngsDist.cpp:349)
 constexpr double kRise = 1e-13;                 // a rho step counts as "rising" above rounding noise only
 
-// shared-memory layout (in doubles)
-constexpr int kRhoRow = 0;                              // [64][51]     rho_row[r * 51 + t]        t = 1..49 (slot 50: scratch)
-constexpr int kRhoCol = kRhoRow + kEdge * kRowLd;       // [50][64]     rho_col[t * 64 + c]        t = 1..49
-constexpr int kAhat = kRhoCol + kIter * kEdge;          // [2][64][51]  ahat_g of row r at step t: [(g * 64 + r) * 51 + t - 1]
-constexpr int kU = kAhat + 2 * kEdge * kRowLd;          // [50][3][64]  (u2, u0 - u2, u1 - u2) of column c: [((t - 1) * 3 + k) * 64 + c]
-constexpr int kRaw = kU + kIter * 3 * kEdge;            // [2][6][256]  staged posteriors of one 8-site chunk (rows, columns)
+// shared-memory layout (in doubles).  The bisection may probe up to index pos + 31 <= 81 of a rho table before the
+// result is masked; those reads stay inside this block (rho_row is followed by rho_col, rho_col by the factor tables).
+constexpr int kRhoRow = 0;                              // [64][51]     rho of row r at step t:    [r * 51 + t]          t = 1..49
+constexpr int kRhoCol = kRhoRow + kEdge * kRowLd;       // [50][64]     rho of column c at step t: [t * 64 + c]          t = 1..49
+constexpr int kFacRow = kRhoCol + kIter * kEdge;        // [2][64][51]  ahat_g of row r at step t: [(g * 64 + r) * 51 + t - 1]
+constexpr int kFacCol = kFacRow + 2 * kEdge * kRowLd;   // [50][2][64]  ahat_g of column c:        [((t - 1) * 2 + g) * 64 + c]
+constexpr int kRaw = kFacCol + kIter * 2 * kEdge;       // [2][6][256]  staged posteriors of one 8-site chunk (rows, columns)
 constexpr int kWgt = kRaw + 2 * 6 * 256;                // [8]          bootstrap weights of the chunk
 constexpr int kDoubles = kWgt + 8;
 constexpr size_t kSmemBytes = (size_t) kDoubles * 8 + 3 * 128 * sizeof(int);   // + tstar[2][128] (alternating) + valid[128]
@@ -57,10 +58,10 @@ struct EmArgs {
   double *partials;             // [n_splits][ld][ld]
   uint64_t NC, n_sites, ld;
   uint32_t n_chunks, n_splits, n64, n_tiles;
-  double E[9];                  // rows: score[2][:], score[0][:] - score[2][:], score[1][:] - score[2][:]
+  double K[9];                  // score folded with a2 = 1 - a0 - a1, b2 = 1 - b0 - b1 (see pair_term)
 };
 
-// 1 / s for s in [1, 3]: MUFU.RCP64H seed (>= 20 bits) + two Newton steps (error ~1 ulp); no slow path needed.
+// 1 / s: MUFU.RCP64H seed (>= 20 bits) + two Newton steps (error ~1 ulp); s is a normal number in [1/3, 3] here.
 __device__ __forceinline__ double fast_rcp(double s) {
   double x;
   asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(s));
@@ -74,60 +75,133 @@ struct Pow3 { double v0, v1, v2; };
 __device__ __forceinline__ Pow3 mul3(const Pow3 &a, const Pow3 &b) { return {a.v0 * b.v0, a.v1 * b.v1, a.v2 * b.v2}; }
 __device__ __forceinline__ double sum3(const Pow3 &a) { return (a.v0 + a.v1) + a.v2; }
 
-// EM steps T0 .. T0+N-1 of one individual-site (SIDE 0 = row of the tile, 1 = column).  Everything indexed by t is a
-// compile-time constant, so the table stores are base + immediate.
-template <int SIDE, int T0, int N>
-__device__ __forceinline__ int build_steps(const Pow3 &x, double *rho_t, double *tab, const double (&E)[9]) {
+// sum_{g1,g2} score[g1][g2] a_g1 b_g2 with a2 = 1 - a0 - a1 and b2 = 1 - b0 - b1 (both triples sum to one):
+//   K0 + b0 K3 + b1 K4 + a0 (K1 + b0 K5 + b1 K6) + a1 (K2 + b0 K7 + b1 K8)          8 FMA
+__device__ __forceinline__ double pair_term(const double (&K)[9], double a0, double a1, double b0, double b1) {
+  const double r0 = fma(b1, K[6], fma(b0, K[5], K[1]));
+  const double r1 = fma(b1, K[8], fma(b0, K[7], K[2]));
+  const double r2 = fma(b1, K[4], fma(b0, K[3], K[0]));
+  return fma(a0, r0, fma(a1, r1, r2));
+}
+
+// EM steps of one quarter (qtr: t = 1..13, 14..26, 27..38, 39..50) of one individual-site.  SIDE 0 = row of the tile
+// (tables indexed [individual][t]), 1 = column ([t][individual]).  A rolled two-step loop keeps the kernel inside the
+// instruction cache (a fully unrolled, per-quarter specialised build thrashed it) without register moves.
+template <int SIDE>
+__device__ __forceinline__ int build_steps(const Pow3 &x, int qtr, double *rho_t, double *fac) {
+  constexpr int RS = SIDE == 0 ? 1 : kEdge;               // rho stride per step
+  constexpr int FS = SIDE == 0 ? 1 : 2 * kEdge;           // factor stride per step
+  constexpr int FG = SIDE == 0 ? kEdge * kRowLd : kEdge;  // factor stride per genotype
   // state at step t: p = x^t, Sc = S(t), Sp = S(t-1), rp = rho(t-1)
   Pow3 p;
   double Sp, Sc, rp;
-  if (T0 == 1) {
-    p = x; Sp = 3.0; Sc = sum3(x); rp = INFINITY;
+  int t, n_rho;                                   // first step, number of steps that store rho (t <= 49)
+  if (qtr == 0) {
+    p = x; Sp = 3.0; Sc = sum3(x); rp = INFINITY; t = 1; n_rho = 13;
   } else {
-    // x^(T0-2) by square-and-multiply (T0 - 2 = 12, 25, 37), then two more steps
-    const Pow3 x2 = mul3(x, x), x4 = mul3(x2, x2), x8 = mul3(x4, x4);
+    // x^(t0-2) by square-and-multiply (t0 - 2 = 12 = 8+4, 25 = 16+8+1, 37 = 32+4+1), then two more steps
+    const Pow3 x2 = mul3(x, x), x4 = mul3(x2, x2), x8 = mul3(x4, x4), x16 = mul3(x8, x8);
     Pow3 b;
-    if (T0 - 2 == 12) b = mul3(x8, x4);
-    else if (T0 - 2 == 25) { const Pow3 x16 = mul3(x8, x8); b = mul3(mul3(x16, x8), x); }
-    else { const Pow3 x16 = mul3(x8, x8), x32 = mul3(x16, x16); b = mul3(mul3(x32, x4), x); }
+    if (qtr == 1) { b = mul3(x8, x4); t = 14; n_rho = 13; }
+    else if (qtr == 2) { b = mul3(mul3(x16, x8), x); t = 27; n_rho = 12; }
+    else { b = mul3(mul3(mul3(x16, x16), x4), x); t = 39; n_rho = 11; }
     const double Sm2 = sum3(b);
     const Pow3 pm1 = mul3(b, x);
     Sp = sum3(pm1);
     p = mul3(pm1, x);
     Sc = sum3(p);
     const double ip = fast_rcp(Sp);
-    rp = ((Sc * Sm2) * ip) * ip;                                      // rho(T0 - 1)
+    rp = ((Sc * Sm2) * ip) * ip;                                      // rho(t0 - 1)
   }
   int tstar = 0;
-#pragma unroll
-  for (int k = 0; k < N; k++) {
-    const int t = T0 + k;
-    const Pow3 n = mul3(p, x);
-    const double Sn = sum3(n);
-    const double inv = fast_rcp(Sc);
-    const double rho = ((Sn * Sp) * inv) * inv;
-    if (t < kIter) {
-      if (rho - rp > kRise) tstar = t;
-      rho_t[SIDE == 0 ? t : t * kEdge] = rho;
-    }
-    if (SIDE == 0) {
-      tab[t - 1] = p.v0 * inv;
-      tab[kEdge * kRowLd + t - 1] = p.v1 * inv;
-    } else {
-      tab[((t - 1) * 3 + 0) * kEdge] = (E[0] * p.v0 + E[1] * p.v1 + E[2] * p.v2) * inv;
-      tab[((t - 1) * 3 + 1) * kEdge] = (E[3] * p.v0 + E[4] * p.v1 + E[5] * p.v2) * inv;
-      tab[((t - 1) * 3 + 2) * kEdge] = (E[6] * p.v0 + E[7] * p.v1 + E[8] * p.v2) * inv;
-    }
+  rho_t += t * RS;
+  fac += (t - 1) * FS;
+  // one EM step: (p, Sp, Sc, rp) at t  ->  (n, Sc, Sn, rho) at t + 1; stores rho(t) and the factors of step t
+  auto step = [&](const Pow3 &pc, double Spv, double Scv, double rpv, Pow3 &pn, double &Snv, double &rhov, int tt, int off) {
+    pn = mul3(pc, x);
+    Snv = sum3(pn);
+    const double inv = fast_rcp(Scv);
+    rhov = ((Snv * Spv) * inv) * inv;
+    if (rhov - rpv > kRise) tstar = tt;
+    rho_t[off * RS] = rhov;
+    fac[off * FS] = pc.v0 * inv;
+    fac[off * FS + FG] = pc.v1 * inv;
+  };
+  if (n_rho & 1) {                                                    // odd count: peel one step, then go two at a time
+    Pow3 n; double Sn, rho;
+    step(p, Sp, Sc, rp, n, Sn, rho, t, 0);
     p = n; Sp = Sc; Sc = Sn; rp = rho;
+    t++; rho_t += RS; fac += FS;
+  }
+#pragma unroll 1
+  for (int k = n_rho >> 1; k > 0; k--) {                             // ping-pong: no register moves for the carried state
+    Pow3 n; double Sn, rho;
+    step(p, Sp, Sc, rp, n, Sn, rho, t, 0);
+    step(n, Sc, Sn, rho, p, Sp, rp, t + 1, 1);                        // now p = x^(t+2), Sp(out) = S(t+2), rp = rho(t+1)
+    const double S1 = Sn;                                             // S(t+1)
+    Sc = Sp; Sp = S1;
+    t += 2; rho_t += 2 * RS; fac += 2 * FS;
+  }
+  if (qtr == 3) {                                                     // t = 50: the factors only (rho(50) is never tested)
+    const double inv = fast_rcp(Sc);
+    fac[0] = p.v0 * inv;
+    fac[FG] = p.v1 * inv;
   }
   return tstar;
+}
+
+// NE pairs of one thread for the current site: rows r0 (+16 when NE == 4), columns lane (+32); T by bisection, then
+// the pair term.  NE == 2 serves diagonal tiles, where rows >= 32 only pair with columns >= 32.
+template <int NE, bool WEIGHTED>
+__device__ __forceinline__ void pair_group(const double *sm, const int *ts, const int *valid, const int (&tcol)[2], const bool (&vcol)[2],
+                                           bool diag, int r0, int lane, double w, const double (&K)[9], double *acc) {
+  const double *rho_row = sm + kRhoRow, *rho_col = sm + kRhoCol, *fac_row = sm + kFacRow, *fac_col = sm + kFacCol;
+  int pos[NE], tfix[NE];
+  const double *pr[NE], *pc[NE];                                      // &rho_row[r][pos], &rho_col[pos][c]
+  bool ok[NE];
+#pragma unroll
+  for (int e = 0; e < NE; e++) {
+    const int h = NE == 4 ? (e & 1) : 1, r = r0 + (NE == 4 ? 16 * (e >> 1) : 16 * e), cc = h * 32 + lane;
+    ok[e] = (!diag || cc > r) && vcol[h] && valid[r] != 0;
+    const int tm = max(ts[r], tcol[h]);
+    pos[e] = ok[e] ? tm + 1 : kIter;
+    tfix[e] = 0;
+    if (ok[e] && tm > 0) {                              // rare: scan the non-monotone prefix 1..tm
+      for (int t = 1; t <= tm; t++)
+        if (rho_row[r * kRowLd + t] * rho_col[t * kEdge + cc] < kExpTol) { tfix[e] = t; pos[e] = kIter; break; }
+    }
+    pr[e] = rho_row + r * kRowLd + pos[e];
+    pc[e] = rho_col + pos[e] * kEdge + cc;
+  }
+  // first t in [pos, 49] whose rho product is below e^0.001, else 50 (branch-free; every t < pos is known to be above)
+#pragma unroll
+  for (int s = 32; s >= 1; s >>= 1) {
+#pragma unroll
+    for (int e = 0; e < NE; e++) {
+      const double prod = pr[e][s - 1] * pc[e][(s - 1) * kEdge];
+      const bool adv = (pos[e] + s <= kIter) && !(prod < kExpTol);
+      pos[e] += adv ? s : 0;
+      pr[e] += adv ? s : 0;
+      pc[e] += adv ? s * kEdge : 0;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < NE; e++) {
+    const int h = NE == 4 ? (e & 1) : 1, r = r0 + (NE == 4 ? 16 * (e >> 1) : 16 * e), cc = h * 32 + lane;
+    const int T1 = (tfix[e] ? tfix[e] : pos[e]) - 1;
+    const double a0 = fac_row[r * kRowLd + T1], a1 = fac_row[(kEdge + r) * kRowLd + T1];
+    const double b0 = fac_col[(T1 * 2) * kEdge + cc], b1 = fac_col[(T1 * 2 + 1) * kEdge + cc];
+    double d = pair_term(K, a0, a1, b0, b1);
+    if (WEIGHTED) d *= w;
+    if (ok[e]) acc[NE == 4 ? e : 2 * e + 1] += d;
+  }
 }
 
 // grid = n_splits * n_tiles (split-major); block 512
 template <bool WEIGHTED>
 __global__ void __launch_bounds__(kThreads, 1) k_dist_em(EmArgs a) {
   extern __shared__ __align__(16) double sm[];
-  double *rho_row = sm + kRhoRow, *rho_col = sm + kRhoCol, *ahat = sm + kAhat, *ucol = sm + kU, *raw = sm + kRaw, *wgt = sm + kWgt;
+  double *raw = sm + kRaw, *wgt = sm + kWgt;
   int *tsb = reinterpret_cast<int *>(sm + kDoubles), *valid = tsb + 256;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -139,13 +213,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_em(EmArgs a) {
   const uint32_t c0 = (uint32_t) (((uint64_t) q * a.n_chunks) / a.n_splits);
   const uint32_t c1 = (uint32_t) (((uint64_t) (q + 1) * a.n_chunks) / a.n_splits);
 
-  // build role: warp -> (quarter of the EM steps, side, 32 individuals); rotated so that every SM sub-partition
-  // (warp & 3) gets row and column warps alike (column warps do more arithmetic).
+  // build role: warp -> (quarter of the EM steps, side, 32 individuals); rotated so that the row and column warps of a
+  // quarter are spread over the four SM sub-partitions (warp & 3).
   const int b_qtr = warp >> 2, b_role = ((warp & 3) + b_qtr) & 3, b_side = b_role >> 1, b_k = (b_role & 1) * 32 + lane;
-  double E[9];
+  double K[9];
 #pragma unroll
-  for (int k = 0; k < 9; k++) E[k] = a.E[k];
+  for (int k = 0; k < 9; k++) K[k] = a.K[k];
 
+  // pairs of this thread: rows warp + 16 k (k = 0..3) x columns lane + 32 h (h = 0, 1): acc[k * 2 + h]
   double acc[8];
 #pragma unroll
   for (int k = 0; k < 8; k++) acc[k] = 0.0;
@@ -179,84 +254,38 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_em(EmArgs a) {
         const double m = fmax(x.v0, fmax(x.v1, x.v2));
         const bool ok = m > 0;                                             // all-zero = padded or pairwise-deleted
         if (ok) {
-          x.v0 /= m; x.v1 /= m; x.v2 /= m;                                 // true divisions: the largest becomes exactly 1
+          const double im = fast_rcp(m);                                   // rho and ahat are scale invariant: the largest
+          x.v0 *= im; x.v1 *= im; x.v2 *= im;                              // entry only has to be ~1 so that nothing underflows
           int tstar;
-          if (b_side == 0) {
-            double *rt = rho_row + b_k * kRowLd, *tab = ahat + b_k * kRowLd;
-            if (b_qtr == 0) tstar = build_steps<0, 1, 13>(x, rt, tab, E);
-            else if (b_qtr == 1) tstar = build_steps<0, 14, 13>(x, rt, tab, E);
-            else if (b_qtr == 2) tstar = build_steps<0, 27, 12>(x, rt, tab, E);
-            else tstar = build_steps<0, 39, 12>(x, rt, tab, E);
-          } else {
-            double *rt = rho_col + b_k, *tab = ucol + b_k;
-            if (b_qtr == 0) tstar = build_steps<1, 1, 13>(x, rt, tab, E);
-            else if (b_qtr == 1) tstar = build_steps<1, 14, 13>(x, rt, tab, E);
-            else if (b_qtr == 2) tstar = build_steps<1, 27, 12>(x, rt, tab, E);
-            else tstar = build_steps<1, 39, 12>(x, rt, tab, E);
-          }
+          if (b_side == 0) tstar = build_steps<0>(x, b_qtr, sm + kRhoRow + b_k * kRowLd, sm + kFacRow + b_k * kRowLd);
+          else tstar = build_steps<1>(x, b_qtr, sm + kRhoCol + b_k, sm + kFacCol + b_k);
           if (tstar) atomicMax(&ts[b_side * 64 + b_k], tstar);
         }
         if (b_qtr == 0) valid[b_side * 64 + b_k] = ok ? 1 : 0;
       }
       __syncthreads();
 
-      // ================= pairs: T by bisection, then the 2-FMA term =================
+      // ================= pairs =================
       if (tid < 128) tsb[(par ^ 1) * 128 + tid] = 0;         // the next site's tstar accumulators
       int tcol[2];
       bool vcol[2];
 #pragma unroll
       for (int h = 0; h < 2; h++) { tcol[h] = ts[64 + h * 32 + lane]; vcol[h] = valid[64 + h * 32 + lane] != 0; }
-#pragma unroll
-      for (int k2 = 0; k2 < 2; k2++) {
-        int pos[4], tfix[4];
-        bool ok[4];
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const int r = warp + 16 * (k2 * 2 + (e >> 1)), cc = (e & 1) * 32 + lane;
-          ok[e] = (!diag || cc > r) && vcol[e & 1] && valid[r] != 0;
-          const int tm = max(ts[r], tcol[e & 1]);
-          pos[e] = ok[e] ? tm + 1 : kIter;
-          tfix[e] = 0;
-          if (ok[e] && tm > 0) {                        // rare: scan the non-monotone prefix 1..tm
-            for (int t = 1; t <= tm; t++)
-              if (rho_row[r * kRowLd + t] * rho_col[t * kEdge + cc] < kExpTol) { tfix[e] = t; pos[e] = kIter; break; }
-          }
-        }
-        // first t in [pos, 49] whose rho product is below e^0.001, else 50 (branch-free; all t < pos are known to be above)
-#pragma unroll
-        for (int s = 32; s >= 1; s >>= 1) {
-#pragma unroll
-          for (int e = 0; e < 4; e++) {
-            const int r = warp + 16 * (k2 * 2 + (e >> 1)), cc = (e & 1) * 32 + lane;
-            const int idx = pos[e] + s - 1, idc = min(idx, kIter);
-            const double pr = rho_row[r * kRowLd + idc] * rho_col[idc * kEdge + cc];
-            const bool adv = (idx < kIter) && !(pr < kExpTol);
-            pos[e] = adv ? pos[e] + s : pos[e];
-          }
-        }
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const int r = warp + 16 * (k2 * 2 + (e >> 1)), cc = (e & 1) * 32 + lane;
-          const int T1 = (tfix[e] ? tfix[e] : pos[e]) - 1;
-          const double a0 = ahat[r * kRowLd + T1], a1 = ahat[(kEdge + r) * kRowLd + T1];
-          const double *u = ucol + (T1 * 3) * kEdge + cc;
-          double d = fma(a1, u[2 * kEdge], fma(a0, u[kEdge], u[0]));
-          if (WEIGHTED) d *= w;
-          if (ok[e]) acc[k2 * 4 + e] += d;
-        }
-      }
+      pair_group<4, WEIGHTED>(sm, ts, valid, tcol, vcol, diag, warp, lane, w, K, acc);
+      if (diag) pair_group<2, WEIGHTED>(sm, ts, valid, tcol, vcol, diag, warp + 32, lane, w, K, acc + 4);
+      else pair_group<4, WEIGHTED>(sm, ts, valid, tcol, vcol, diag, warp + 32, lane, w, K, acc + 4);
       par ^= 1;
       __syncthreads();
     }
   }
 
 #pragma unroll
-  for (int k2 = 0; k2 < 2; k2++)
+  for (int k = 0; k < 4; k++)
 #pragma unroll
-    for (int e = 0; e < 4; e++) {
-      const int r = warp + 16 * (k2 * 2 + (e >> 1)), cc = (e & 1) * 32 + lane;
+    for (int h = 0; h < 2; h++) {
+      const int r = warp + 16 * k, cc = h * 32 + lane;
       const uint64_t i = (uint64_t) ti * kEdge + r, j = (uint64_t) tj * kEdge + cc;
-      a.partials[((uint64_t) q * a.ld + i) * a.ld + j] = (i < j) ? acc[k2 * 4 + e] : 0.0;
+      a.partials[((uint64_t) q * a.ld + i) * a.ld + j] = (i < j) ? acc[k * 2 + h] : 0.0;
     }
 }
 
@@ -330,12 +359,16 @@ cudaError_t ngsd_launch_dist_em(ngsd_ctx *ctx, uint32_t n_chunks, uint32_t n_spl
   a.n64 = (uint32_t) em_n64(ctx);
   a.n_tiles = a.n64 * (a.n64 + 1) / 2;
   a.ld = (uint64_t) a.n64 * kEdge;
-  const double *D = ctx->cfg.score;
-  for (int k = 0; k < 3; k++) {
-    a.E[0 + k] = D[6 + k];
-    a.E[3 + k] = D[0 + k] - D[6 + k];
-    a.E[6 + k] = D[3 + k] - D[6 + k];
-  }
+  const double *D = ctx->cfg.score;   // D[g1 * 3 + g2], g1 = genotype of the row individual (i1 < i2, ngsDist.cpp:351-353)
+  a.K[0] = D[8];
+  a.K[1] = D[2] - D[8];
+  a.K[2] = D[5] - D[8];
+  a.K[3] = D[6] - D[8];
+  a.K[4] = D[7] - D[8];
+  a.K[5] = D[0] - D[2] - D[6] + D[8];
+  a.K[6] = D[1] - D[2] - D[7] + D[8];
+  a.K[7] = D[3] - D[5] - D[6] + D[8];
+  a.K[8] = D[4] - D[5] - D[7] + D[8];
   const uint64_t grid = (uint64_t) n_splits * a.n_tiles;
   if (grid == 0 || grid > 0x7fffffffull) return cudaErrorInvalidConfiguration;
   if (weighted)
