@@ -67,7 +67,9 @@ typedef struct {
   int32_t input_kind;        /* ngsd_input_kind                                                      */
   int32_t device;            /* CUDA device ordinal this context owns                                */
   int32_t reserved;          /* flags: bit 0 = keep all three operand planes (disables the sum-to-one reduction that is
-                                used when indep_geno && !pairwise_del; for inspection through ngsd_get_posteriors)  */
+                                used when indep_geno && !pairwise_del; for inspection through ngsd_get_posteriors);
+                                bit 1 = do not use the integer (int8 tensor core) path for called genotypes, i.e. run
+                                them through the FP64 contraction like soft posteriors (A/B testing)              */
 } ngsd_cfg;
 
 typedef struct ngsd_ctx ngsd_ctx;
@@ -77,13 +79,14 @@ typedef struct ngsd_ctx ngsd_ctx;
 typedef struct {
   float frontend_ms;         /* K1 front-end kernel(s)                                   */
   float count_ms;            /* K3 mask-count kernel                                     */
-  float dist_ms;             /* K2 DMMA contraction (or K2b pair-site EM) kernel         */
+  float dist_ms;             /* K2 DMMA contraction / K2b pair-site EM / K2c int8 contraction kernel */
   float epilogue_ms;         /* K4 split reduction + epilogue kernel                     */
   float total_ms;            /* first launch to last launch of the call                  */
   int32_t launches;
   int32_t dist_ctas;         /* grid size of the distance kernel                         */
   uint64_t dist_dmma;        /* warp-level DMMA.8x8x4 instructions the K2 launch issued  */
   uint64_t active_sites;     /* sites with non-zero weight in the call                   */
+  uint64_t dist_imma;        /* warp-level IMMA.16832 instructions of the K2c launch (called-genotype integer path) */
 } ngsd_timing;
 
 NGSD_API void ngsd_default_cfg(ngsd_cfg *cfg);   /* init_pars (parse_args.cpp:6-37) for the fields above */

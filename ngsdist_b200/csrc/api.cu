@@ -117,7 +117,7 @@ int ngsd_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
     ngsd_set_error(nullptr, "missing data threshold must be smaller than calling genotype threshold!");
     return NGSD_ERR_THRESH;
   }
-  if (cfg->input_kind < 0 || cfg->input_kind > 2 || (cfg->reserved & ~1)) { ngsd_set_error(nullptr, "invalid input_kind / flags"); return NGSD_ERR_ARG; }
+  if (cfg->input_kind < 0 || cfg->input_kind > 2 || (cfg->reserved & ~3)) { ngsd_set_error(nullptr, "invalid input_kind / flags"); return NGSD_ERR_ARG; }
   if ((cfg->input_kind == NGSD_INPUT_GENOTYPES || cfg->call_geno) && !cfg->indep_geno) {
     ngsd_set_error(nullptr, "indep_geno must be set for genotype input / call_geno (ngsDist.cpp:55-62)");
     return NGSD_ERR_ARG;
@@ -173,7 +173,19 @@ int ngsd_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
   ctx->sc = ctx->planes == 3 ? NGSD_SC : NGSD_SC2;
   ctx->NC = ctx->planes == 3 ? ctx->NW * 8 : (ctx->NW * 16 + 2) / 3;
   ctx->pushed.assign(ctx->NW, 0);
-  const uint64_t plane = ctx->RB * ctx->NC * NGSD_TILE_DOUBLES;
+  // Called genotypes (every triple one-hot or "missing"): exact integer contraction on the int8 tensor cores, 2 bits per
+  // individual-site in HBM instead of FP64 planes (dist_imma.cu).  --call_geno leaves soft triples between the two
+  // thresholds (gen_func.cpp:908), so it qualifies only when they coincide (the default 0 / 0).
+  const bool hard_calls = cfg->input_kind == NGSD_INPUT_GENOTYPES || (cfg->call_geno && cfg->N_thresh == cfg->call_thresh);
+  ctx->int_path = hard_calls && cfg->indep_geno && !(cfg->reserved & 2) && !getenv("NGSD_NO_INT") &&
+                  ngsd_int_lut(cfg->score, cfg->pairwise_del != 0, ctx->int_lut, &ctx->int_scale, &ctx->int_max_byte);
+  if (ctx->int_path) {
+    ctx->planes = 3;
+    ctx->sc = NGSD_SC;
+    ctx->NC = ctx->NW * 8;
+    CREATE_CUDA(dev_alloc(&ctx->codes, ctx->RB * ctx->NW * 512));
+  }
+  const uint64_t plane = ctx->int_path ? 0 : ctx->RB * ctx->NC * NGSD_TILE_DOUBLES;
   CREATE_CUDA(dev_alloc(&ctx->Apack, plane));
   CREATE_CUDA(dev_alloc(&ctx->Bpack, plane));
   CREATE_CUDA(dev_alloc(&ctx->mask, ctx->RB * ctx->NW * 128));
@@ -206,6 +218,7 @@ int ngsd_destroy(ngsd_ctx *ctx) {
   cudaFree(ctx->d_tiles); cudaFree(ctx->d_partials); cudaFree(ctx->d_weights); cudaFree(ctx->d_chunk_ids);
   cudaFree(ctx->d_ent_word); cudaFree(ctx->d_ent_mask); cudaFree(ctx->d_cnt); cudaFree(ctx->d_split_begin); cudaFree(ctx->d_split_scale); cudaFree(ctx->d_sched);
   cudaFree(ctx->d_out); cudaFree(ctx->d_num); cudaFree(ctx->d_cntout);
+  cudaFree(ctx->codes); cudaFree(ctx->d_wsite); cudaFree(ctx->d_word_layer); cudaFree(ctx->d_word_ids);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
   for (int b = 0; b < 2; b++) {
@@ -359,14 +372,215 @@ int ngsd_get_posteriors(ngsd_ctx *ctx, double *P_host, uint8_t *miss_host) {
 
 // ---------------------------------------------------------------------------------------------- distances ----
 
+// Entry list of K3 (mask_count.cu): (64-site word, level mask) pairs.  Integer weights are decomposed into level masks
+// W_v = {s : w_s >= v}, so cnt = sum_v popc(m_i & m_j & W_v) stays exact for any block size; replicate 0 is every word
+// with an all-ones mask.
+static uint64_t build_count_entries(const ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_blocks, uint64_t block_size,
+                                    uint32_t maxw, uint32_t *h_ew, uint64_t *h_em) {
+  uint64_t n_entries = 0;
+  if (!block_counts) {
+    for (uint64_t w = 0; w < ctx->NW; w++) { h_ew[w] = (uint32_t) w; h_em[w] = ~0ull; }
+    return ctx->NW;
+  }
+  std::vector<uint64_t> level(ctx->NW);
+  for (uint32_t v = 1; v <= maxw; v++) {
+    std::fill(level.begin(), level.end(), 0ull);
+    for (uint64_t b = 0; b < n_blocks; b++) {
+      if (block_counts[b] < v) continue;
+      uint64_t s0 = b * block_size, s1 = s0 + block_size;
+      while (s0 < s1) {   // set bits [s0, s1) word by word
+        const uint64_t w = s0 >> 6, lo = s0 & 63, hi = std::min<uint64_t>(64, lo + (s1 - s0));
+        const uint64_t m = (hi == 64 ? ~0ull : ((1ull << hi) - 1)) & ~((1ull << lo) - 1);
+        level[w] |= m;
+        s0 += hi - lo;
+      }
+    }
+    for (uint64_t w = 0; w < ctx->NW; w++)
+      if (level[w]) { h_ew[n_entries] = (uint32_t) w; h_em[n_entries] = level[w]; n_entries++; }
+  }
+  return n_entries;
+}
+
+static int ensure_dist_buffers(ngsd_ctx *ctx, uint64_t slots);
+static int ensure_entries(ngsd_ctx *ctx, uint64_t n);
+
+// One matrix on the called-genotype integer path (K2c dist_imma.cu): same contract as ngsd_distances.
+static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_blocks, uint64_t block_size, double *out,
+                         double *num_opt, uint64_t *cnt_opt) {
+  const bool weighted = block_counts != nullptr;
+  const uint64_t n_eff = weighted ? n_blocks * block_size : ctx->n_sites;
+  const uint64_t NW = ctx->NW, nsp = NW * 64;
+  uint32_t maxw = 1;
+  if (weighted)
+    for (uint64_t b = 0; b < n_blocks; b++) maxw = std::max(maxw, block_counts[b]);
+  const uint32_t layers = (maxw + 126) / 127;                  // site weights are int8 operand bytes: <= 127 per layer
+  const bool do_count = ctx->cfg.pairwise_del != 0;
+  const uint64_t ent_max = do_count ? NW * (weighted ? maxw : 1) : 0;
+  const uint64_t bytes_w = (uint64_t) layers * nsp, bytes_ids = (uint64_t) layers * NW * sizeof(uint32_t);
+  int rc = ensure_pinned(ctx, bytes_w + 2 * bytes_ids + ent_max * (sizeof(uint32_t) + sizeof(uint64_t)) + 256);
+  if (rc) return rc;
+  uint64_t *h_em = (uint64_t *) ctx->h_pin;
+  uint8_t *h_w = (uint8_t *) (h_em + ent_max);
+  uint32_t *h_ids = (uint32_t *) (h_w + ((bytes_w + 63) / 64) * 64);
+  uint32_t *h_layer = h_ids + (uint64_t) layers * NW;
+  uint32_t *h_ew = h_layer + (uint64_t) layers * NW;
+
+  // per-site weights (bootstrap multiplicities of ngsDist.cpp:416-437; 1 for replicate 0; 0 beyond the sites in use)
+  uint64_t active_sites = n_eff;
+  memset(h_w, 0, bytes_w);
+  if (!weighted) {
+    memset(h_w, 1, ctx->n_sites);
+  } else {
+    active_sites = 0;
+    for (uint64_t b = 0; b < n_blocks; b++) {
+      uint32_t left = block_counts[b];
+      if (left) active_sites += block_size;
+      for (uint32_t l = 0; l < layers && left; l++) {
+        const uint32_t w = std::min<uint32_t>(left, 127);
+        memset(h_w + (uint64_t) l * nsp + b * block_size, (int) w, block_size);
+        left -= w;
+      }
+    }
+  }
+  uint64_t n_words = 0;
+  for (uint32_t l = 0; l < layers; l++)
+    for (uint64_t w = 0; w < NW; w++) {
+      const uint64_t *p8 = (const uint64_t *) (h_w + (uint64_t) l * nsp + w * 64);
+      if (p8[0] | p8[1] | p8[2] | p8[3] | p8[4] | p8[5] | p8[6] | p8[7]) { h_ids[n_words] = (uint32_t) w; h_layer[n_words] = l; n_words++; }
+    }
+  uint64_t n_entries = 0;
+  if (do_count) n_entries = build_count_entries(ctx, block_counts, n_blocks, block_size, maxw, h_ew, h_em);
+
+  const uint64_t n2 = ctx->n_ind * ctx->n_ind;
+  if (ctx->n_tiles == 0 || n_words == 0) {   // a tile shard that owns nothing (or no active site): all-zero sums
+    rc = ensure_dist_buffers(ctx, 1);
+    if (rc) return rc;
+    NGSD_CUDA(ctx, cudaMemsetAsync(ctx->d_out, 0, n2 * sizeof(double), ctx->stream));
+    NGSD_CUDA(ctx, cudaMemsetAsync(ctx->d_num, 0, n2 * sizeof(double), ctx->stream));
+    NGSD_CUDA(ctx, cudaMemsetAsync(ctx->d_cntout, 0, n2 * sizeof(uint64_t), ctx->stream));
+    if (ctx->n_tiles == 0) {
+      if (out) NGSD_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, n2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      if (num_opt) NGSD_CUDA(ctx, cudaMemcpyAsync(num_opt, ctx->d_num, n2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      if (cnt_opt) NGSD_CUDA(ctx, cudaMemcpyAsync(cnt_opt, ctx->d_cntout, n2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+      NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      ctx->timing = ngsd_timing();
+      return NGSD_OK;
+    }
+  }
+
+  // K splits of the word list; an int32 accumulator must hold max_byte * weight * sites of one split
+  int grid = ctx->n_sm;
+  std::vector<uint32_t> splits = plan_splits((uint32_t) n_words, ctx->n_tiles, (double) ctx->n_tiles, grid);
+  {
+    const uint64_t per_word = (uint64_t) std::max(ctx->int_max_byte, 1) * std::min<uint32_t>(maxw, 127) * 64;
+    const uint32_t cap = (uint32_t) std::max<uint64_t>(1, 2147483647ull / per_word);
+    std::vector<uint32_t> cut;
+    cut.push_back(0);
+    for (size_t k = 1; k < splits.size(); k++) {
+      while (splits[k] - cut.back() > cap) cut.push_back(cut.back() + cap);
+      if (splits[k] > cut.back()) cut.push_back(splits[k]);
+    }
+    if (cut.size() < 2) cut.push_back(0);
+    splits.swap(cut);
+  }
+  const uint32_t n_splits = (uint32_t) splits.size() - 1;
+  const uint64_t n_units = (uint64_t) n_splits * ctx->n_tiles;
+  grid = (int) std::min<uint64_t>(grid, std::max<uint64_t>(n_units, 1));
+  rc = ensure_dist_buffers(ctx, n_units / 2 + 1);            // int32 partials: half a slot per unit
+  if (rc) return rc;
+  if (do_count) {
+    rc = ensure_entries(ctx, n_entries);
+    if (rc) return rc;
+  }
+  if (bytes_w > ctx->wsite_cap) {
+    cudaFree(ctx->d_wsite);
+    ctx->d_wsite = nullptr;
+    ctx->wsite_cap = 0;
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_wsite, bytes_w));
+    ctx->wsite_cap = bytes_w;
+  }
+  if ((uint64_t) layers * NW > ctx->word_cap) {
+    cudaFree(ctx->d_word_ids);
+    cudaFree(ctx->d_word_layer);
+    ctx->d_word_ids = ctx->d_word_layer = nullptr;
+    ctx->word_cap = 0;
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_word_ids, (uint64_t) layers * NW));
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_word_layer, (uint64_t) layers * NW));
+    ctx->word_cap = (uint64_t) layers * NW;
+  }
+  if (splits.size() > ctx->split_cap) {
+    cudaFree(ctx->d_split_begin);
+    ctx->d_split_begin = nullptr;
+    ctx->split_cap = 0;
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_split_begin, splits.size() + 64));
+    cudaFree(ctx->d_split_scale);
+    ctx->d_split_scale = nullptr;
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_split_scale, splits.size() + 64));
+    ctx->split_cap = (uint32_t) splits.size() + 64;
+  }
+
+  ctx->timing = ngsd_timing();
+  NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_split_begin, splits.data(), splits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_wsite, h_w, bytes_w, cudaMemcpyHostToDevice, ctx->stream));
+  if (n_words) {
+    NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_word_ids, h_ids, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_word_layer, h_layer, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (n_entries) {
+    NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_ent_word, h_ew, n_entries * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_ent_mask, h_em, n_entries * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  int launches = 0;
+  tick(ctx, 2);
+  if (do_count) NGSD_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+  tick(ctx, 3);
+  if (n_words) {
+    NGSD_CUDA(ctx, ngsd_launch_dist_imma(ctx, (uint32_t) n_units, grid));
+    launches++;
+  }
+  tick(ctx, 4);
+  if (do_count) {   // K3 on the auxiliary stream, next to the persistent K2c CTAs
+    NGSD_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+    NGSD_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->aux_stream));
+    NGSD_CUDA(ctx, ngsd_launch_mask_count(ctx, n_entries, ctx->aux_stream));
+    NGSD_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->aux_stream));
+    NGSD_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
+    NGSD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+    launches += n_entries ? 1 : 0;
+  }
+  tick(ctx, 8);
+  if (n_words) {
+    NGSD_CUDA(ctx, ngsd_launch_epilogue_int(ctx, n_splits, n_eff, do_count));
+    launches += 2;
+  }
+  tick(ctx, 5);
+  if (out) NGSD_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, n2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (num_opt) NGSD_CUDA(ctx, cudaMemcpyAsync(num_opt, ctx->d_num, n2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (cnt_opt) NGSD_CUDA(ctx, cudaMemcpyAsync(cnt_opt, ctx->d_cntout, n2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  float ms;
+  ctx->timing.count_ms = 0;
+  if (do_count) { cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ctx->timing.count_ms = ms; }
+  cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->timing.dist_ms = ms;
+  cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[5]); ctx->timing.epilogue_ms = ms;
+  cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[5]); ctx->timing.total_ms = ms;
+  ctx->timing.launches = launches;
+  ctx->timing.dist_ctas = grid;
+  ctx->timing.dist_imma = (uint64_t) n_words * 8 * ctx->n_tiles * 128ull;   // 8 k-steps per word, 8 warps x 16 IMMA per k-step
+  ctx->timing.active_sites = active_sites;
+  return NGSD_OK;
+}
+
 static int ensure_dist_buffers(ngsd_ctx *ctx, uint64_t slots) {
   const uint64_t n2 = ctx->n_ind * ctx->n_ind;
   if (!ctx->d_out) {
     NGSD_CUDA(ctx, dev_alloc(&ctx->d_out, n2));
     NGSD_CUDA(ctx, dev_alloc(&ctx->d_num, n2));
     NGSD_CUDA(ctx, dev_alloc(&ctx->d_cntout, n2));
-    NGSD_CUDA(ctx, dev_alloc(&ctx->d_weights, ctx->NC * NGSD_SC_MAX));
-    NGSD_CUDA(ctx, dev_alloc(&ctx->d_chunk_ids, ctx->NC));
+    if (!ctx->int_path) {
+      NGSD_CUDA(ctx, dev_alloc(&ctx->d_weights, ctx->NC * NGSD_SC_MAX));
+      NGSD_CUDA(ctx, dev_alloc(&ctx->d_chunk_ids, ctx->NC));
+    }
     if (ctx->cfg.pairwise_del) NGSD_CUDA(ctx, dev_alloc(&ctx->d_cnt, ctx->n_pad * ctx->n_pad));
   }
   if (slots > ctx->partial_slots) {
@@ -411,6 +625,7 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
     }
     n_eff = n_blocks * block_size;
   }
+  if (ctx->int_path) return distances_int(ctx, block_counts, n_blocks, block_size, out, num_opt, cnt_opt);
   const uint64_t SC = (uint64_t) ctx->sc;
   const uint64_t NCu = (ctx->n_sites + SC - 1) / SC;   // chunks that hold data
 
@@ -464,29 +679,7 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
       memcpy(h_c, sorted.data(), n_chunks * sizeof(uint32_t));
     }
   }
-  if (ctx->cfg.pairwise_del) {
-    if (!weighted) {
-      for (uint64_t w = 0; w < ctx->NW; w++) { h_ew[w] = (uint32_t) w; h_em[w] = ~0ull; }
-      n_entries = ctx->NW;
-    } else {
-      std::vector<uint64_t> level(ctx->NW);
-      for (uint32_t v = 1; v <= maxw; v++) {
-        std::fill(level.begin(), level.end(), 0ull);
-        for (uint64_t b = 0; b < n_blocks; b++) {
-          if (block_counts[b] < v) continue;
-          uint64_t s0 = b * block_size, s1 = s0 + block_size;
-          while (s0 < s1) {   // set bits [s0, s1) word by word
-            const uint64_t w = s0 >> 6, lo = s0 & 63, hi = std::min<uint64_t>(64, lo + (s1 - s0));
-            const uint64_t m = (hi == 64 ? ~0ull : ((1ull << hi) - 1)) & ~((1ull << lo) - 1);
-            level[w] |= m;
-            s0 += hi - lo;
-          }
-        }
-        for (uint64_t w = 0; w < ctx->NW; w++)
-          if (level[w]) { h_ew[n_entries] = (uint32_t) w; h_em[n_entries] = level[w]; n_entries++; }
-      }
-    }
-  }
+  if (ctx->cfg.pairwise_del) n_entries = build_count_entries(ctx, block_counts, n_blocks, block_size, maxw, h_ew, h_em);
 
   if (ctx->n_tiles == 0) {   // a tile shard that owns nothing: all-zero contribution
     int rc0 = ensure_dist_buffers(ctx, 1);

@@ -23,6 +23,7 @@ struct FrontCfg {
   int call_geno;
   int pairwise_del;
   int planes;        // 3, or 2 (sum-to-one reduction, see ngsd_internal.h)
+  int int_path;      // called genotypes: write 2-bit codes for dist_imma.cu instead of FP64 planes
   double N_thresh, call_thresh;
   double score[9];
 };
@@ -139,9 +140,10 @@ template <bool EXACT>
 __global__ void __launch_bounds__(512, EXACT ? 1 : 2) k_frontend(FrontCfg c, const double *__restrict__ raw, const int8_t *__restrict__ codes,
                                                       uint64_t n_ind, uint64_t site0, uint64_t n, uint64_t NC, uint64_t NW,
                                                       double *__restrict__ Apack, double *__restrict__ Bpack,
-                                                      double *__restrict__ Cplane, uint64_t ldc,
+                                                      double *__restrict__ Cplane, uint64_t ldc, uint32_t *__restrict__ codes_out,
                                                       uint64_t *__restrict__ mask, int *__restrict__ err) {
   __shared__ unsigned nib[16][32];
+  __shared__ unsigned cod[16][32];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const uint64_t i = (uint64_t) blockIdx.x * 32 + tx;
   const uint64_t word = site0 / 64 + blockIdx.y;
@@ -163,7 +165,7 @@ __global__ void __launch_bounds__(512, EXACT ? 1 : 2) k_frontend(FrontCfg c, con
       }
     }
   }
-  unsigned bits = 0;
+  unsigned bits = 0, cbits = 0xFF;      // codes of this thread's 4 sites, 2 bits each; 3 = missing / padding
   int bad = 0;
 #pragma unroll
   for (int q = 0; q < 4; q++) {
@@ -180,6 +182,9 @@ __global__ void __launch_bounds__(512, EXACT ? 1 : 2) k_frontend(FrontCfg c, con
         if (!ok) bad |= 1;
       }
       present = !miss_data(p);
+      // called / genotype data: the triple is one-hot or the uniform "missing" triple (dist_imma.cu)
+      const unsigned cg = (p[0] == 1.0) ? 0u : (p[1] == 1.0) ? 1u : (p[2] == 1.0) ? 2u : 3u;
+      cbits = (cbits & ~(3u << (2 * q))) | (cg << (2 * q));
       if (c.pairwise_del && !present) p[0] = p[1] = p[2] = 0;       // the skip of ngsDist.cpp:335-338, folded into the operands
       A[q][0] = p[0]; A[q][1] = p[1]; A[q][2] = p[2];
     }
@@ -200,7 +205,9 @@ __global__ void __launch_bounds__(512, EXACT ? 1 : 2) k_frontend(FrontCfg c, con
       b += c.score[3 * g + 2] * A[q][2];
       Bv[g][q] = b;
     }
-  if (c.planes == 3) {
+  if (c.int_path) {
+    cod[ty][tx] = cbits;
+  } else if (c.planes == 3) {
     const uint64_t chunk = sgrp >> 1, h = sgrp & 1;
     const uint64_t base = (rb * NC + chunk) * NGSD_TILE_DOUBLES + (r >> 3) * 32 + (r & 7) * 4;
 #pragma unroll
@@ -240,17 +247,25 @@ __global__ void __launch_bounds__(512, EXACT ? 1 : 2) k_frontend(FrontCfg c, con
     for (int k = 0; k < 16; k++) w |= (uint64_t) nib[k][tx] << (4 * k);
     mask[(rb * NW + word) * 128 + r] = w;
   }
+  if (c.int_path && ty < 4) {           // word ty of this individual: sites 16 ty .. 16 ty + 15 of the 64-site word
+    const unsigned w = cod[4 * ty][tx] | (cod[4 * ty + 1][tx] << 8) | (cod[4 * ty + 2][tx] << 16) | (cod[4 * ty + 3][tx] << 24);
+    codes_out[((rb * NW + word) * 4 + ty) * 128 + r] = w;
+  }
 }
 
 // Inspection: packed A planes + mask -> [ind][site][3] / [ind][site]
-__global__ void k_unpack(const double *__restrict__ Apack, const uint64_t *__restrict__ mask, uint64_t n_ind, uint64_t n_sites,
-                         uint64_t NC, uint64_t NW, int planes, double *__restrict__ P, uint8_t *__restrict__ miss) {
+__global__ void k_unpack(const double *__restrict__ Apack, const uint32_t *__restrict__ codes, const uint64_t *__restrict__ mask,
+                         uint64_t n_ind, uint64_t n_sites, uint64_t NC, uint64_t NW, int planes, double *__restrict__ P,
+                         uint8_t *__restrict__ miss) {
   const uint64_t idx = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_ind * n_sites) return;
   const uint64_t i = idx / n_sites, s = idx % n_sites;
   const uint64_t rb = i >> 7, r = i & 127, sgrp = s >> 2, q = s & 3;
   if (P) {
-    if (planes == 3) {
+    if (codes) {
+      const unsigned code = (codes[((rb * NW + (s >> 6)) * 4 + ((s >> 4) & 3)) * 128 + r] >> (2 * (s & 15))) & 3u;
+      for (unsigned g = 0; g < 3; g++) P[idx * 3 + g] = code == 3u ? kThird : (code == g ? 1.0 : 0.0);
+    } else if (planes == 3) {
       const uint64_t chunk = sgrp >> 1, h = sgrp & 1;
       const uint64_t base = (rb * NC + chunk) * NGSD_TILE_DOUBLES + (r >> 3) * 32 + (r & 7) * 4 + q;
       for (int g = 0; g < 3; g++) P[idx * 3 + g] = Apack[base + (uint64_t) (g * 2 + h) * 512];
@@ -299,22 +314,23 @@ cudaError_t ngsd_launch_frontend(ngsd_ctx *ctx, const ngsd_frontend_args &a) {
   c.call_geno = ctx->cfg.call_geno;
   c.pairwise_del = ctx->cfg.pairwise_del;
   c.planes = ctx->planes;
+  c.int_path = ctx->int_path ? 1 : 0;
   c.N_thresh = ctx->cfg.N_thresh;
   c.call_thresh = ctx->cfg.call_thresh;
   for (int k = 0; k < 9; k++) c.score[k] = ctx->cfg.score[k];
   dim3 grid((unsigned) (ctx->n_pad / 32), (unsigned) ((a.n + 63) / 64)), block(32, 16);
   if (c.call_geno)
     k_frontend<true><<<grid, block, 0, ctx->stream>>>(c, a.raw, a.codes, ctx->n_ind, a.site0, a.n, ctx->NC, ctx->NW, ctx->Apack,
-                                                      ctx->Bpack, ctx->Cplane, ctx->ldc, ctx->mask, ctx->d_err);
+                                                      ctx->Bpack, ctx->Cplane, ctx->ldc, ctx->codes, ctx->mask, ctx->d_err);
   else
     k_frontend<false><<<grid, block, 0, ctx->stream>>>(c, a.raw, a.codes, ctx->n_ind, a.site0, a.n, ctx->NC, ctx->NW, ctx->Apack,
-                                                       ctx->Bpack, ctx->Cplane, ctx->ldc, ctx->mask, ctx->d_err);
+                                                       ctx->Bpack, ctx->Cplane, ctx->ldc, ctx->codes, ctx->mask, ctx->d_err);
   return cudaGetLastError();
 }
 
 cudaError_t ngsd_launch_unpack(ngsd_ctx *ctx, double *P_dev, uint8_t *miss_dev) {
   const uint64_t tot = ctx->n_ind * ctx->n_sites;
-  k_unpack<<<(unsigned) ((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->Apack, ctx->mask, ctx->n_ind, ctx->n_sites, ctx->NC,
+  k_unpack<<<(unsigned) ((tot + 255) / 256), 256, 0, ctx->stream>>>(ctx->Apack, ctx->codes, ctx->mask, ctx->n_ind, ctx->n_sites, ctx->NC,
                                                                     ctx->NW, ctx->planes, P_dev, miss_dev);
   return cudaGetLastError();
 }

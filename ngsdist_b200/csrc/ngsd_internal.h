@@ -56,6 +56,15 @@ struct ngsd_ctx {
   double *d_cvec = nullptr;                    // [n_pad] weighted row sums of Cplane for the current matrix
   double *Apack = nullptr, *Bpack = nullptr;   // [RB][NC][3072]
   uint64_t *mask = nullptr;                    // [RB][NW][128] presence bits (1 = data present)
+  // called-genotype integer path (dist_imma.cu): 2-bit codes instead of FP64 planes
+  bool int_path = false;
+  uint32_t *codes = nullptr;                   // [RB][NW][4][128] 16 sites per word, code 3 = missing
+  uint8_t *d_wsite = nullptr; uint64_t wsite_cap = 0;        // [layers][NW*64] per-site weights
+  uint32_t *d_word_layer = nullptr; uint64_t word_cap = 0;   // weight layer of each word-list entry (ids live in d_chunk_ids)
+  uint32_t *d_word_ids = nullptr;
+  uint32_t int_lut[4] = {0, 0, 0, 0};
+  double int_scale = 1.0;
+  int int_max_byte = 0;
   int *d_err = nullptr;                        // device error flags (bit0 NaN, bit1 bad genotype code)
   // push state
   std::vector<uint8_t> pushed;                 // per 64-site word: pushed?
@@ -131,3 +140,7 @@ cudaError_t ngsd_launch_dist_em(ngsd_ctx *ctx, uint32_t n_chunks, uint32_t n_spl
 cudaError_t ngsd_launch_finish(ngsd_ctx *ctx);
 cudaError_t ngsd_launch_cvec(ngsd_ctx *ctx, bool weighted, uint64_t n_eff);
 cudaError_t ngsd_launch_epilogue_em(ngsd_ctx *ctx, uint32_t n_splits, uint64_t const_cnt, bool use_cnt);
+// K2c: called genotypes on the int8 tensor cores (dist_imma.cu)
+bool ngsd_int_lut(const double *score, bool pairwise_del, uint32_t lut[4], double *scale, int *max_byte);
+cudaError_t ngsd_launch_dist_imma(ngsd_ctx *ctx, uint32_t n_units, int grid);
+cudaError_t ngsd_launch_epilogue_int(ngsd_ctx *ctx, uint32_t n_splits, uint64_t const_cnt, bool use_cnt);
