@@ -122,6 +122,58 @@ __device__ __forceinline__ bool posterior_fast(const FrontCfg &c, double x0, dou
   return ok;
 }
 
+// Fast path of call_geno when N_thresh == call_thresh (every triple ends up called or missing; the integer path).
+// call_geno (gen_func.cpp:886-914) only needs, in log space: the first strict maximum, the exact-tie test L[min] == L[max]
+// and max_pp = exp(L[max]) against the thresholds.  log and "- norm" are monotone, so away from near-ties the order of
+// the normalised logs is the order of the raw values, and max_pp = x_max / sum(x) to ~1e-13.  Returns false -- the
+// caller then runs the reference's exact log-space sequence -- whenever rounding could make a difference: non-positive
+// or non-finite input, two values (or max_pp and a threshold) within 1e-9 of each other.  code: 0..2 called, 3 missing.
+__device__ __forceinline__ bool called_code_fast(const FrontCfg &c, double x0, double x1, double x2, unsigned &code) {
+  const double kTie = 1e-9;
+  unsigned mp = 0;
+  double mx = x0, mn;
+  if (x1 > mx) { mx = x1; mp = 1; }
+  if (x2 > mx) { mx = x2; mp = 2; }
+  mn = fmin(x0, fmin(x1, x2));
+  double max_pp;
+  if (!c.in_log) {
+    const double sum = (x0 + x1) + x2;
+    if (!(mn >= 0.0) || !(mx > 0.0) || !(sum < INFINITY)) return false;   // negatives, all zero, NaN, inf: reference corner cases
+    // (a zero next to a positive maximum is harmless: log(0) = -1e15 / -inf stays the strict minimum after normalisation)
+    if (mn == mx) {                                                  // all equal: max_pp = -1, max_pos = 0 (gen_func.cpp:895-897)
+      if (-1.0 >= c.call_thresh) { code = 0u; return true; }
+      if (-1.0 < c.N_thresh) { code = 3u; return true; }
+      return false;
+    }
+    const double tol = kTie * mx;
+    // a runner-up (or the minimum, for the all-equal test) within tol of the maximum could collapse onto it in log space
+    const double second = mp == 0 ? fmax(x1, x2) : mp == 1 ? fmax(x0, x2) : fmax(x0, x1);
+    if (mx - second <= tol) return false;
+    max_pp = (c.N_thresh == 0.0 && c.call_thresh == 0.0) ? 1.0 : mx / sum;   // default thresholds: only the sign matters
+  } else {
+    if (!(mn > -INFINITY) || !(mx < INFINITY)) return false;
+    if (mn == mx) {
+      if (-1.0 >= c.call_thresh) { code = 0u; return true; }
+      if (-1.0 < c.N_thresh) { code = 3u; return true; }
+      return false;
+    }
+    const double tol = kTie * (1.0 + fabs(mx) + fabs(mn));
+    const double second = mp == 0 ? fmax(x1, x2) : mp == 1 ? fmax(x0, x2) : fmax(x0, x1);
+    if (mx - second <= tol) return false;
+    if (c.N_thresh == 0.0 && c.call_thresh == 0.0) {
+      max_pp = 1.0;                                                  // any positive value: only the sign matters
+    } else {
+      max_pp = 1.0 / ((exp(x0 - mx) + exp(x1 - mx)) + exp(x2 - mx));
+    }
+  }
+  if (fabs(max_pp - c.N_thresh) <= kTie || fabs(max_pp - c.call_thresh) <= kTie) {
+    if (!(c.N_thresh == 0.0 && c.call_thresh == 0.0)) return false;  // knife edge at a user threshold
+  }
+  if (max_pp >= c.call_thresh) { code = mp; return true; }           // gen_func.cpp:908-913
+  if (max_pp < c.N_thresh) { code = 3u; return true; }               // gen_func.cpp:903-905
+  return false;
+}
+
 // Genotype-code input (read_data.cpp:88-95,98 followed by ngsDist.cpp:172-173): exact one-hot / uniform triples.
 __device__ __forceinline__ bool posterior_from_code(int g, double p[3]) {
   if (g > 2) { p[0] = p[1] = p[2] = 0; return false; }
@@ -140,10 +192,9 @@ template <bool EXACT>
 __global__ void __launch_bounds__(512, EXACT ? 1 : 2) k_frontend(FrontCfg c, const double *__restrict__ raw, const int8_t *__restrict__ codes,
                                                       uint64_t n_ind, uint64_t site0, uint64_t n, uint64_t NC, uint64_t NW,
                                                       double *__restrict__ Apack, double *__restrict__ Bpack,
-                                                      double *__restrict__ Cplane, uint64_t ldc, uint32_t *__restrict__ codes_out,
+                                                      double *__restrict__ Cplane, uint64_t ldc,
                                                       uint64_t *__restrict__ mask, int *__restrict__ err) {
   __shared__ unsigned nib[16][32];
-  __shared__ unsigned cod[16][32];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const uint64_t i = (uint64_t) blockIdx.x * 32 + tx;
   const uint64_t word = site0 / 64 + blockIdx.y;
@@ -165,7 +216,7 @@ __global__ void __launch_bounds__(512, EXACT ? 1 : 2) k_frontend(FrontCfg c, con
       }
     }
   }
-  unsigned bits = 0, cbits = 0xFF;      // codes of this thread's 4 sites, 2 bits each; 3 = missing / padding
+  unsigned bits = 0;
   int bad = 0;
 #pragma unroll
   for (int q = 0; q < 4; q++) {
@@ -182,9 +233,6 @@ __global__ void __launch_bounds__(512, EXACT ? 1 : 2) k_frontend(FrontCfg c, con
         if (!ok) bad |= 1;
       }
       present = !miss_data(p);
-      // called / genotype data: the triple is one-hot or the uniform "missing" triple (dist_imma.cu)
-      const unsigned cg = (p[0] == 1.0) ? 0u : (p[1] == 1.0) ? 1u : (p[2] == 1.0) ? 2u : 3u;
-      cbits = (cbits & ~(3u << (2 * q))) | (cg << (2 * q));
       if (c.pairwise_del && !present) p[0] = p[1] = p[2] = 0;       // the skip of ngsDist.cpp:335-338, folded into the operands
       A[q][0] = p[0]; A[q][1] = p[1]; A[q][2] = p[2];
     }
@@ -205,9 +253,7 @@ __global__ void __launch_bounds__(512, EXACT ? 1 : 2) k_frontend(FrontCfg c, con
       b += c.score[3 * g + 2] * A[q][2];
       Bv[g][q] = b;
     }
-  if (c.int_path) {
-    cod[ty][tx] = cbits;
-  } else if (c.planes == 3) {
+  if (c.planes == 3) {
     const uint64_t chunk = sgrp >> 1, h = sgrp & 1;
     const uint64_t base = (rb * NC + chunk) * NGSD_TILE_DOUBLES + (r >> 3) * 32 + (r & 7) * 4;
 #pragma unroll
@@ -247,9 +293,75 @@ __global__ void __launch_bounds__(512, EXACT ? 1 : 2) k_frontend(FrontCfg c, con
     for (int k = 0; k < 16; k++) w |= (uint64_t) nib[k][tx] << (4 * k);
     mask[(rb * NW + word) * 128 + r] = w;
   }
-  if (c.int_path && ty < 4) {           // word ty of this individual: sites 16 ty .. 16 ty + 15 of the 64-site word
+}
+
+// The exact log-space sequence of the reference for one triple, out of line: the integer-path kernel below only needs
+// it for the rare triples its fast test cannot decide, and inlining it would cost that kernel its occupancy.
+__device__ __noinline__ unsigned called_code_exact(const FrontCfg &c, double x0, double x1, double x2, int *bad) {
+  double p[3];
+  if (!posterior(c, x0, x1, x2, p)) *bad |= 1;
+  return (p[0] == 1.0) ? 0u : (p[1] == 1.0) ? 1u : (p[2] == 1.0) ? 2u : 3u;   // one-hot or the uniform "missing" triple
+}
+
+// Front end of the integer path (called genotypes / genotype input; dist_imma.cu): same thread mapping as k_frontend,
+// but the only outputs are 2 bits per individual-site (codes [RB][NW][4][128], 16 sites per word, 3 = missing or
+// padding) and the presence mask.  HBM-bound: 24 B (or 1 B of genotype code) read per individual-site, 0.4 B written.
+__global__ void __launch_bounds__(512, 2) k_frontend_codes(FrontCfg c, const double *__restrict__ raw, const int8_t *__restrict__ codes,
+                                                            uint64_t n_ind, uint64_t site0, uint64_t n, uint64_t NW,
+                                                            uint32_t *__restrict__ codes_out, uint64_t *__restrict__ mask,
+                                                            int *__restrict__ err) {
+  __shared__ unsigned cod[16][32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const uint64_t i = (uint64_t) blockIdx.x * 32 + tx;
+  const uint64_t word = site0 / 64 + blockIdx.y;
+  const uint64_t s_local0 = (uint64_t) blockIdx.y * 64 + ty * 4;
+  double A[4][3];
+  int gc[4] = {-1, -1, -1, -1};
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint64_t sl = s_local0 + q;
+    A[q][0] = A[q][1] = A[q][2] = 0;
+    if (i < n_ind && sl < n) {
+      if (codes) {
+        gc[q] = (int) codes[sl * n_ind + i];
+      } else {
+        const double *x = raw + (sl * n_ind + i) * 3;
+        A[q][0] = x[0]; A[q][1] = x[1]; A[q][2] = x[2];
+      }
+    }
+  }
+  unsigned cbits = 0xFF;                  // 2 bits per site; 3 = missing / padding
+  int bad = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint64_t sl = s_local0 + q;
+    if (i < n_ind && sl < n) {
+      unsigned cg;
+      if (codes) {
+        cg = gc[q] < 0 ? 3u : (unsigned) gc[q];                      // read_data.cpp:88-95: -1 = missing
+        if (gc[q] > 2) { bad |= 2; cg = 3u; }
+      } else if (!called_code_fast(c, A[q][0], A[q][1], A[q][2], cg)) {
+        cg = called_code_exact(c, A[q][0], A[q][1], A[q][2], &bad);
+      }
+      cbits = (cbits & ~(3u << (2 * q))) | (cg << (2 * q));
+    }
+  }
+  if (bad) atomicOr(err, bad);
+  cod[ty][tx] = cbits;
+  __syncthreads();
+  const uint64_t rb = i >> 7, r = i & 127;
+  if (ty < 4) {                           // word ty of this individual: sites 16 ty .. 16 ty + 15 of the 64-site word
     const unsigned w = cod[4 * ty][tx] | (cod[4 * ty + 1][tx] << 8) | (cod[4 * ty + 2][tx] << 16) | (cod[4 * ty + 3][tx] << 24);
     codes_out[((rb * NW + word) * 4 + ty) * 128 + r] = w;
+  } else if (ty == 4) {                   // presence mask (miss_data of gen_func.cpp:862-868: exactly the code-3 entries)
+    uint64_t m = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const unsigned cb = cod[k][tx];
+#pragma unroll
+      for (int q = 0; q < 4; q++) m |= (uint64_t) (((cb >> (2 * q)) & 3u) != 3u) << (4 * k + q);
+    }
+    mask[(rb * NW + word) * 128 + r] = m;
   }
 }
 
@@ -319,12 +431,15 @@ cudaError_t ngsd_launch_frontend(ngsd_ctx *ctx, const ngsd_frontend_args &a) {
   c.call_thresh = ctx->cfg.call_thresh;
   for (int k = 0; k < 9; k++) c.score[k] = ctx->cfg.score[k];
   dim3 grid((unsigned) (ctx->n_pad / 32), (unsigned) ((a.n + 63) / 64)), block(32, 16);
-  if (c.call_geno)
+  if (ctx->int_path)
+    k_frontend_codes<<<grid, block, 0, ctx->stream>>>(c, a.raw, a.codes, ctx->n_ind, a.site0, a.n, ctx->NW, ctx->codes, ctx->mask,
+                                                      ctx->d_err);
+  else if (c.call_geno)
     k_frontend<true><<<grid, block, 0, ctx->stream>>>(c, a.raw, a.codes, ctx->n_ind, a.site0, a.n, ctx->NC, ctx->NW, ctx->Apack,
-                                                      ctx->Bpack, ctx->Cplane, ctx->ldc, ctx->codes, ctx->mask, ctx->d_err);
+                                                      ctx->Bpack, ctx->Cplane, ctx->ldc, ctx->mask, ctx->d_err);
   else
     k_frontend<false><<<grid, block, 0, ctx->stream>>>(c, a.raw, a.codes, ctx->n_ind, a.site0, a.n, ctx->NC, ctx->NW, ctx->Apack,
-                                                       ctx->Bpack, ctx->Cplane, ctx->ldc, ctx->codes, ctx->mask, ctx->d_err);
+                                                       ctx->Bpack, ctx->Cplane, ctx->ldc, ctx->mask, ctx->d_err);
   return cudaGetLastError();
 }
 

@@ -1,0 +1,107 @@
+"""Called-genotype integer path (K2c dist_imma.cu, int8 tensor cores on 2-bit codes) through the C ABI.
+
+Everything is integer until num = acc / S, so against the oracle: cnt bit-exact everywhere; num and model-0 distances
+bit-exact with --pairwise_del or without missing data; 1e-9 otherwise (the reference's own sequential FP sum of the
+uniform-triple terms is what differs).  The same data forced through the FP64 contraction (ngsd_cfg.reserved bit 1)
+must agree too -- the A/B check that both contractions implement the same gen_dist (ngsDist.cpp:325-404).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from test_gpu_parity import assert_close, nb
+
+pytestmark = pytest.mark.gpu
+
+
+def run(raw, genotypes=None, **pk):
+    n_sites, n_ind = raw.shape[:2] if genotypes is None else genotypes.shape
+    p = nb().Params(n_ind=n_ind, n_sites=n_sites, **pk)
+    with nb().NgsDistB200(p) as g:
+        if genotypes is None:
+            g.push_sites(raw)
+        else:
+            g.push_genotypes(genotypes)
+        return g.run(want_num=True, want_cnt=True)
+
+
+@pytest.mark.parametrize("pdel", [True, False])
+@pytest.mark.parametrize("avg", [False, True])
+@pytest.mark.parametrize("miss", [0.0, 0.15])
+def test_called_vs_oracle_and_fp64_path(pdel, avg, miss):
+    """--call_geno (default thresholds), bootstrap blocks that straddle the 64-site words (block 37), both score matrices."""
+    n_ind, n_sites = 203, 3001
+    raw = oracle.synth_raw(77, miss, n_ind, n_sites)
+    kw = dict(call_geno=True, pairwise_del=pdel, avg_nuc_dist=avg, evol_model=0, n_boot_rep=2, boot_block_size=37, seed=9)
+    res = run(raw, in_probs=True, **kw)
+    res64 = run(raw, in_probs=True, force_fp64=True, **kw)
+    ora = oracle.run_job(raw, indep=True, call_geno=True, pairwise_del=pdel, avg_nuc_dist=avg, evol_model=0, n_boot_rep=2,
+                         boot_block_size=37, seed=9)
+    assert len(res) == len(ora) == 3
+    exact = pdel or miss == 0.0
+    for rep, (r, r64, o) in enumerate(zip(res, res64, ora)):
+        assert np.array_equal(r["cnt"], o["cnt"]), "cnt rep %d" % rep
+        assert np.array_equal(r["cnt"], r64["cnt"])
+        if exact:
+            assert np.array_equal(r["num"], o["num"]), "num must be bit-exact (rep %d)" % rep
+            assert np.array_equal(r["dist"], o["dist"], equal_nan=True), "model-0 distances must be bit-exact (rep %d)" % rep
+            assert np.array_equal(r["num"], r64["num"])
+        else:
+            assert_close(r["num"], o["num"], "num rep %d" % rep)
+            assert_close(r["dist"], o["dist"], "dist rep %d" % rep)
+            assert_close(r["num"], r64["num"], "int vs fp64 rep %d" % rep)
+        assert np.array_equal(r["dist"], r["dist"].T) and (np.diag(r["dist"]) == 0).all()
+
+
+def test_genotype_input_many_tiles_jc69():
+    """Genotype codes {-1,0,1,2} (read_data.cpp:88-95) on 700 individuals (21 tiles), JC69, vs oracle blocks."""
+    rng = np.random.RandomState(5)
+    n_ind, n_sites = 700, 2500
+    geno = rng.randint(-1, 3, size=(n_sites, n_ind)).astype(np.int8)
+    P = oracle.frontend_geno(geno)
+    for pdel in (False, True):
+        r = run(None, genotypes=geno, in_probs=False, indep_geno=True, pairwise_del=pdel, evol_model=2)[0]
+        for (r0, c0) in [(0, 0), (64, 600), (636, 636)]:
+            o = oracle.distances_block(P, r0, r0 + 64, c0, c0 + 64, indep=True, pairwise_del=pdel, evol_model=2)
+            sub = np.triu(np.ones((64, 64), bool), 1) if r0 == c0 else np.ones((64, 64), bool)
+            assert np.array_equal(r["cnt"][r0:r0 + 64, c0:c0 + 64][sub], o["cnt"][sub])
+            assert_close(r["num"][r0:r0 + 64, c0:c0 + 64][sub], o["num"][sub], "num pdel=%d" % pdel)
+            assert_close(r["dist"][r0:r0 + 64, c0:c0 + 64][sub], o["dist"][sub], "dist pdel=%d" % pdel)
+
+
+def test_large_multiplicities_use_weight_layers():
+    """Block multiplicities above 127 (one int8 operand byte) are split into layers; linearity in the weights is exact."""
+    n_ind, n_sites, bs = 130, 1280, 128
+    raw = oracle.synth_raw(3, 0.1, n_ind, n_sites)
+    p = nb().Params(n_ind=n_ind, n_sites=n_sites, in_probs=True, call_geno=True, pairwise_del=True, evol_model=0)
+    with nb().NgsDistB200(p) as g:
+        g.push_sites(raw)
+        nbk = n_sites // bs
+        c_big = np.array([300, 0, 1, 127, 128, 0, 5, 0, 2, 254], dtype=np.uint32)
+        unit = [np.eye(nbk, dtype=np.uint32)[b] for b in range(nbk)]
+        big = g.distances(c_big, bs, want_num=True, want_cnt=True)
+        num = np.zeros((n_ind, n_ind))
+        cnt = np.zeros((n_ind, n_ind), dtype=np.uint64)
+        for b in range(nbk):
+            if c_big[b]:
+                r = g.distances(unit[b], bs, want_num=True, want_cnt=True)
+                num += float(c_big[b]) * r["num"]
+                cnt += np.uint64(c_big[b]) * r["cnt"]
+    assert np.array_equal(big["cnt"], cnt)
+    assert np.array_equal(big["num"], num)        # multiples of 0.5 far below 2^53: every sum here is exact
+
+
+def test_soft_thresholds_fall_back_to_fp64_planes():
+    """N_thresh < call_thresh leaves soft triples (gen_func.cpp:908): that data must not take the integer path."""
+    n_ind, n_sites = 60, 700
+    raw = oracle.synth_raw(21, 0.1, n_ind, n_sites)
+    kw = dict(call_geno=True, N_thresh=0.4, call_thresh=0.8, evol_model=0)
+    r = run(raw, in_probs=True, **kw)[0]
+    o = oracle.run_job(raw, indep=True, **kw)[0]
+    assert np.array_equal(r["cnt"], o["cnt"])
+    assert_close(r["num"], o["num"])
+    # equal thresholds: every triple is called or missing -> integer path, still the reference's answer
+    kw = dict(call_geno=True, N_thresh=0.6, call_thresh=0.6, pairwise_del=True, evol_model=0)
+    r = run(raw, in_probs=True, **kw)[0]
+    o = oracle.run_job(raw, indep=True, **kw)[0]
+    assert np.array_equal(r["cnt"], o["cnt"]) and np.array_equal(r["num"], o["num"])
