@@ -63,6 +63,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
   while (!mbar_try_wait(bar, parity)) {}
 }
+// producer-side wait: back off between polls, the consumers on the same SM sub-partition need the issue slots
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(200);
+}
 __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
                "l"(src), "r"(bytes), "r"(smem_u32(bar))
@@ -125,7 +129,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_imma(ImmaArgs a) {
         for (uint32_t c = c0; c < c1; c++) {
           const uint64_t word = a.word_ids[c];
           const uint8_t *wsrc = a.wsite + ((uint64_t) a.word_layer[c] * a.NW + word) * 64;
-          mbar_wait(&empty[stage], phase ^ 1);
+          mbar_wait_sleep(&empty[stage], phase ^ 1);
           meta[stage * 2] = u;
           meta[stage * 2 + 1] = (c == c0 ? kFirst : 0u) | (c + 1 == c1 ? kLast : 0u);
           mbar_expect_tx(&full[stage], kStageBytes);
@@ -163,30 +167,36 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_imma(ImmaArgs a) {
     const uint8_t *Ws = stageW(stage) + q;
 #pragma unroll
     for (int k = 0; k < 4; k++) {                                   // 16 sites per packed word
+      // After the rotation the four code fields this lane needs from a word (sites q, q+4, q+8, q+12 of the 16) sit at
+      // bits 3..4 (A: 8 * code) or 2..3 (B: 4 * code) of its four bytes; one mask per word isolates all of them.
       uint32_t ar[4][2], br[4];
 #pragma unroll
       for (int mi = 0; mi < 4; mi++) {
-        ar[mi][0] = __funnelshift_r(As[k * 128 + mi * 16], As[k * 128 + mi * 16], rotA);
-        ar[mi][1] = __funnelshift_r(As[k * 128 + mi * 16 + 8], As[k * 128 + mi * 16 + 8], rotA);
+        const uint32_t x0 = As[k * 128 + mi * 16], x1 = As[k * 128 + mi * 16 + 8];
+        ar[mi][0] = __funnelshift_r(x0, x0, rotA) & 0x18181818u;
+        ar[mi][1] = __funnelshift_r(x1, x1, rotA) & 0x18181818u;
       }
 #pragma unroll
-      for (int ni = 0; ni < 4; ni++) br[ni] = __funnelshift_r(Bs[k * 128 + ni * 8], Bs[k * 128 + ni * 8], rotB);
+      for (int ni = 0; ni < 4; ni++) {
+        const uint32_t y = Bs[k * 128 + ni * 8];
+        br[ni] = __funnelshift_r(y, y, rotB) & 0x0C0C0C0Cu;
+      }
 #pragma unroll
       for (int p = 0; p < 2; p++) {                                 // one IMMA k-step = 8 sites = K 32
         const uint32_t w0 = Ws[k * 16 + p * 8], w1 = Ws[k * 16 + p * 8 + 4];
         uint32_t bf[4][2];
 #pragma unroll
-        for (int ni = 0; ni < 4; ni++) {
-          bf[ni][0] = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(lut) + ((br[ni] >> (16 * p)) & 0xC));
-          bf[ni][1] = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(lut) + ((br[ni] >> (16 * p + 8)) & 0xC));
+        for (int ni = 0; ni < 4; ni++) {                            // B word = table column of the code: one LDS
+          bf[ni][0] = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(lut) + __byte_perm(br[ni], 0, 0x4440 + 2 * p));
+          bf[ni][1] = *reinterpret_cast<const uint32_t *>(reinterpret_cast<const unsigned char *>(lut) + __byte_perm(br[ni], 0, 0x4441 + 2 * p));
         }
 #pragma unroll
-        for (int mi = 0; mi < 4; mi++) {
+        for (int mi = 0; mi < 4; mi++) {                            // A word = weight << (8 * code); shf.wrap reads 5 bits only
           uint32_t af[4];
-          af[0] = w0 << ((ar[mi][0] >> (16 * p)) & 0x18);
-          af[1] = w0 << ((ar[mi][1] >> (16 * p)) & 0x18);
-          af[2] = w1 << ((ar[mi][0] >> (16 * p + 8)) & 0x18);
-          af[3] = w1 << ((ar[mi][1] >> (16 * p + 8)) & 0x18);
+          af[0] = __funnelshift_l(0u, w0, ar[mi][0] >> (16 * p));
+          af[1] = __funnelshift_l(0u, w0, ar[mi][1] >> (16 * p));
+          af[2] = __funnelshift_l(0u, w1, ar[mi][0] >> (16 * p + 8));
+          af[3] = __funnelshift_l(0u, w1, ar[mi][1] >> (16 * p + 8));
 #pragma unroll
           for (int ni = 0; ni < 4; ni++) imma16832(acc[mi][ni], af, bf[ni][0], bf[ni][1]);
         }
