@@ -149,6 +149,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--core-only", action="store_true", help="skip the em_path / called_path extras (profiling runs)")
     ap.add_argument("--n-ind", type=int, default=N_IND)
     ap.add_argument("--n-sites", type=int, default=N_SITES)
     args = ap.parse_args()
@@ -239,7 +240,7 @@ def main():
 
     # ---- the literal default of the reference for this config (no --indep_geno): per pair-site EM (K2b) ----
     em = None
-    if rank == 0 and world == 1:
+    if rank == 0 and world == 1 and not args.core_only:
         pe = nb.Params(n_ind=n_ind, n_sites=n_sites, in_probs=True, indep_geno=False, evol_model=2)
         ge = nb.NgsDistB200(pe, device=local)
         ge.push_sites_device(raw_dev.data_ptr(), 0, n_sites)
@@ -251,6 +252,42 @@ def main():
         ge.close()
         em = {"workload": "same data, default --probs (no --indep_geno): per pair-site EM (emOptim2.cpp em2), kernel k_dist_em",
               "ms_per_matrix": statistics.median(em_ms), "value": pairs(n_ind) * n_sites / (statistics.median(em_ms) * 1e-3), "unit": UNIT}
+
+    # ---- called genotypes (BASELINE configs[3] geometry, reduced site count): exact int8 tensor-core contraction (K2c) ----
+    called = None
+    if rank == 0 and world == 1 and (n_ind, n_sites) == (N_IND, N_SITES) and not args.core_only:
+        cn, cs = 5000, 100_000
+        pc = nb.Params(n_ind=cn, n_sites=cs, in_probs=True, call_geno=True, pairwise_del=False, evol_model=0)
+        gc = nb.NgsDistB200(pc, device=local)
+        chunk = 4096
+        buf = torch.empty((chunk, cn, 3), dtype=torch.float64, device="cuda")
+        fe_ms = 0.0
+        for s0 in range(0, cs, chunk):
+            m = min(chunk, cs - s0)
+            gc.synth_raw_device(buf.data_ptr(), SEED, 0.05, s0, m)
+            gc.push_sites_device(buf.data_ptr(), s0, m)
+            fe_ms += gc.timing().frontend_ms
+        del buf
+        gc.frontend()
+        out_c = torch.empty((cn, cn), dtype=torch.float64).pin_memory()
+        gc.distances_raw(None, 0, 1, out_c.data_ptr())          # warm-up
+        c_ms = []
+        for _ in range(3):
+            gc.distances_raw(None, 0, 1, out_c.data_ptr())
+            tc = gc.timing()
+            c_ms.append(tc.dist_ms)
+        imma_peak = nb.probe_int8_tmacs(local)
+        k_ms = statistics.median(c_ms)
+        exe = tc.dist_imma * 4096.0 / (k_ms * 1e-3) * 1e-12
+        called = {"workload": "C4 geometry at 1/50 of the sites: %d ind x %d sites, 5 %% missing, --call_geno (integer path, bit-exact), kernel k_dist_imma" % (cn, cs),
+                  "kernel_ms": k_ms, "value": pairs(cn) * cs / (k_ms * 1e-3), "unit": UNIT,
+                  "frontend_ms": fe_ms, "frontend_gbs_raw": cn * cs * 24 / (fe_ms * 1e-3) * 1e-9,
+                  "roofline": {"bound": "tensor", "kernel": "k_dist_imma (mma.sync int8 IMMA.16832)", "achieved": exe, "peak": imma_peak,
+                               "unit": "TMAC/s", "frac": exe / imma_peak,
+                               "peak_source": "live register-only IMMA.16832 issue-rate probe in this run",
+                               "note": "4 int8 MAC per pair-site (one-hot code x table column); operands are expanded in registers from 2-bit codes"}}
+        gc.close()
+        del out_c
 
     units_step = pairs(n_ind) * n_sites                # nominal pair-site evaluations per step per rank
     value = units_step * world * args.steps / (ms_total * 1e-3)
@@ -279,7 +316,7 @@ def main():
             "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
             "data": "synthetic",
             "config": {"workload": WORKLOAD if (n_ind, n_sites) == (N_IND, N_SITES) else "synthetic GL %d x %d --indep_geno -m 2" % (n_ind, n_sites),
-                       "n_ind": n_ind, "n_sites": n_sites, "pairs": pairs(n_ind), "l2": "inputs_larger_than_l2 (1.2 GB raw, 2.4 GB packed operands)",
+                       "n_ind": n_ind, "n_sites": n_sites, "pairs": pairs(n_ind), "l2": "inputs_larger_than_l2 (1.2 GB raw, 1.6 GB packed operands + 0.4 GB B2 plane)",
                        "sharding": "one independent job per GPU, no collective", "timed": "front end + contraction + epilogue + D2H of the matrix"},
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n_sites * n_ind * 24, "d2h_bytes_per_step": n_ind * n_ind * 8,
@@ -287,7 +324,7 @@ def main():
             "gpu_launches": n_launch,
             "roofline": {"bound": "tensor", "kernel": "k_dist_dmma (FP64 DMMA.8x8x4 contraction)", "achieved": achieved, "peak": peak,
                          "unit": "TFLOP/s", "frac": achieved / peak, "traffic": traffic,
-                         "traffic_note": "DRAM bytes read+written by one k_dist_dmma launch (ncu --set full, profiles/r01_ncu_summary.md); operands are 2.4 GB",
+                         "traffic_note": "DRAM bytes read+written by one k_dist_dmma launch (ncu --set full, profiles/r01_ncu_summary.md); operands are 1.6 GB",
                          "peak_source": "live DMMA.8x8x4 issue-rate probe in this run (MEASURED_PEAKS.json has no FP64 figure; cuBLAS Dgemm measured 35.5)",
                          "executed_flops_per_launch": tim.dist_dmma * 512.0, "kernel_ms": dist_ms,
                          "useful_tflops_at_6flop_per_pair_site": useful, "useful_frac": useful / peak,
@@ -297,6 +334,8 @@ def main():
         }
         if em is not None:
             line["em_path"] = em
+        if called is not None:
+            line["called_path"] = called
         if world == 1 and not args.no_cpu_baseline:
             import oracle
             if oracle.have_ref():

@@ -216,6 +216,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_imma(ImmaArgs a) {
   }
 }
 
+// register-only IMMA loop: the int8 tensor issue-rate ceiling of mma.sync on this part (roofline denominator of K2c)
+__global__ void k_imma_peak(int *out, int iters) {
+  int c[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; i++) c[i][0] = c[i][1] = c[i][2] = c[i][3] = 0;
+  const uint32_t a[4] = {threadIdx.x, threadIdx.x * 3u, 7u, 9u};
+  const uint32_t b0 = threadIdx.x + 1u, b1 = 5u;
+  for (int it = 0; it < iters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) imma16832(c[i], a, b0, b1);
+  }
+  int s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1] + c[i][2] + c[i][3];
+  if (s == 0x12345678) out[0] = s;
+}
+
 struct EpiIntArgs {
   const int32_t *partials;    // [n_splits][n_tiles][16384] fragment order
   const ngsd_tile *tiles;
@@ -346,4 +363,31 @@ cudaError_t ngsd_launch_epilogue_int(ngsd_ctx *ctx, uint32_t n_splits, uint64_t 
   k_zero_diag_int<<<(unsigned) ((ctx->n_ind + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_out, ctx->d_num, ctx->d_cntout, ctx->n_ind);
   k_epilogue_int<<<dim3(ctx->n_tiles, 16), 256, 0, ctx->stream>>>(a);
   return cudaGetLastError();
+}
+
+extern "C" int ngsd_probe_int8_tmacs(int device, double *imma_tmacs) {
+  if (cudaSetDevice(device) != cudaSuccess) return NGSD_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return NGSD_ERR_CUDA;
+  int *d = nullptr;
+  if (cudaMalloc(&d, 64) != cudaSuccess) return NGSD_ERR_CUDA;
+  const int iters = 8192, warps = 16, nsm = prop.multiProcessorCount;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int r = 0; r < 4; r++) {
+    cudaEventRecord(e0);
+    k_imma_peak<<<nsm, warps * 32>>>(d, iters);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(d); return NGSD_ERR_CUDA; }
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(d);
+  *imma_tmacs = (double) nsm * warps * iters * 8 * 4096.0 / (best * 1e-3) * 1e-12;
+  return NGSD_OK;
 }

@@ -19,10 +19,16 @@
 #include <time.h>
 #include <zlib.h>
 
+#include <condition_variable>
+#include <mutex>
+#include <algorithm>
+#include <functional>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../../include/ngsdist_b200.h"
+#include "fast_io.h"
 
 static const char *kVersion = "1.0.10-b200";
 
@@ -162,10 +168,8 @@ static void numeric_fields(const std::string &line, std::vector<double> &out) {
     if (!*s) break;
     const char *e = s;
     while (*e && *e != ' ' && *e != '\t') e++;
-    char *endp = nullptr;
-    std::string tok(s, e - s);
-    double v = strtod(tok.c_str(), &endp);
-    if (endp && *endp == '\0' && endp != tok.c_str()) out.push_back(v);
+    double v;
+    if (fastio::parse_number(s, e, &v)) out.push_back(v);
     s = e;
   }
 }
@@ -214,22 +218,89 @@ static void check_positions(const Pars &p) {   // only validated, never used (mo
 
 // ---- writer (ngsDist.cpp:282-287; "%.10f" as gen_func.cpp:479-496) ------------------------------------------------
 
-static void write_matrix(FILE *fh, const std::vector<std::string> &lab, const double *d, uint64_t n) {
-  fprintf(fh, "\n%lu\n", n);
-  std::string row;
-  char num[64];
-  for (uint64_t i = 0; i < n; i++) {
-    row.assign(lab[i]);
+static void format_rows(const std::vector<std::string> &lab, const double *d, uint64_t n, uint64_t r0, uint64_t r1, std::string *out) {
+  out->clear();
+  char num[512];
+  for (uint64_t i = r0; i < r1; i++) {
+    out->append(lab[i]);
     for (uint64_t j = 0; j < n; j++) {
-      int len = snprintf(num, sizeof(num), "\t%.10f", d[i * n + j]);
-      row.append(num, len);
+      const double v = d[i * n + j];
+      num[0] = '\t';
+      int len;
+      if (fabs(v) < 4503599627370496.0 || !(v == v) || isinf(v)) len = 1 + fastio::fmt_fixed10(num + 1, v);
+      else len = snprintf(num, sizeof(num), "\t%.10f", v);
+      out->append(num, len);
     }
-    row.push_back('\n');
-    fwrite(row.data(), 1, row.size(), fh);
+    out->push_back('\n');
   }
 }
 
+// One matrix in the reference's layout: "\n<n>\n" then label<TAB>v0<TAB>...<TAB>v{n-1} per row, "%.10f" values.
+// Rows are formatted by n_threads threads in bands (bounded memory) and written in order.
+static void write_matrix(FILE *fh, const std::vector<std::string> &lab, const double *d, uint64_t n, unsigned n_threads) {
+  fprintf(fh, "\n%lu\n", n);
+  const unsigned T = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>(n_threads, n / 64 + 1));
+  const uint64_t band = std::max<uint64_t>(1, std::min<uint64_t>(n, ((uint64_t) 64 << 20) / (n * 14 + 64) + 1));   // ~64 MB of text per round
+  std::vector<std::string> parts(T);
+  for (uint64_t b0 = 0; b0 < n; b0 += band) {
+    const uint64_t b1 = std::min(n, b0 + band), rows = b1 - b0;
+    if (T == 1) {
+      format_rows(lab, d, n, b0, b1, &parts[0]);
+    } else {
+      std::vector<std::thread> th;
+      for (unsigned t = 0; t < T; t++)
+        th.emplace_back(format_rows, std::cref(lab), d, n, b0 + rows * t / T, b0 + rows * (t + 1) / T, &parts[t]);
+      for (auto &x : th) x.join();
+    }
+    for (unsigned t = 0; t < T; t++) fwrite(parts[t].data(), 1, parts[t].size(), fh);
+  }
+}
+
+// --selftest_io N: the exact fast "%.10f" and the fast number parser against libc on N random values (no GPU needed)
+static int selftest_io(uint64_t n) {
+  uint64_t x = 0x9E3779B97F4A7C15ull, bad = 0;
+  auto next = [&]() { x ^= x << 13; x ^= x >> 7; x ^= x << 17; return x; };
+  char a[512], b[512];
+  auto check = [&](double v) {
+    const int la = fastio::fmt_fixed10(a, v);
+    a[la] = 0;
+    snprintf(b, sizeof(b), "%.10f", v);
+    if (strcmp(a, b) != 0) { if (bad < 10) fprintf(stderr, "fmt mismatch: %s vs %s (%a)\n", a, b, v); bad++; }
+    if (v == v) {                                   // parse back what libc prints with 17 / 10 / 6 digits
+      for (const char *f : {"%.17g", "%.10f", "%.6f", "%g"}) {
+        snprintf(b, sizeof(b), f, v);
+        double w1 = 0, w2 = strtod(b, nullptr);
+        const bool ok = fastio::parse_number(b, b + strlen(b), &w1);
+        if (!ok || memcmp(&w1, &w2, 8) != 0) { if (bad < 10) fprintf(stderr, "parse mismatch on '%s'\n", b); bad++; }
+      }
+    }
+  };
+  const double specials[] = {0.0, -0.0, 1.0, 0.5, 0.25, 0.125, 1e-10, 5e-11, 0.00000000005, 1.00000000005, 2.5e-10, 0.99999999995,
+                             123456.00000000005, INFINITY, -INFINITY, NAN, -NAN, 4503599627370495.5, 1e300, 1e-300, 4.9e-324, 0.1, 0.3, 2.0 / 3};
+  for (double v : specials) { check(v); check(-v); }
+  for (uint64_t k = 0; k < n; k++) {
+    const uint64_t r = next();
+    double v;
+    switch (k % 6) {
+      case 0: v = (double) (r >> 11) * 0x1p-53; break;                                // [0,1)
+      case 1: v = (double) (r >> 11) * 0x1p-53 * 10.0; break;                         // typical distances
+      case 2: v = (double) (r % 20000000001ull) * 5e-11; break;                        // near decimal half-way points
+      case 3: v = ldexp((double) (r >> 11) * 0x1p-53, (int) (next() % 80) - 60); break;
+      case 4: memcpy(&v, &r, 8); if (!(fabs(v) < 1e15)) v = 0.75; break;               // random bit patterns
+      default: v = (double) ((int64_t) (r % 2000001) - 1000000) / 1e6; break;         // short decimals
+    }
+    check(v);
+  }
+  double w;
+  const char *not_numbers[] = {"", "-", "+", ".", "abc", "1.2.3", "1e", "0x", "--1", "1-", "marker"};
+  for (const char *t : not_numbers)
+    if (fastio::parse_number(t, t + strlen(t), &w)) { fprintf(stderr, "parsed a non-number: '%s'\n", t); bad++; }
+  fprintf(stderr, "selftest_io: %lu values, %lu mismatches\n", n, bad);
+  return bad ? 1 : 0;
+}
+
 int main(int argc, char **argv) {
+  if (argc >= 2 && strcmp(argv[1], "--selftest_io") == 0) return selftest_io(argc >= 3 ? (uint64_t) atol(argv[2]) : 1000000);
   Pars p;
   parse_args(&p, argc, argv);
   const uint64_t n_comb = (uint64_t) ((pow((double) p.n_ind, 2) - p.n_ind) / 2);
@@ -282,80 +353,143 @@ int main(int argc, char **argv) {
   if (ngsd_create(&cfg, &ctx)) die(cfg.evol_model > 2 ? "gen_dist" : "main", ngsd_last_error(nullptr));
 
   // ---- read + front end, chunk by chunk (replaces read_geno + ngsDist.cpp:161-174) ----
+  // A reader thread fills one of two pinned chunk buffers (file read / inflate, text parsing on --n_threads threads)
+  // while the main thread pushes the other one through the front end: disk, parser, PCIe and GPU overlap.
   if (p.verbose >= 1) fprintf(stderr, "==> Reading genotype data\n");
   gzFile fh = open_gz(p.in_geno, p.in_bin ? "rb" : "r");
   if (!fh) die("read_geno", "cannot open GENO file!");
   const uint64_t per_site = p.n_ind * 3;
   uint64_t chunk = ((uint64_t) 32 << 20) / (per_site * sizeof(double)) / 64 * 64;
   if (chunk < 64) chunk = 64;
-  double *raw = codes_input ? nullptr : (double *) ngsd_host_alloc(chunk * per_site * sizeof(double));
-  std::vector<int8_t> codes(codes_input ? chunk * p.n_ind : 0);
-  if (!codes_input && !raw) die("main", "cannot allocate pinned host buffer");
-  std::string line;
-  std::vector<double> fields;
+  if (const char *e = getenv("NGSD_CLI_CHUNK")) chunk = std::max<uint64_t>(64, (uint64_t) atol(e) / 64 * 64);   // tests: force many chunks
   const uint64_t n_geno = p.in_probs ? 3 : 1;
-  uint64_t s_first_data = 0;   // becomes 1 once the first data line was seen (the header rule only applies before that)
-  for (uint64_t s0 = 0; s0 < p.n_sites; s0 += chunk) {
-    const uint64_t n = (p.n_sites - s0 < chunk) ? p.n_sites - s0 : chunk;
-    if (p.in_bin) {
-      const uint64_t bytes = n * per_site * sizeof(double);
-      uint64_t got = 0;
-      while (got < bytes) {
-        const unsigned want = (unsigned) ((bytes - got > (1u << 30)) ? (1u << 30) : bytes - got);
-        int r = gzread(fh, (char *) raw + got, want);
-        if (r <= 0) {
-          if (gzeof(fh)) die("read_geno", "GENO file at premature EOF. Check GENO file and number of sites!");
-          die("read_geno", "cannot read binary GENO file. Check GENO file and number of sites!");
-        }
-        got += (uint64_t) r;
+  struct Slot {
+    double *raw = nullptr;
+    std::vector<int8_t> codes;
+    uint64_t s0 = 0, n = 0;
+    bool full = false;
+  } slots[2];
+  for (auto &sl : slots) {
+    if (codes_input) sl.codes.resize(chunk * p.n_ind);
+    else if (!(sl.raw = (double *) ngsd_host_alloc(chunk * per_site * sizeof(double)))) die("main", "cannot allocate pinned host buffer");
+  }
+  std::mutex mu;
+  std::condition_variable cv;
+
+  auto fill_binary = [&](Slot &sl) {
+    const uint64_t bytes = sl.n * per_site * sizeof(double);
+    uint64_t got = 0;
+    while (got < bytes) {
+      const unsigned want = (unsigned) ((bytes - got > (1u << 30)) ? (1u << 30) : bytes - got);
+      int r = gzread(fh, (char *) sl.raw + got, want);
+      if (r <= 0) {
+        if (gzeof(fh)) die("read_geno", "GENO file at premature EOF. Check GENO file and number of sites!");
+        die("read_geno", "cannot read binary GENO file. Check GENO file and number of sites!");
       }
-    } else {
-      for (uint64_t s = 0; s < n; s++) {
-        for (;;) {
-          if (!read_line(fh, line)) {
-            if (gzeof(fh)) die("read_geno", "GENO file at premature EOF. Check GENO file and number of sites!");
-            die("read_geno", "cannot read GZip GENO file. Check GENO file and number of sites!");
-          }
-          if (line.empty()) { fields.clear(); break; }        // consumes a site (read_data.cpp:58-59)
-          numeric_fields(line, fields);
-          if (fields.empty() || (s_first_data == 0 && s0 + s == 0 && fields.size() < p.n_ind * n_geno)) {
-            fprintf(stderr, "> Header found! Skipping line...\n");
-            continue;                                           // header: does not consume a site
-          }
-          break;
+      got += (uint64_t) r;
+    }
+  };
+  bool first_data_seen = false;   // the header rule only applies before the first data line
+  std::vector<std::string> lines;
+  std::vector<std::vector<double>> fields;
+  auto fill_text = [&](Slot &sl) {
+    uint64_t s = 0;
+    while (s < sl.n) {
+      // (1) sequential: the next batch of lines, at most one per site still missing
+      const uint64_t want = sl.n - s;
+      if (lines.size() < want) { lines.resize(want); fields.resize(want); }
+      for (uint64_t k = 0; k < want; k++)
+        if (!read_line(fh, lines[k])) {
+          if (gzeof(fh)) die("read_geno", "GENO file at premature EOF. Check GENO file and number of sites!");
+          die("read_geno", "cannot read GZip GENO file. Check GENO file and number of sites!");
         }
-        if (line.empty()) {
-          fprintf(stderr, "> Empty line at site %lu: treated as missing data for every individual\n", s0 + s);
+      // (2) parallel: tokenise + convert (the expensive part of a text input)
+      const unsigned T = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>(p.n_threads, want / 8 + 1));
+      auto parse_range = [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) numeric_fields(lines[k], fields[k]); };
+      if (T == 1) {
+        parse_range(0, want);
+      } else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; t++) th.emplace_back(parse_range, want * t / T, want * (t + 1) / T);
+        for (auto &x : th) x.join();
+      }
+      // (3) sequential: the reference's per-line rules, in file order
+      for (uint64_t k = 0; k < want; k++) {
+        const std::string &line = lines[k];
+        const std::vector<double> &f = fields[k];
+        if (line.empty()) {                                     // consumes a site (read_data.cpp:58-59)
+          fprintf(stderr, "> Empty line at site %lu: treated as missing data for every individual\n", sl.s0 + s);
           for (uint64_t i = 0; i < p.n_ind; i++) {
-            if (codes_input) codes[s * p.n_ind + i] = -1;
-            else raw[(s * p.n_ind + i) * 3 + 0] = raw[(s * p.n_ind + i) * 3 + 1] = raw[(s * p.n_ind + i) * 3 + 2] = p.in_logscale ? log(1.0 / 3) : 1.0 / 3;
+            if (codes_input) sl.codes[s * p.n_ind + i] = -1;
+            else sl.raw[(s * p.n_ind + i) * 3 + 0] = sl.raw[(s * p.n_ind + i) * 3 + 1] = sl.raw[(s * p.n_ind + i) * 3 + 2] = p.in_logscale ? log(1.0 / 3) : 1.0 / 3;
           }
+          s++;
           continue;
         }
-        s_first_data = 1;
-        if (fields.size() < p.n_ind * n_geno) die("read_geno", "wrong GENO file format. Less fields than expected!");
-        const double *ptr = fields.data() + (fields.size() - p.n_ind * n_geno);   // last n_ind*n_geno numeric columns
+        if (f.empty() || (!first_data_seen && sl.s0 + s == 0 && f.size() < p.n_ind * n_geno)) {
+          fprintf(stderr, "> Header found! Skipping line...\n");
+          continue;                                             // header: does not consume a site
+        }
+        first_data_seen = true;
+        if (f.size() < p.n_ind * n_geno) die("read_geno", "wrong GENO file format. Less fields than expected!");
+        const double *ptr = f.data() + (f.size() - p.n_ind * n_geno);   // last n_ind*n_geno numeric columns
         if (codes_input) {
           for (uint64_t i = 0; i < p.n_ind; i++) {
             int g = (int) ptr[i];
             if (g > 2) die("read_geno", "wrong GENO file format. Genotypes must be coded as {-1,0,1,2} !");
-            codes[s * p.n_ind + i] = (int8_t) (g < 0 ? -1 : g);
+            sl.codes[s * p.n_ind + i] = (int8_t) (g < 0 ? -1 : g);
           }
         } else {
-          memcpy(raw + s * per_site, ptr, per_site * sizeof(double));
+          memcpy(sl.raw + s * per_site, ptr, per_site * sizeof(double));
         }
+        s++;
       }
     }
-    int rc = codes_input ? ngsd_push_genotypes(ctx, codes.data(), s0, n) : ngsd_push_sites(ctx, raw, s0, n);
-    if (rc) die("read_geno", ngsd_last_error(ctx));
+  };
+  std::thread reader([&]() {
+    int w = 0;
+    for (uint64_t s0 = 0; s0 < p.n_sites; s0 += chunk, w ^= 1) {
+      Slot &sl = slots[w];
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return !sl.full; });
+      }
+      sl.s0 = s0;
+      sl.n = (p.n_sites - s0 < chunk) ? p.n_sites - s0 : chunk;
+      if (p.in_bin) fill_binary(sl); else fill_text(sl);
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        sl.full = true;
+      }
+      cv.notify_all();
+    }
+  });
+  {
+    int r = 0;
+    for (uint64_t s0 = 0; s0 < p.n_sites; s0 += chunk, r ^= 1) {
+      Slot &sl = slots[r];
+      {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return sl.full; });
+      }
+      int rc = codes_input ? ngsd_push_genotypes(ctx, sl.codes.data(), sl.s0, sl.n) : ngsd_push_sites(ctx, sl.raw, sl.s0, sl.n);
+      if (rc) die("read_geno", ngsd_last_error(ctx));
+      {
+        std::lock_guard<std::mutex> lk(mu);
+        sl.full = false;
+      }
+      cv.notify_all();
+    }
   }
+  reader.join();
   {  // the file must be at EOF (read_data.cpp:106-109)
     char extra;
     int r = gzread(fh, &extra, 1);
     if (!(r <= 0 && gzeof(fh))) die("read_geno", "GENO file not at EOF. Check GENO file and number of sites!");
   }
   gzclose(fh);
-  if (raw) ngsd_host_free(raw);
+  for (auto &sl : slots)
+    if (sl.raw) ngsd_host_free(sl.raw);
   if (ngsd_frontend(ctx)) die("read_geno", ngsd_last_error(ctx));
 
   if (p.verbose >= 2) fprintf(stderr, "==> Setting seed for random number generator\n");
@@ -396,7 +530,7 @@ int main(int argc, char **argv) {
                   cnt[i1 * p.n_ind + i2], num[i1 * p.n_ind + i2] / (double) cnt[i1 * p.n_ind + i2], labels[i1].c_str(), i1,
                   labels[i2].c_str(), i2);
     if (p.verbose >= 2) fprintf(stderr, "> Printing distance matrix\n");
-    write_matrix(out_fh, labels, dist.data(), p.n_ind);
+    write_matrix(out_fh, labels, dist.data(), p.n_ind, p.n_threads);
   }
   fclose(out_fh);
   if (p.verbose >= 1) fprintf(stderr, "==> Freeing memory...\n");

@@ -44,6 +44,53 @@ def test_cli_argument_errors(args, msg):
     assert "ERROR: [" in r.stderr and msg in r.stderr
 
 
+def test_cli_io_selftest_exact_formatter_and_parser():
+    """The writer's exact fast "%.10f" and the reader's fast number parser against libc on 2e6 random values (+ specials,
+    decimal half-way points, non-numbers): must be byte / bit identical."""
+    r = run_cli(["--selftest_io", "2000000"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "0 mismatches" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [c for c in MAN["binary"] + MAN["text"] if c["n_sites"] > 64][:6], ids=lambda c: c["name"])
+def test_cli_chunked_threaded_reader(case, tmp_path):
+    """Many 64-site chunks through the double-buffered reader thread (NGSD_CLI_CHUNK) give the same file as one chunk."""
+    outs = []
+    for chunk in ("64", "1000000"):
+        out = str(tmp_path / ("out%s.dist" % chunk))
+        args = ["--geno", os.path.join(GOLDEN, case["input"]), "--n_ind", str(case["n_ind"]), "--n_sites", str(case["n_sites"]),
+                "--out", out, "--n_threads", "3", "--verbose", "0"] + case["flags"]
+        r = run_cli(args, env=dict(os.environ, NGSD_CLI_CHUNK=chunk))
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(open(out).read())
+    assert outs[0] == outs[1]
+
+
+@pytest.mark.gpu
+def test_cli_text_reader_many_chunks_matches_binary_input(tmp_path):
+    """C1-style text input (header + 3 leading label columns, gz) read in 64-site chunks by the threaded parser gives
+    the same .dist as the same values read from the binary file."""
+    import gzip
+    from util import load_bin
+    n_ind, n_sites = 24, 400
+    raw = load_bin("g24x400.bin", n_ind, n_sites)
+    txt = str(tmp_path / "g.txt.gz")
+    with gzip.open(txt, "wt") as fh:
+        fh.write("marker\tallele1\tallele2\t" + "\t".join("Ind%d" % (i // 3) for i in range(n_ind * 3)) + "\n")
+        for s in range(n_sites):
+            fh.write("chr1_%d\tA\tC\t" % s + "\t".join(repr(float(v)) for v in raw[s].reshape(-1)) + "\n")
+    outs = []
+    for geno, chunk in ((os.path.join(GOLDEN, "g24x400.bin"), "1000000"), (txt, "64")):
+        out = str(tmp_path / ("o%s.dist" % chunk))
+        r = run_cli(["--geno", geno, "--probs", "--n_ind", str(n_ind), "--n_sites", str(n_sites), "--out", out, "--n_threads", "4",
+                     "--verbose", "0", "--indep_geno", "--n_boot_rep", "2", "--boot_block_size", "10", "--seed", "5"],
+                    env=dict(os.environ, NGSD_CLI_CHUNK=chunk))
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(open(out).read())
+    assert outs[0] == outs[1]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", MAN["binary"] + MAN["text"], ids=lambda c: c["name"])
 def test_cli_reproduces_reference_dist_files(case, tmp_path):

@@ -13,7 +13,7 @@ def main(path):
         base = re.sub(r"<.*>", "", k)
         if base == "k_frontend" and not cur:
             cur = [(k, us)]
-        elif cur and base in ("k_dist_dmma", "k_zero_diag", "k_epilogue"):
+        elif cur and base in ("k_dist_dmma", "k_cvec", "k_zero_diag", "k_epilogue"):
             cur.append((k, us))
             if base == "k_epilogue":
                 steps.append(cur); cur = []
