@@ -9,6 +9,7 @@
 // buffer; input is streamed in chunks (the whole data set is never held on the host); an empty text line consumes a
 // site like the reference does but yields a missing site (1/3,1/3,1/3) instead of the reference's accidental (0,0,0);
 // --verbose >= 5 per-site dumps are not produced; additive flag --device N selects the GPU.
+#include <fcntl.h>
 #include <getopt.h>
 #include <math.h>
 #include <stdint.h>
@@ -17,6 +18,7 @@
 #include <string.h>
 #include <sys/stat.h>
 #include <time.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <condition_variable>
@@ -376,9 +378,25 @@ int main(int argc, char **argv) {
   std::mutex mu;
   std::condition_variable cv;
 
+  // A plain (not gzip-compressed) binary file is read with read(2) straight into the pinned buffer; zlib's transparent
+  // mode (what gzopen gives the reference, read_data.cpp:24-31) is kept for stdin and for compressed binaries.
+  int raw_fd = -1;
+  if (p.in_bin && strcmp(p.in_geno, "-") != 0) {
+    FILE *probe = fopen(p.in_geno, "rb");
+    unsigned char magic[2] = {0, 0};
+    const bool is_gz = probe && fread(magic, 1, 2, probe) == 2 && magic[0] == 0x1f && magic[1] == 0x8b;
+    if (probe) fclose(probe);
+    if (!is_gz) raw_fd = open(p.in_geno, O_RDONLY);
+  }
   auto fill_binary = [&](Slot &sl) {
     const uint64_t bytes = sl.n * per_site * sizeof(double);
     uint64_t got = 0;
+    while (raw_fd >= 0 && got < bytes) {
+      const ssize_t r = read(raw_fd, (char *) sl.raw + got, bytes - got);
+      if (r == 0) die("read_geno", "GENO file at premature EOF. Check GENO file and number of sites!");
+      if (r < 0) die("read_geno", "cannot read binary GENO file. Check GENO file and number of sites!");
+      got += (uint64_t) r;
+    }
     while (got < bytes) {
       const unsigned want = (unsigned) ((bytes - got > (1u << 30)) ? (1u << 30) : bytes - got);
       int r = gzread(fh, (char *) sl.raw + got, want);
@@ -484,8 +502,13 @@ int main(int argc, char **argv) {
   reader.join();
   {  // the file must be at EOF (read_data.cpp:106-109)
     char extra;
-    int r = gzread(fh, &extra, 1);
-    if (!(r <= 0 && gzeof(fh))) die("read_geno", "GENO file not at EOF. Check GENO file and number of sites!");
+    if (raw_fd >= 0) {
+      if (read(raw_fd, &extra, 1) != 0) die("read_geno", "GENO file not at EOF. Check GENO file and number of sites!");
+      close(raw_fd);
+    } else {
+      int r = gzread(fh, &extra, 1);
+      if (!(r <= 0 && gzeof(fh))) die("read_geno", "GENO file not at EOF. Check GENO file and number of sites!");
+    }
   }
   gzclose(fh);
   for (auto &sl : slots)

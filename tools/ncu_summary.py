@@ -10,6 +10,7 @@ KEYS = [
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "warps active %"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "SM throughput %"),
     ("sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active", "DMMA pipe % (active)"),
+    ("sm__inst_executed_pipe_tensor_subpipe_imma.avg.pct_of_peak_sustained_active", "IMMA pipe % (active)"),
     ("sm__ops_path_tensor_src_fp64.sum.pct_of_peak_sustained_elapsed", "FP64 tensor ops % of peak (elapsed)"),
     ("sm__ops_path_tensor_src_fp64.sum.per_second", "FP64 tensor FMA/ns"),
     ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "FP64 (DFMA) pipe %"),
