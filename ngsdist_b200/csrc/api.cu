@@ -469,7 +469,7 @@ static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n
   }
 
   // K splits of the word list; an int32 accumulator must hold max_byte * weight * sites of one split
-  int grid = ctx->n_sm;
+  int grid = ctx->n_sm * ngsd_imma_ctas_per_sm();
   std::vector<uint32_t> splits = plan_splits((uint32_t) n_words, ctx->n_tiles, (double) ctx->n_tiles, grid);
   {
     const uint64_t per_word = (uint64_t) std::max(ctx->int_max_byte, 1) * std::min<uint32_t>(maxw, 127) * 64;

@@ -30,6 +30,9 @@
 
 namespace {
 
+#ifndef NGSD_IMMA_CTAS
+#define NGSD_IMMA_CTAS 1
+#endif
 constexpr int kStages = 8;
 constexpr int kConsumerWarps = 8;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;
@@ -94,7 +97,7 @@ struct ImmaArgs {
 
 enum : uint32_t { kFirst = 1u, kLast = 2u, kExit = 8u };
 
-__global__ void __launch_bounds__(kThreads, 1) k_dist_imma(ImmaArgs a) {
+__global__ void __launch_bounds__(kThreads, NGSD_IMMA_CTAS) k_dist_imma(ImmaArgs a) {
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t) kStages * kStageBytes);
   uint64_t *empty = full + kStages;
@@ -310,6 +313,8 @@ bool ngsd_int_lut(const double *score, bool pairwise_del, uint32_t lut[4], doubl
   *max_byte = mx;
   return true;
 }
+
+int ngsd_imma_ctas_per_sm() { return NGSD_IMMA_CTAS; }
 
 cudaError_t ngsd_launch_dist_imma(ngsd_ctx *ctx, uint32_t n_units, int grid) {
   static bool attr_set[64] = {};

@@ -17,6 +17,11 @@ constexpr double kNegInfClamp = -1e15;               // "INF" of shared/gen_func
 constexpr double kEps = 1e-5;                        // EPSILON, shared/gen_func.hpp:16
 constexpr double kThird = 0x1.5555555555555p-2;      // exp(log(1/3)) as glibc evaluates it
 
+// One 32-byte sector per instruction (sm_100 has 256-bit global stores: STG.E.ENL2.256); p must be 32-byte aligned.
+__device__ __forceinline__ void st256(double *p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+
 struct FrontCfg {
   int kind;          // ngsd_input_kind
   int in_log;
@@ -259,12 +264,8 @@ __global__ void __launch_bounds__(512, EXACT ? 1 : 2) k_frontend(FrontCfg c, con
 #pragma unroll
     for (int g = 0; g < 3; g++) {
       const uint64_t o = base + (uint64_t) (g * 2 + h) * (16 * 32);
-      double2 *pa = reinterpret_cast<double2 *>(Apack + o);
-      double2 *pb = reinterpret_cast<double2 *>(Bpack + o);
-      pa[0] = make_double2(A[0][g], A[1][g]);
-      pa[1] = make_double2(A[2][g], A[3][g]);
-      pb[0] = make_double2(Bv[g][0], Bv[g][1]);
-      pb[1] = make_double2(Bv[g][2], Bv[g][3]);
+      st256(Apack + o, A[0][g], A[1][g], A[2][g], A[3][g]);
+      st256(Bpack + o, Bv[g][0], Bv[g][1], Bv[g][2], Bv[g][3]);
     }
   } else {
     // two planes: A = (p0, p1), B = (B0 - B2, B1 - B2), C = B2; chunk of 12 sites, k4-group = g*3 + h
@@ -273,16 +274,10 @@ __global__ void __launch_bounds__(512, EXACT ? 1 : 2) k_frontend(FrontCfg c, con
 #pragma unroll
     for (int g = 0; g < 2; g++) {
       const uint64_t o = base + (uint64_t) (g * 3 + h) * (16 * 32);
-      double2 *pa = reinterpret_cast<double2 *>(Apack + o);
-      double2 *pb = reinterpret_cast<double2 *>(Bpack + o);
-      pa[0] = make_double2(A[0][g], A[1][g]);
-      pa[1] = make_double2(A[2][g], A[3][g]);
-      pb[0] = make_double2(Bv[g][0] - Bv[2][0], Bv[g][1] - Bv[2][1]);
-      pb[1] = make_double2(Bv[g][2] - Bv[2][2], Bv[g][3] - Bv[2][3]);
+      st256(Apack + o, A[0][g], A[1][g], A[2][g], A[3][g]);
+      st256(Bpack + o, Bv[g][0] - Bv[2][0], Bv[g][1] - Bv[2][1], Bv[g][2] - Bv[2][2], Bv[g][3] - Bv[2][3]);
     }
-    double2 *pc = reinterpret_cast<double2 *>(Cplane + i * ldc + sgrp * 4);
-    pc[0] = make_double2(Bv[2][0], Bv[2][1]);
-    pc[1] = make_double2(Bv[2][2], Bv[2][3]);
+    st256(Cplane + i * ldc + sgrp * 4, Bv[2][0], Bv[2][1], Bv[2][2], Bv[2][3]);
   }
 
   nib[ty][tx] = bits;
