@@ -292,10 +292,16 @@ __global__ void __launch_bounds__(512, EXACT ? 1 : 2) k_frontend(FrontCfg c, con
 
 // The exact log-space sequence of the reference for one triple, out of line: the integer-path kernel below only needs
 // it for the rare triples its fast test cannot decide, and inlining it would cost that kernel its occupancy.
-__device__ __noinline__ unsigned called_code_exact(const FrontCfg &c, double x0, double x1, double x2, int *bad) {
+// (scalars by value and the result in one word: passing the parameter struct by reference would spill it to local
+// memory in every thread of the caller.)  Returns the code, + 4 when a NaN was found on the binary path.
+__device__ __noinline__ unsigned called_code_exact(int kind, int in_log, double N_thresh, double call_thresh, double x0, double x1, double x2) {
+  FrontCfg c;
+  c.kind = kind; c.in_log = in_log; c.call_geno = 1; c.pairwise_del = 0; c.planes = 3; c.int_path = 1;
+  c.N_thresh = N_thresh; c.call_thresh = call_thresh;
   double p[3];
-  if (!posterior(c, x0, x1, x2, p)) *bad |= 1;
-  return (p[0] == 1.0) ? 0u : (p[1] == 1.0) ? 1u : (p[2] == 1.0) ? 2u : 3u;   // one-hot or the uniform "missing" triple
+  const bool ok = posterior(c, x0, x1, x2, p);
+  const unsigned code = (p[0] == 1.0) ? 0u : (p[1] == 1.0) ? 1u : (p[2] == 1.0) ? 2u : 3u;   // one-hot or the uniform "missing" triple
+  return code | (ok ? 0u : 4u);
 }
 
 // Front end of the integer path (called genotypes / genotype input; dist_imma.cu): same thread mapping as k_frontend,
@@ -326,6 +332,7 @@ __global__ void __launch_bounds__(512, 2) k_frontend_codes(FrontCfg c, const dou
     }
   }
   unsigned cbits = 0xFF;                  // 2 bits per site; 3 = missing / padding
+  unsigned need_exact = 0;                // sites the fast test could not decide (near-ties, corner cases): rare
   int bad = 0;
 #pragma unroll
   for (int q = 0; q < 4; q++) {
@@ -336,9 +343,19 @@ __global__ void __launch_bounds__(512, 2) k_frontend_codes(FrontCfg c, const dou
         cg = gc[q] < 0 ? 3u : (unsigned) gc[q];                      // read_data.cpp:88-95: -1 = missing
         if (gc[q] > 2) { bad |= 2; cg = 3u; }
       } else if (!called_code_fast(c, A[q][0], A[q][1], A[q][2], cg)) {
-        cg = called_code_exact(c, A[q][0], A[q][1], A[q][2], &bad);
+        need_exact |= 1u << q;
+        cg = 3u;
       }
       cbits = (cbits & ~(3u << (2 * q))) | (cg << (2 * q));
+    }
+  }
+  if (need_exact) {                       // the reference's exact log-space sequence, values re-read (keeps the hot loop lean)
+    for (int q = 0; q < 4; q++) {
+      if (!((need_exact >> q) & 1u)) continue;
+      const double *x = raw + ((s_local0 + q) * n_ind + i) * 3;
+      unsigned cg = called_code_exact(c.kind, c.in_log, c.N_thresh, c.call_thresh, x[0], x[1], x[2]);
+      if (cg & 4u) bad |= 1;
+      cbits = (cbits & ~(3u << (2 * q))) | ((cg & 3u) << (2 * q));
     }
   }
   if (bad) atomicOr(err, bad);
