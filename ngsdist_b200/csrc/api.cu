@@ -415,7 +415,7 @@ static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n
     for (uint64_t b = 0; b < n_blocks; b++) maxw = std::max(maxw, block_counts[b]);
   const uint32_t layers = (maxw + 126) / 127;                  // site weights are int8 operand bytes: <= 127 per layer
   const bool do_count = ctx->cfg.pairwise_del != 0;
-  const uint64_t ent_max = do_count ? NW * (weighted ? maxw : 1) : 0;
+  const uint64_t ent_max = 0;   // the counts are a second int8 GEMM inside K2c: no K3 entry list
   const uint64_t bytes_w = (uint64_t) layers * nsp, bytes_ids = (uint64_t) layers * NW * sizeof(uint32_t);
   int rc = ensure_pinned(ctx, bytes_w + 2 * bytes_ids + ent_max * (sizeof(uint32_t) + sizeof(uint64_t)) + 256);
   if (rc) return rc;
@@ -448,8 +448,7 @@ static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n
       const uint64_t *p8 = (const uint64_t *) (h_w + (uint64_t) l * nsp + w * 64);
       if (p8[0] | p8[1] | p8[2] | p8[3] | p8[4] | p8[5] | p8[6] | p8[7]) { h_ids[n_words] = (uint32_t) w; h_layer[n_words] = l; n_words++; }
     }
-  uint64_t n_entries = 0;
-  if (do_count) n_entries = build_count_entries(ctx, block_counts, n_blocks, block_size, maxw, h_ew, h_em);
+  (void) h_ew; (void) h_em;
 
   const uint64_t n2 = ctx->n_ind * ctx->n_ind;
   if (ctx->n_tiles == 0 || n_words == 0) {   // a tile shard that owns nothing (or no active site): all-zero sums
@@ -486,12 +485,8 @@ static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n
   const uint32_t n_splits = (uint32_t) splits.size() - 1;
   const uint64_t n_units = (uint64_t) n_splits * ctx->n_tiles;
   grid = (int) std::min<uint64_t>(grid, std::max<uint64_t>(n_units, 1));
-  rc = ensure_dist_buffers(ctx, n_units / 2 + 1);            // int32 partials: half a slot per unit
+  rc = ensure_dist_buffers(ctx, do_count ? n_units + 1 : n_units / 2 + 1);   // int32 partials: sum tile (+ count tile) per unit
   if (rc) return rc;
-  if (do_count) {
-    rc = ensure_entries(ctx, n_entries);
-    if (rc) return rc;
-  }
   if (bytes_w > ctx->wsite_cap) {
     cudaFree(ctx->d_wsite);
     ctx->d_wsite = nullptr;
@@ -526,31 +521,17 @@ static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n
     NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_word_ids, h_ids, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_word_layer, h_layer, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   }
-  if (n_entries) {
-    NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_ent_word, h_ew, n_entries * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-    NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_ent_mask, h_em, n_entries * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
-  }
   int launches = 0;
   tick(ctx, 2);
-  if (do_count) NGSD_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
   tick(ctx, 3);
   if (n_words) {
-    NGSD_CUDA(ctx, ngsd_launch_dist_imma(ctx, (uint32_t) n_units, grid));
-    launches++;
+    NGSD_CUDA(ctx, ngsd_launch_dist_imma(ctx, (uint32_t) n_units, grid, do_count));
+    launches += do_count ? 2 : 1;
   }
   tick(ctx, 4);
-  if (do_count) {   // K3 on the auxiliary stream, next to the persistent K2c CTAs
-    NGSD_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
-    NGSD_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->aux_stream));
-    NGSD_CUDA(ctx, ngsd_launch_mask_count(ctx, n_entries, ctx->aux_stream));
-    NGSD_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->aux_stream));
-    NGSD_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
-    NGSD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
-    launches += n_entries ? 1 : 0;
-  }
   tick(ctx, 8);
   if (n_words) {
-    NGSD_CUDA(ctx, ngsd_launch_epilogue_int(ctx, n_splits, n_eff, do_count));
+    NGSD_CUDA(ctx, ngsd_launch_epilogue_int(ctx, n_splits, n_eff, do_count, do_count));
     launches += 2;
   }
   tick(ctx, 5);
@@ -559,14 +540,13 @@ static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n
   if (cnt_opt) NGSD_CUDA(ctx, cudaMemcpyAsync(cnt_opt, ctx->d_cntout, n2 * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
   NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   float ms;
-  ctx->timing.count_ms = 0;
-  if (do_count) { cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ctx->timing.count_ms = ms; }
+  ctx->timing.count_ms = 0;                                  // part of dist_ms: the count GEMM runs inside K2c
   cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->timing.dist_ms = ms;
   cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[5]); ctx->timing.epilogue_ms = ms;
   cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[5]); ctx->timing.total_ms = ms;
   ctx->timing.launches = launches;
   ctx->timing.dist_ctas = grid;
-  ctx->timing.dist_imma = (uint64_t) n_words * 8 * ctx->n_tiles * 128ull;   // 8 k-steps per word, 8 warps x 16 IMMA per k-step
+  ctx->timing.dist_imma = (uint64_t) n_words * (do_count ? 10 : 8) * ctx->n_tiles * 128ull;   // 8 (+2 count) k-steps per word, 8 warps x 16 IMMA per k-step
   ctx->timing.active_sites = active_sites;
   return NGSD_OK;
 }
@@ -581,7 +561,7 @@ static int ensure_dist_buffers(ngsd_ctx *ctx, uint64_t slots) {
       NGSD_CUDA(ctx, dev_alloc(&ctx->d_weights, ctx->NC * NGSD_SC_MAX));
       NGSD_CUDA(ctx, dev_alloc(&ctx->d_chunk_ids, ctx->NC));
     }
-    if (ctx->cfg.pairwise_del) NGSD_CUDA(ctx, dev_alloc(&ctx->d_cnt, ctx->n_pad * ctx->n_pad));
+    if (ctx->cfg.pairwise_del && !ctx->int_path) NGSD_CUDA(ctx, dev_alloc(&ctx->d_cnt, ctx->n_pad * ctx->n_pad));
   }
   if (slots > ctx->partial_slots) {
     cudaFree(ctx->d_partials);

@@ -37,8 +37,9 @@ constexpr int kStages = 8;
 constexpr int kConsumerWarps = 8;
 constexpr int kThreads = (kConsumerWarps + 1) * 32;
 constexpr int kCodeBytes = 4 * 128 * 4;                       // one operand of one stage: [4 words][128 rows] uint32
-constexpr int kStageBytes = 2 * kCodeBytes + 64;              // A codes + B codes + 64 site weights (uint8)
-constexpr size_t kSmemBytes = (size_t) kStages * kStageBytes + 2 * kStages * sizeof(uint64_t) + kStages * 2 * sizeof(uint32_t) + 64 + 128;
+constexpr int kMaskBytes = 128 * 8;                           // presence bits of one operand of one stage (COUNT only)
+constexpr int kStageBytesMax = 2 * kCodeBytes + 64 + 2 * kMaskBytes;   // A codes + B codes + 64 site weights (uint8) [+ masks]
+constexpr size_t kSmemBytes = (size_t) kStages * kStageBytesMax + 2 * kStages * sizeof(uint64_t) + kStages * 2 * sizeof(uint32_t) + 64 + 2 * 256 * 8 + 64;
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -83,6 +84,7 @@ __device__ __forceinline__ void imma16832(int (&c)[4], const uint32_t (&a)[4], u
 
 struct ImmaArgs {
   const uint32_t *codes;        // [RB][NW][4][128]
+  const uint64_t *mask;         // [RB][NW][128] presence bits (COUNT only)
   const uint8_t *wsite;         // [n_layers][NW * 64] per-site weights (0 for padding sites)
   const uint32_t *word_ids;     // [n_words] active 64-site words
   const uint32_t *word_layer;   // [n_words] weight layer of each entry
@@ -93,19 +95,32 @@ struct ImmaArgs {
   uint64_t NW;
   uint32_t n_tiles, n_units;
   uint32_t lut[4];              // B words: byte k of lut[c] = S * f(k, c)
+  uint32_t pstride;             // ints per unit in `partials` (16384, or 32768 with the count tile behind the sum tile)
 };
 
 enum : uint32_t { kFirst = 1u, kLast = 2u, kExit = 8u };
 
+// COUNT = false: the contraction described above.  COUNT = true: the same machinery computes ONLY the shared-site
+// counts of --pairwise_del, cnt(i,j) = sum_s w_s m_i(s) m_j(s) (ngsDist.cpp:335-338,362), as an int8 GEMM with ONE byte
+// per site (K = 32 sites per IMMA, a quarter of the instructions of the contraction): A' bytes = w_s m_i(s), B' bytes =
+// m_j(s), expanded from the presence bit masks a byte (8 sites) at a time through two 256-entry tables.  On this path
+// it replaces the AND+POPC kernel (mask_count.cu), which was the longer of the two when they ran side by side.  (One
+// fused kernel with both accumulator sets needs > 168 registers -- the cap for a 9-warp CTA -- and spills.)
+template <bool COUNT>
 __global__ void __launch_bounds__(kThreads, NGSD_IMMA_CTAS) k_dist_imma(ImmaArgs a) {
+  constexpr int kStageBytes = COUNT ? 2 * kMaskBytes + 64 : 2 * kCodeBytes + 64;
+  constexpr int kOffW = COUNT ? 2 * kMaskBytes : 2 * kCodeBytes;
   extern __shared__ __align__(128) unsigned char smem[];
   uint64_t *full = reinterpret_cast<uint64_t *>(smem + (size_t) kStages * kStageBytes);
   uint64_t *empty = full + kStages;
   uint32_t *meta = reinterpret_cast<uint32_t *>(empty + kStages);   // [kStages][2] = {unit, flags}
   uint32_t *lut = meta + 2 * kStages;                               // [4]
+  uint2 *lutA = reinterpret_cast<uint2 *>(lut + 4), *lutB = lutA + 256;   // [256] 8 presence bits -> 8 bytes of 0xFF / 0x01
   auto stageA = [&](int s) { return reinterpret_cast<const uint32_t *>(smem + (size_t) s * kStageBytes); };
   auto stageB = [&](int s) { return reinterpret_cast<const uint32_t *>(smem + (size_t) s * kStageBytes + kCodeBytes); };
-  auto stageW = [&](int s) { return reinterpret_cast<const uint8_t *>(smem + (size_t) s * kStageBytes + 2 * kCodeBytes); };
+  auto stageW = [&](int s) { return reinterpret_cast<const uint8_t *>(smem + (size_t) s * kStageBytes + kOffW); };
+  auto stageMA = [&](int s) { return reinterpret_cast<const uint64_t *>(smem + (size_t) s * kStageBytes); };
+  auto stageMB = [&](int s) { return reinterpret_cast<const uint64_t *>(smem + (size_t) s * kStageBytes + kMaskBytes); };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -113,6 +128,13 @@ __global__ void __launch_bounds__(kThreads, NGSD_IMMA_CTAS) k_dist_imma(ImmaArgs
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (threadIdx.x == 0) { lut[0] = a.lut[0]; lut[1] = a.lut[1]; lut[2] = a.lut[2]; lut[3] = a.lut[3]; }
+  if (COUNT && threadIdx.x < 256) {
+    const uint32_t n = threadIdx.x, lo = n & 15u, hi = n >> 4;
+    const uint32_t one_lo = (lo & 1u) | ((lo & 2u) << 7) | ((lo & 4u) << 14) | ((lo & 8u) << 21);
+    const uint32_t one_hi = (hi & 1u) | ((hi & 2u) << 7) | ((hi & 4u) << 14) | ((hi & 8u) << 21);
+    lutB[n] = make_uint2(one_lo, one_hi);
+    lutA[n] = make_uint2(one_lo * 0xFFu, one_hi * 0xFFu);
+  }
   __syncthreads();
 
   int stage = 0;
@@ -137,9 +159,14 @@ __global__ void __launch_bounds__(kThreads, NGSD_IMMA_CTAS) k_dist_imma(ImmaArgs
           meta[stage * 2 + 1] = (c == c0 ? kFirst : 0u) | (c + 1 == c1 ? kLast : 0u);
           mbar_expect_tx(&full[stage], kStageBytes);
           unsigned char *dst = smem + (size_t) stage * kStageBytes;
-          bulk_g2s(dst, Ab + word * 512, kCodeBytes, &full[stage]);
-          bulk_g2s(dst + kCodeBytes, Bb + word * 512, kCodeBytes, &full[stage]);
-          bulk_g2s(dst + 2 * kCodeBytes, wsrc, 64, &full[stage]);
+          if (COUNT) {
+            bulk_g2s(dst, a.mask + ((uint64_t) tl.ti * a.NW + word) * 128, kMaskBytes, &full[stage]);
+            bulk_g2s(dst + kMaskBytes, a.mask + ((uint64_t) tl.tj * a.NW + word) * 128, kMaskBytes, &full[stage]);
+          } else {
+            bulk_g2s(dst, Ab + word * 512, kCodeBytes, &full[stage]);
+            bulk_g2s(dst + kCodeBytes, Bb + word * 512, kCodeBytes, &full[stage]);
+          }
+          bulk_g2s(dst + kOffW, wsrc, 64, &full[stage]);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
       }
@@ -153,6 +180,7 @@ __global__ void __launch_bounds__(kThreads, NGSD_IMMA_CTAS) k_dist_imma(ImmaArgs
   // ===== consumers: 2 x 4 warps, warp tile 64 (rows) x 32 (columns) =====
   const int wm = warp >> 2, wn = warp & 3, g = lane >> 2, q = lane & 3;
   const int rotA = (2 * q - 3) & 31, rotB = (2 * q - 2) & 31;       // bring this lane's code field to bits 3..4 / 2..3
+  const int rotC = (8 * q - 3) & 31;                                // presence byte of this lane's 8 sites -> bits 3..10 (x 8 bytes)
   int acc[4][4][4];
   for (;;) {
     mbar_wait(&full[stage], phase);
@@ -166,10 +194,37 @@ __global__ void __launch_bounds__(kThreads, NGSD_IMMA_CTAS) k_dist_imma(ImmaArgs
 #pragma unroll
           for (int k = 0; k < 4; k++) acc[mi][ni][k] = 0;
     }
+    if (COUNT) {
+      // The K order of the count GEMM is free as long as both operands use it: lane q takes the 8 consecutive sites
+      // 32 j + 8 q .. + 7 (K 4q..4q+3 = the first four, K 16+4q..+3 = the last four), i.e. ONE byte of a presence word,
+      // expanded to its two fragment registers by one 8-byte table read; the 8 site weights are one 8-byte read too.
+      const uint32_t *Ma = reinterpret_cast<const uint32_t *>(stageMA(stage)) + (wm * 64 + g) * 2;
+      const uint32_t *Mb = reinterpret_cast<const uint32_t *>(stageMB(stage)) + (wn * 32 + g) * 2;
+      const uint2 *W64 = reinterpret_cast<const uint2 *>(stageW(stage)) + q;
+#pragma unroll
+      for (int j = 0; j < 2; j++) {                                 // one IMMA k-step = 32 sites, one byte per site
+        const uint2 ww = W64[j * 4];
+        uint2 bf[4];
+#pragma unroll
+        for (int ni = 0; ni < 4; ni++) {
+          const uint32_t h = Mb[ni * 16 + j];
+          bf[ni] = *reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned char *>(lutB) + (__funnelshift_r(h, h, rotC) & 0x7F8u));
+        }
+#pragma unroll
+        for (int mi = 0; mi < 4; mi++) {
+          const uint32_t h0 = Ma[mi * 32 + j], h1 = Ma[mi * 32 + 16 + j];
+          const uint2 e0 = *reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned char *>(lutA) + (__funnelshift_r(h0, h0, rotC) & 0x7F8u));
+          const uint2 e1 = *reinterpret_cast<const uint2 *>(reinterpret_cast<const unsigned char *>(lutA) + (__funnelshift_r(h1, h1, rotC) & 0x7F8u));
+          const uint32_t af[4] = {e0.x & ww.x, e1.x & ww.x, e0.y & ww.y, e1.y & ww.y};
+#pragma unroll
+          for (int ni = 0; ni < 4; ni++) imma16832(acc[mi][ni], af, bf[ni].x, bf[ni].y);
+        }
+      }
+    }
     const uint32_t *As = stageA(stage) + wm * 64 + g, *Bs = stageB(stage) + wn * 32 + g;
     const uint8_t *Ws = stageW(stage) + q;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {                                   // 16 sites per packed word
+    for (int k = 0; k < (COUNT ? 0 : 4); k++) {                     // 16 sites per packed word
       // After the rotation the four code fields this lane needs from a word (sites q, q+4, q+8, q+12 of the 16) sit at
       // bits 3..4 (A: 8 * code) or 2..3 (B: 4 * code) of its four bytes; one mask per word isolates all of them.
       uint32_t ar[4][2], br[4];
@@ -209,12 +264,12 @@ __global__ void __launch_bounds__(kThreads, NGSD_IMMA_CTAS) k_dist_imma(ImmaArgs
     if (lane == 0) mbar_arrive(&empty[stage]);
     if (++stage == kStages) { stage = 0; phase ^= 1; }
     if (fl & kLast) {
-      int4 *dst = reinterpret_cast<int4 *>(a.partials + (uint64_t) u * NGSD_TILE_ELEMS) + (warp * 16) * 32 + lane;
+      int4 *dst = reinterpret_cast<int4 *>(a.partials + (uint64_t) u * a.pstride) + (warp * 16) * 32 + lane;
 #pragma unroll
       for (int mi = 0; mi < 4; mi++)
 #pragma unroll
-        for (int ni = 0; ni < 4; ni++)
-          dst[(mi * 4 + ni) * 32] = make_int4(acc[mi][ni][0], acc[mi][ni][1], acc[mi][ni][2], acc[mi][ni][3]);
+        for (int ni = 0; ni < 4; ni++)      // the count launch writes the second tile of the unit's slot
+          dst[(COUNT ? NGSD_TILE_ELEMS / 4 : 0) + (mi * 4 + ni) * 32] = make_int4(acc[mi][ni][0], acc[mi][ni][1], acc[mi][ni][2], acc[mi][ni][3]);
     }
   }
 }
@@ -237,9 +292,11 @@ __global__ void k_imma_peak(int *out, int iters) {
 }
 
 struct EpiIntArgs {
-  const int32_t *partials;    // [n_splits][n_tiles][16384] fragment order
+  const int32_t *partials;    // [n_splits][n_tiles][pstride] fragment order (sum tile, then count tile when in_kernel_cnt)
+  uint32_t pstride;
+  int in_kernel_cnt;
   const ngsd_tile *tiles;
-  const uint32_t *cnt;        // [n_pad][n_pad] or nullptr
+  const uint32_t *cnt;        // [n_pad][n_pad] (K3) or nullptr
   double *out, *num;
   uint64_t *cntout;
   uint64_t n_ind, n_pad, const_cnt, tot_sites;
@@ -256,19 +313,23 @@ __global__ void __launch_bounds__(256) k_epilogue_int(EpiIntArgs a) {
   const int lane = e & 31, frag = (e >> 5) & 15, warp = e >> 9;
   const int wm = warp >> 2, wn = warp & 3, mi = frag >> 2, ni = frag & 3;
   const int row0 = wm * 64 + mi * 16 + (lane >> 2), col0 = wn * 32 + ni * 8 + 2 * (lane & 3);
-  const int4 *src = reinterpret_cast<const int4 *>(a.partials + (uint64_t) t * NGSD_TILE_ELEMS) + e;
-  const uint64_t stride = (uint64_t) a.n_tiles * (NGSD_TILE_ELEMS / 4);
-  long long s[4] = {0, 0, 0, 0};
+  const int4 *src = reinterpret_cast<const int4 *>(a.partials + (uint64_t) t * a.pstride) + e;
+  const uint64_t stride = (uint64_t) a.n_tiles * (a.pstride / 4);
+  long long s[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0};
   for (uint32_t q = 0; q < a.n_splits; q++) {
     const int4 v = src[(uint64_t) q * stride];
     s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    if (a.in_kernel_cnt) {
+      const int4 w = src[(uint64_t) q * stride + NGSD_TILE_ELEMS / 4];
+      c[0] += w.x; c[1] += w.y; c[2] += w.z; c[3] += w.w;
+    }
   }
 #pragma unroll
   for (int k = 0; k < 4; k++) {
     const uint64_t i = (uint64_t) tl.ti * NGSD_TILE + row0 + (k >> 1) * 8, j = (uint64_t) tl.tj * NGSD_TILE + col0 + (k & 1);
     if (i >= j || j >= a.n_ind) continue;
     const double num = (double) s[k] / a.scale;
-    uint64_t cnt = a.cnt ? (uint64_t) a.cnt[i * a.n_pad + j] : a.const_cnt;
+    uint64_t cnt = a.in_kernel_cnt ? (uint64_t) c[k] : (a.cnt ? (uint64_t) a.cnt[i * a.n_pad + j] : a.const_cnt);
     if (a.num) a.num[i * a.n_ind + j] = a.num[j * a.n_ind + i] = num;
     if (a.cntout) a.cntout[i * a.n_ind + j] = a.cntout[j * a.n_ind + i] = cnt;
     if (a.tot_sites > 0) cnt = a.tot_sites;
@@ -316,15 +377,20 @@ bool ngsd_int_lut(const double *score, bool pairwise_del, uint32_t lut[4], doubl
 
 int ngsd_imma_ctas_per_sm() { return NGSD_IMMA_CTAS; }
 
-cudaError_t ngsd_launch_dist_imma(ngsd_ctx *ctx, uint32_t n_units, int grid) {
+cudaError_t ngsd_launch_dist_imma(ngsd_ctx *ctx, uint32_t n_units, int grid, bool count) {
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
-    cudaError_t e = cudaFuncSetAttribute((const void *) k_dist_imma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBytes);
-    if (e != cudaSuccess) return e;
+    const void *fns[2] = {(const void *) k_dist_imma<false>, (const void *) k_dist_imma<true>};
+    for (const void *f : fns) {
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBytes);
+      if (e != cudaSuccess) return e;
+    }
     attr_set[ctx->device & 63] = true;
   }
   ImmaArgs a;
   a.codes = ctx->codes;
+  a.mask = ctx->mask;
+  a.pstride = count ? 2 * NGSD_TILE_ELEMS : NGSD_TILE_ELEMS;
   a.wsite = ctx->d_wsite;
   a.word_ids = ctx->d_word_ids;
   a.word_layer = ctx->d_word_layer;
@@ -338,15 +404,22 @@ cudaError_t ngsd_launch_dist_imma(ngsd_ctx *ctx, uint32_t n_units, int grid) {
   for (int k = 0; k < 4; k++) a.lut[k] = ctx->int_lut[k];
   cudaError_t e = cudaMemsetAsync(ctx->d_sched, 0, sizeof(uint32_t), ctx->stream);
   if (e != cudaSuccess) return e;
-  k_dist_imma<<<grid, kThreads, kSmemBytes, ctx->stream>>>(a);
+  k_dist_imma<false><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a);
+  if (count) {      // second pass of the same unit list: the shared-site counts
+    e = cudaMemsetAsync(ctx->d_sched, 0, sizeof(uint32_t), ctx->stream);
+    if (e != cudaSuccess) return e;
+    k_dist_imma<true><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a);
+  }
   return cudaGetLastError();
 }
 
-cudaError_t ngsd_launch_epilogue_int(ngsd_ctx *ctx, uint32_t n_splits, uint64_t const_cnt, bool use_cnt) {
+cudaError_t ngsd_launch_epilogue_int(ngsd_ctx *ctx, uint32_t n_splits, uint64_t const_cnt, bool use_cnt, bool in_kernel_cnt) {
   EpiIntArgs a;
   a.partials = reinterpret_cast<const int32_t *>(ctx->d_partials);
+  a.pstride = in_kernel_cnt ? 2 * NGSD_TILE_ELEMS : NGSD_TILE_ELEMS;
+  a.in_kernel_cnt = in_kernel_cnt ? 1 : 0;
   a.tiles = ctx->d_tiles;
-  a.cnt = use_cnt ? ctx->d_cnt : nullptr;
+  a.cnt = (use_cnt && !in_kernel_cnt) ? ctx->d_cnt : nullptr;
   a.out = ctx->d_out;
   a.num = ctx->d_num;
   a.cntout = ctx->d_cntout;
