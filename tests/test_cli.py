@@ -146,3 +146,75 @@ def test_cli_labels_stdin_and_nan_spelling(tmp_path):
                             "--verbose", "0"] + flags[1:], stdin=fh, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
     assert r.returncode == 0, r.stderr
     assert out2.read_text() == text
+
+
+@pytest.mark.gpu
+def test_cli_c1_reference_test_script_matrix(tmp_path):
+    """BASELINE configs[0] (C1): the 18 runs of the reference's own examples/test.sh (genotype text, BEAGLE-style text with
+    header + 3 leading columns + --pos, binary, plain text posteriors; bootstrap, block size, --call_geno, thresholds) at
+    its shape, 24 individuals x 10 000 sites with --labels, on synthetic data (the script's inputs are not shipped, SURVEY
+    D4).  Every run is executed by the drop-in CLI and by the unmodified reference binary and the .dist files are compared:
+    same layout and labels, values within 1e-9 (default --probs rows run the per pair-site EM in both)."""
+    import gzip
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref/ngsDist not built")
+    n_ind, n_sites = 24, 10000
+    raw = oracle.synth_raw(20251018, 0.05, n_ind, n_sites)
+    P = raw / raw.sum(axis=2, keepdims=True)
+    # keep 6-decimal text values off the --call_thresh 0.9 knife edge (a 1-ulp log/exp difference could flip a call there,
+    # SURVEY App. E-7): no triple whose printed maximum is exactly 0.900000
+    P[np.round(P, 6).max(axis=2) == 0.9] = (0.91, 0.05, 0.04)
+    labels = str(tmp_path / "testA.labels")
+    open(labels, "w").write("".join("ind%02d_pop%d\n" % (i, i // 8) for i in range(n_ind)))
+    # genotype text: chr, position, then one code per individual (-1 = missing where the synthetic triple is uniform)
+    geno = np.argmax(raw, axis=2).astype(int)
+    geno[(raw[..., 0] == raw[..., 1]) & (raw[..., 1] == raw[..., 2])] = -1
+    f_geno = str(tmp_path / "testA_T.geno.gz")
+    with gzip.open(f_geno, "wt") as fh:
+        for s in range(n_sites):
+            fh.write("chrSIM\t%d\t" % (s + 1) + "\t".join(str(g) for g in geno[s]) + "\n")
+    f_beagle = str(tmp_path / "testA_2.beagle.gz")
+    with gzip.open(f_beagle, "wt") as fh:
+        fh.write("marker\tallele1\tallele2\t" + "\t".join("Ind%d" % (i // 3) for i in range(3 * n_ind)) + "\n")
+        for s in range(n_sites):
+            fh.write("chrSIM_%d\t0\t1\t" % (s + 1) + "\t".join("%.6f" % v for v in P[s].reshape(-1)) + "\n")
+    f_pos = str(tmp_path / "testA.pos")
+    open(f_pos, "w").write("".join("chrSIM\t%d\n" % (s + 1) for s in range(n_sites)))
+    f_bin = str(tmp_path / "testA_32.geno")
+    P.tofile(f_bin)
+    f_txt = str(tmp_path / "testA_8.geno.gz")
+    with gzip.open(f_txt, "wt") as fh:
+        for s in range(n_sites):
+            fh.write("chrSIM\t%d\t" % (s + 1) + "\t".join("%.6f" % v for v in P[s].reshape(-1)) + "\n")
+    boot = [[], ["--n_boot_rep", "5"], ["--n_boot_rep", "5", "--boot_block_size", "10"]]
+    call = [["--n_boot_rep", "5", "--boot_block_size", "10", "--call_geno"],
+            ["--n_boot_rep", "5", "--boot_block_size", "10", "--call_geno", "--N_thresh", "0.3", "--call_thresh", "0.9"]]
+    runs = [("T%d" % k, f_geno, b) for k, b in enumerate(boot)]
+    runs += [("2_%d" % k, f_beagle, ["--probs", "--pos", f_pos] + b) for k, b in enumerate(boot + call)]
+    runs += [("32_%d" % k, f_bin, ["--probs"] + b) for k, b in enumerate(boot + call)]
+    runs += [("8_%d" % k, f_txt, ["--probs"] + b) for k, b in enumerate(boot + call)]
+    assert len(runs) == 18
+    threads = str(os.cpu_count() or 4)
+    worst = 0.0
+    for name, path, extra in runs:
+        outs = []
+        for binary in (CLI, oracle.REF_BIN):
+            out = str(tmp_path / ("%s_%s.dist" % (name, "ref" if binary == oracle.REF_BIN else "b200")))
+            cmd = [binary, "--n_threads", threads, "--seed", "12345", "--verbose", "0", "--geno", path, "--n_ind", str(n_ind),
+                   "--n_sites", str(n_sites), "--labels", labels] + extra + ["--out", out]
+            r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+            assert r.returncode == 0, (name, r.stderr[-1500:])
+            outs.append(out)
+        ta, tb = open(outs[0]).read(), open(outs[1]).read()
+        la, lb = ta.split("\n"), tb.split("\n")
+        assert len(la) == len(lb), name
+        assert [x.split("\t")[0] for x in la] == [x.split("\t")[0] for x in lb], "%s: layout / labels differ" % name
+        ma = [m for _, m in oracle.parse_dist(outs[0], n_ind)]
+        mb = [m for _, m in oracle.parse_dist(outs[1], n_ind)]
+        assert len(ma) == len(mb) == (1 + (5 if "--n_boot_rep" in extra else 0))
+        for x, y in zip(ma, mb):
+            assert np.array_equal(np.isnan(x), np.isnan(y))
+            d = np.nanmax(np.abs(x - y))
+            worst = max(worst, float(d))
+            assert d <= 1e-9 * max(1.0, float(np.nanmax(np.abs(y)))) + 1.01e-10, (name, d)   # + one unit of the 10th printed decimal
+    print("C1 test.sh matrix: 18 runs, worst |difference| of printed values %.3g" % worst)
