@@ -69,7 +69,9 @@ typedef struct {
   int32_t reserved;          /* flags: bit 0 = keep all three operand planes (disables the sum-to-one reduction that is
                                 used when indep_geno && !pairwise_del; for inspection through ngsd_get_posteriors);
                                 bit 1 = do not use the integer (int8 tensor core) path for called genotypes, i.e. run
-                                them through the FP64 contraction like soft posteriors (A/B testing)              */
+                                them through the FP64 contraction like soft posteriors (A/B testing);
+                                bit 2 = contract every bootstrap replicate directly (weighted contraction) instead of
+                                reusing per-block partial sums (the bootstrap block cache)                          */
 } ngsd_cfg;
 
 typedef struct ngsd_ctx ngsd_ctx;
@@ -87,6 +89,8 @@ typedef struct {
   uint64_t dist_dmma;        /* warp-level DMMA.8x8x4 instructions the K2 launch issued  */
   uint64_t active_sites;     /* sites with non-zero weight in the call                   */
   uint64_t dist_imma;        /* warp-level IMMA.16832 instructions of the K2c launch (called-genotype integer path) */
+  int32_t block_cache;       /* bootstrap block cache: 0 not used, 1 built by this call, 2 reused (no contraction launched) */
+  int32_t pad_;
 } ngsd_timing;
 
 NGSD_API void ngsd_default_cfg(ngsd_cfg *cfg);   /* init_pars (parse_args.cpp:6-37) for the fields above */

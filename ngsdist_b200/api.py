@@ -42,7 +42,7 @@ class _Cfg(C.Structure):
 class Timing(C.Structure):
     _fields_ = [("frontend_ms", C.c_float), ("count_ms", C.c_float), ("dist_ms", C.c_float), ("epilogue_ms", C.c_float),
                 ("total_ms", C.c_float), ("launches", C.c_int32), ("dist_ctas", C.c_int32), ("dist_dmma", C.c_uint64),
-                ("active_sites", C.c_uint64), ("dist_imma", C.c_uint64)]
+                ("active_sites", C.c_uint64), ("dist_imma", C.c_uint64), ("block_cache", C.c_int32), ("pad_", C.c_int32)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -142,6 +142,7 @@ class Params:
     in_text: bool = False      # text reader semantics (no -inf clamp) instead of the binary reader's
     keep_planes: bool = False  # ngsd_cfg.reserved bit 0: keep all three operand planes (exact ngsd_get_posteriors)
     force_fp64: bool = False   # ngsd_cfg.reserved bit 1: called genotypes through the FP64 contraction (A/B testing)
+    no_block_cache: bool = False  # ngsd_cfg.reserved bit 2: contract every bootstrap replicate directly
 
     def resolved(self):
         """Apply the parse-time implications and main()'s forcing rules (parse_args.cpp:91-94,123-130; ngsDist.cpp:55-62)."""
@@ -201,7 +202,7 @@ class NgsDistB200:
         cfg.input_is_log = int(p.in_logscale)
         cfg.input_kind = 2 if not p.in_probs else (1 if p.in_text else 0)
         cfg.device = device
-        cfg.reserved = (1 if p.keep_planes else 0) | (2 if p.force_fp64 else 0)
+        cfg.reserved = (1 if p.keep_planes else 0) | (2 if p.force_fp64 else 0) | (4 if p.no_block_cache else 0)
         self._h = C.c_void_p()
         rc = L.ngsd_create(C.byref(cfg), C.byref(self._h))
         if rc:

@@ -117,7 +117,7 @@ int ngsd_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
     ngsd_set_error(nullptr, "missing data threshold must be smaller than calling genotype threshold!");
     return NGSD_ERR_THRESH;
   }
-  if (cfg->input_kind < 0 || cfg->input_kind > 2 || (cfg->reserved & ~3)) { ngsd_set_error(nullptr, "invalid input_kind / flags"); return NGSD_ERR_ARG; }
+  if (cfg->input_kind < 0 || cfg->input_kind > 2 || (cfg->reserved & ~7)) { ngsd_set_error(nullptr, "invalid input_kind / flags"); return NGSD_ERR_ARG; }
   if ((cfg->input_kind == NGSD_INPUT_GENOTYPES || cfg->call_geno) && !cfg->indep_geno) {
     ngsd_set_error(nullptr, "indep_geno must be set for genotype input / call_geno (ngsDist.cpp:55-62)");
     return NGSD_ERR_ARG;
@@ -218,6 +218,7 @@ int ngsd_destroy(ngsd_ctx *ctx) {
   cudaFree(ctx->d_tiles); cudaFree(ctx->d_partials); cudaFree(ctx->d_weights); cudaFree(ctx->d_chunk_ids);
   cudaFree(ctx->d_ent_word); cudaFree(ctx->d_ent_mask); cudaFree(ctx->d_cnt); cudaFree(ctx->d_split_begin); cudaFree(ctx->d_split_scale); cudaFree(ctx->d_sched);
   cudaFree(ctx->d_out); cudaFree(ctx->d_num); cudaFree(ctx->d_cntout);
+  cudaFree(ctx->d_cache);
   cudaFree(ctx->codes); cudaFree(ctx->d_wsite); cudaFree(ctx->d_word_layer); cudaFree(ctx->d_word_ids);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -249,6 +250,7 @@ static void mark_pushed(ngsd_ctx *ctx, uint64_t site0, uint64_t n) {
   for (uint64_t w = site0 / 64; w < (site0 + n + 63) / 64; w++)
     if (!ctx->pushed[w]) { ctx->pushed[w] = 1; ctx->words_pushed++; }
   ctx->frontend_done = false;
+  ctx->cache_valid = false;
 }
 
 int ngsd_push_sites_device(ngsd_ctx *ctx, const double *raw_dev, uint64_t site0, uint64_t n) {
@@ -675,16 +677,59 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
     ctx->timing = ngsd_timing();
     return NGSD_OK;
   }
+  // ---- bootstrap block cache -------------------------------------------------------------------------------------
+  // Resampling is by whole blocks (ngsDist.cpp:416-437), so num_r(i,j) = sum_b c_r[b] * G_b(i,j) with G_b the sum over
+  // the sites of source block b: compute the per-block partials ONCE (K splits = blocks) and every replicate is a
+  // weighted split reduction in the epilogue -- ~100x less work per replicate at C3 (SURVEY §7 design option (a)).
+  // It needs blocks that are whole site chunks and room for n_blocks partials; otherwise (and with ngsd_cfg.reserved
+  // bit 2, which benchmarks of the per-replicate weighted contraction set) the replicate is contracted directly.
+  const uint64_t em_ld = em_path ? ngsd_em_ld(ctx) : 0;
+  bool use_cache = false, build_cache = false;
+  if (weighted && !(ctx->cfg.reserved & 4) && !getenv("NGSD_NO_BLOCK_CACHE") && block_size % SC == 0 && n_blocks >= 2 &&
+      n_blocks < 0x7fffffffull / std::max<uint32_t>(ctx->n_tiles, 1)) {
+    const uint64_t need = em_path ? n_blocks * em_ld * em_ld : n_blocks * (uint64_t) ctx->n_tiles * NGSD_TILE_ELEMS;
+    if (ctx->cache_valid && ctx->cache_blocks == n_blocks && ctx->cache_bs == block_size) {
+      use_cache = true;
+    } else {
+      size_t fr = 0, tot = 0;
+      NGSD_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
+      const uint64_t avail = (uint64_t) fr + ctx->cache_doubles * sizeof(double);
+      if (need * sizeof(double) + ((uint64_t) 3 << 30) <= avail) {
+        if (need > ctx->cache_doubles) {
+          cudaFree(ctx->d_cache);
+          ctx->d_cache = nullptr;
+          ctx->cache_doubles = 0;
+          ctx->cache_valid = false;
+          NGSD_CUDA(ctx, dev_alloc(&ctx->d_cache, need));
+          ctx->cache_doubles = need;
+        }
+        use_cache = build_cache = true;
+      }
+    }
+  }
+
   ngsd_dist_plan plan;
   uint32_t em_splits = 0;
   plan.weighted = weighted;
   plan.n_chunks = (uint32_t) n_chunks;
   plan.grid = ctx->n_sm;
   const double cost_tiles = (double) (ctx->n_tiles - ctx->n_diag_tiles) + ctx->n_diag_tiles * (136.0 / 256.0);
-  std::vector<uint32_t> splits = plan_splits(plan.n_chunks, ctx->n_tiles, cost_tiles, plan.grid);
+  std::vector<uint32_t> splits;
   std::vector<double> scales;
   plan.uniform_scale = uniform_scale;
-  if (uniform_scale) {   // cut the splits at the class boundaries and record each split's weight
+  if (use_cache) {            // K splits = source blocks, unweighted, identity chunk list
+    const uint32_t per = (uint32_t) (block_size / SC);
+    splits.resize(n_blocks + 1);
+    for (uint64_t b = 0; b <= n_blocks; b++) splits[b] = (uint32_t) (b * per);
+    scales.resize(n_blocks);
+    for (uint64_t b = 0; b < n_blocks; b++) scales[b] = (double) block_counts[b];
+    plan.weighted = false;
+    plan.uniform_scale = false;
+    plan.n_chunks = (uint32_t) (n_blocks * per);
+  } else {
+    splits = plan_splits(plan.n_chunks, ctx->n_tiles, cost_tiles, plan.grid);
+  }
+  if (uniform_scale && !use_cache) {   // cut the splits at the class boundaries and record each split's weight
     std::vector<uint32_t> cut;
     size_t k = 0;
     cut.push_back(0);
@@ -706,9 +751,8 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   plan.n_units = plan.n_splits * ctx->n_tiles;
   plan.grid = (int) std::min<uint64_t>(plan.grid, plan.n_units);
   if (em_path) {
-    em_splits = ngsd_em_splits(ctx, plan.n_chunks);
-    const uint64_t ld = ngsd_em_ld(ctx);
-    plan.n_units = (uint32_t) (((uint64_t) em_splits * ld * ld + NGSD_TILE_ELEMS - 1) / NGSD_TILE_ELEMS);   // workspace slots
+    em_splits = use_cache ? (uint32_t) n_blocks : ngsd_em_splits(ctx, plan.n_chunks);
+    plan.n_units = (uint32_t) (((uint64_t) em_splits * em_ld * em_ld + NGSD_TILE_ELEMS - 1) / NGSD_TILE_ELEMS);   // workspace slots
   }
   if (splits.size() > ctx->split_cap) {
     cudaFree(ctx->d_split_begin);
@@ -720,22 +764,24 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
     NGSD_CUDA(ctx, dev_alloc(&ctx->d_split_scale, splits.size() + 64));
     ctx->split_cap = (uint32_t) splits.size() + 64;
   }
-  rc = ensure_dist_buffers(ctx, plan.n_units);
+  rc = ensure_dist_buffers(ctx, use_cache ? 1 : plan.n_units);
   if (rc) return rc;
   if (ctx->cfg.pairwise_del) {
     rc = ensure_entries(ctx, n_entries);
     if (rc) return rc;
   }
+  ctx->cur_partials = use_cache ? ctx->d_cache : ctx->d_partials;
+  ctx->cur_split_w = use_cache ? ctx->d_split_scale : nullptr;
 
   ctx->timing = ngsd_timing();
   // (pageable source: the copy is staged before the call returns, so `splits` may go out of scope afterwards)
   NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_split_begin, splits.data(), splits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  if (uniform_scale)
+  if (uniform_scale || use_cache)
     NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_split_scale, scales.data(), scales.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (weighted) {
     if (!uniform_scale || ctx->planes == 2)   // per-site weights: scaled B fragments and/or the weighted c-vector
       NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_weights, h_w, bytes_w, cudaMemcpyHostToDevice, ctx->stream));
-    NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_chunk_ids, h_c, n_chunks * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+    if (!use_cache) NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_chunk_ids, h_c, n_chunks * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   }
   if (n_entries) {
     NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_ent_word, h_ew, n_entries * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
@@ -748,8 +794,10 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   tick(ctx, 3);
   // K2 / K2b first, so that its persistent CTAs own every SM; K3 is then launched on the auxiliary stream and its
   // (small) CTAs co-reside with them: integer AND+POPC in the shadow of the FP64 contraction.
-  if (em_path) {
-    NGSD_CUDA(ctx, ngsd_launch_dist_em(ctx, plan.n_chunks, em_splits, weighted));
+  if (use_cache && !build_cache) {
+    // the per-block partials of this geometry are resident: nothing to contract
+  } else if (em_path) {
+    NGSD_CUDA(ctx, ngsd_launch_dist_em(ctx, plan.n_chunks, em_splits, plan.weighted));
     launches++;
   } else if (plan.n_chunks > 0) {
     NGSD_CUDA(ctx, ngsd_launch_dist_dmma(ctx, plan));
@@ -797,8 +845,16 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[5]); ctx->timing.total_ms = ms;
   ctx->timing.launches = launches;
   ctx->timing.dist_ctas = plan.grid;
-  ctx->timing.dist_dmma = em_path ? 0 : (uint64_t) plan.n_chunks * NGSD_K4_PER_CHUNK * ((uint64_t) (ctx->n_tiles - ctx->n_diag_tiles) * 256ull + (uint64_t) ctx->n_diag_tiles * 136ull);
+  ctx->timing.dist_dmma = (em_path || (use_cache && !build_cache)) ? 0 : (uint64_t) plan.n_chunks * NGSD_K4_PER_CHUNK * ((uint64_t) (ctx->n_tiles - ctx->n_diag_tiles) * 256ull + (uint64_t) ctx->n_diag_tiles * 136ull);
   ctx->timing.active_sites = active_sites;
+  ctx->timing.block_cache = use_cache ? (build_cache ? 1 : 2) : 0;
+  if (use_cache) {
+    ctx->cache_valid = true;
+    ctx->cache_blocks = n_blocks;
+    ctx->cache_bs = block_size;
+  }
+  ctx->cur_partials = ctx->d_partials;
+  ctx->cur_split_w = nullptr;
   return NGSD_OK;
 }
 
@@ -819,6 +875,7 @@ int ngsd_set_tile_shard(ngsd_ctx *ctx, uint32_t rank, uint32_t world) {
   if (!mine.empty()) NGSD_CUDA(ctx, cudaMemcpy(ctx->d_tiles, mine.data(), mine.size() * sizeof(ngsd_tile), cudaMemcpyHostToDevice));
   ctx->shard_rank = rank;
   ctx->shard_world = world;
+  ctx->cache_valid = false;
   return NGSD_OK;
 }
 

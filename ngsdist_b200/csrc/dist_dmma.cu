@@ -286,7 +286,7 @@ cudaError_t ngsd_launch_dist_dmma(ngsd_ctx *ctx, const ngsd_dist_plan &p) {
   a.split_begin = ctx->d_split_begin;
   a.split_scale = p.uniform_scale ? ctx->d_split_scale : nullptr;
   a.sched = ctx->d_sched;
-  a.partials = ctx->d_partials;
+  a.partials = ctx->cur_partials;
   a.NC = ctx->NC;
   a.n_tiles = ctx->n_tiles;
   a.n_units = p.n_units;

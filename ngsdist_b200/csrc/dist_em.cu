@@ -291,6 +291,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_em(EmArgs a) {
 
 struct EmEpiArgs {
   const double *partials;
+  const double *split_w;      // [n_splits] weight of each split (bootstrap block cache) or nullptr
   const uint32_t *cnt;        // [n_pad][n_pad] or nullptr
   double *out, *num;
   uint64_t *cntout;
@@ -311,7 +312,14 @@ __global__ void __launch_bounds__(256) k_epilogue_em(EmEpiArgs a) {
   }
   if (i > j) return;
   double num = 0;
-  for (uint32_t q = 0; q < a.n_splits; q++) num += a.partials[((uint64_t) q * a.ld + i) * a.ld + j];
+  if (a.split_w) {
+    for (uint32_t q = 0; q < a.n_splits; q++) {
+      const double w = a.split_w[q];
+      if (w != 0.0) num += w * a.partials[((uint64_t) q * a.ld + i) * a.ld + j];
+    }
+  } else {
+    for (uint32_t q = 0; q < a.n_splits; q++) num += a.partials[((uint64_t) q * a.ld + i) * a.ld + j];
+  }
   uint64_t cnt = a.cnt ? (uint64_t) a.cnt[i * a.n_pad + j] : a.const_cnt;
   if (a.num) a.num[i * a.n_ind + j] = a.num[j * a.n_ind + i] = num;
   if (a.cntout) a.cntout[i * a.n_ind + j] = a.cntout[j * a.n_ind + i] = cnt;
@@ -351,7 +359,7 @@ cudaError_t ngsd_launch_dist_em(ngsd_ctx *ctx, uint32_t n_chunks, uint32_t n_spl
   a.Apack = ctx->Apack;
   a.weights = weighted ? ctx->d_weights : nullptr;
   a.chunk_ids = weighted ? ctx->d_chunk_ids : nullptr;
-  a.partials = ctx->d_partials;
+  a.partials = ctx->cur_partials;
   a.NC = ctx->NC;
   a.n_sites = ctx->n_sites;
   a.n_chunks = n_chunks;
@@ -380,7 +388,8 @@ cudaError_t ngsd_launch_dist_em(ngsd_ctx *ctx, uint32_t n_chunks, uint32_t n_spl
 
 cudaError_t ngsd_launch_epilogue_em(ngsd_ctx *ctx, uint32_t n_splits, uint64_t const_cnt, bool use_cnt) {
   EmEpiArgs a;
-  a.partials = ctx->d_partials;
+  a.partials = ctx->cur_partials;
+  a.split_w = ctx->cur_split_w;
   a.cnt = use_cnt ? ctx->d_cnt : nullptr;
   a.out = ctx->d_out;
   a.num = ctx->d_num;

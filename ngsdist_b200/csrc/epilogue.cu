@@ -9,6 +9,7 @@ namespace {
 
 struct EpiArgs {
   const double *partials;     // [n_splits][n_tiles][16384] fragment order (dist_dmma.cu)
+  const double *split_w;      // [n_splits] weight of each split (bootstrap block cache) or nullptr
   const ngsd_tile *tiles;
   const uint32_t *cnt;        // [n_pad][n_pad] or nullptr
   const double *cvec;         // [n_pad] 2-plane mode: weighted row sums of the B_2 plane, added for column j; or nullptr
@@ -45,6 +46,15 @@ __global__ void __launch_bounds__(256) k_epilogue(EpiArgs a) {
   const uint64_t stride = (uint64_t) a.n_tiles * (NGSD_TILE_ELEMS / 2);   // in double2
   double s0 = 0, s1 = 0;
   uint32_t q = 0;
+  if (a.split_w) {                                       // per-block partials x block multiplicities, in block order
+    for (; q < a.n_splits; q++) {
+      const double w = a.split_w[q];
+      if (w == 0.0) continue;                            // block not drawn in this replicate: its partial is not even read
+      const double2 v = src[(uint64_t) q * stride];
+      s0 += w * v.x;
+      s1 += w * v.y;
+    }
+  }
   for (; q + 8 <= a.n_splits; q += 8) {                  // 8 independent loads in flight, adds in split order
     double2 v[8];
 #pragma unroll
@@ -128,7 +138,8 @@ cudaError_t ngsd_launch_finish(ngsd_ctx *ctx) {
 
 cudaError_t ngsd_launch_epilogue(ngsd_ctx *ctx, const ngsd_epilogue_args &e) {
   EpiArgs a;
-  a.partials = ctx->d_partials;
+  a.partials = ctx->cur_partials;
+  a.split_w = ctx->cur_split_w;
   a.tiles = ctx->d_tiles;
   a.cnt = e.use_cnt ? ctx->d_cnt : nullptr;
   a.cvec = ctx->planes == 2 ? ctx->d_cvec : nullptr;

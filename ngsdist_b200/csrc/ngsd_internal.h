@@ -78,6 +78,12 @@ struct ngsd_ctx {
   // distance workspaces (allocated lazily)
   ngsd_tile *d_tiles = nullptr; uint32_t n_tiles = 0;
   double *d_partials = nullptr; uint64_t partial_slots = 0;
+  // what the contraction launchers write and the epilogues read: d_partials, or the per-block cache below
+  double *cur_partials = nullptr;
+  const double *cur_split_w = nullptr;         // per-split weights applied by the epilogue (block multiplicities) or nullptr
+  // bootstrap block cache: per-block partial sums, computed once; every replicate is then a weighted sum of them
+  double *d_cache = nullptr; uint64_t cache_doubles = 0, cache_blocks = 0, cache_bs = 0;
+  bool cache_valid = false;
   double *d_weights = nullptr;                 // [NC*8] per-site bootstrap weights
   uint32_t *d_chunk_ids = nullptr;             // [NC] active chunk list
   uint32_t *d_split_begin = nullptr; uint32_t split_cap = 0;
