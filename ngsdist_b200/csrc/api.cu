@@ -81,6 +81,26 @@ std::vector<uint32_t> plan_splits(uint32_t n_chunks, uint32_t n_tiles, double co
 
 void tick(ngsd_ctx *ctx, int k) { cudaEventRecord(ctx->ev[k], ctx->stream); }
 
+// development aid: NGSD_SYNC=1 synchronises after every launch of ngsd_distances and names the one that failed
+cudaError_t dbg_sync(ngsd_ctx *ctx, const char *what) {
+  static const bool on = getenv("NGSD_SYNC") != nullptr;
+  if (!on) return cudaSuccess;
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) fprintf(stderr, "NGSD_SYNC: %s failed: %s\n", what, cudaGetErrorString(e));
+  (void) ctx;
+  return e;
+}
+
+cudaError_t upload_tile_index(ngsd_ctx *ctx, const std::vector<ngsd_tile> &tiles) {
+  std::vector<uint32_t> idx(ctx->RB * ctx->RB, 0xFFFFFFFFu);
+  for (size_t t = 0; t < tiles.size(); t++) idx[(uint64_t) tiles[t].ti * ctx->RB + tiles[t].tj] = (uint32_t) t;
+  if (!ctx->d_tile_index) {
+    cudaError_t e = cudaMalloc((void **) &ctx->d_tile_index, idx.size() * sizeof(uint32_t));
+    if (e != cudaSuccess) return e;
+  }
+  return cudaMemcpy(ctx->d_tile_index, idx.data(), idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+}
+
 }  // namespace
 
 extern "C" {
@@ -202,6 +222,7 @@ int ngsd_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
   ctx->n_diag_tiles = (uint32_t) ctx->RB;
   CREATE_CUDA(dev_alloc(&ctx->d_tiles, tiles.size()));
   CREATE_CUDA(cudaMemcpy(ctx->d_tiles, tiles.data(), tiles.size() * sizeof(ngsd_tile), cudaMemcpyHostToDevice));
+  CREATE_CUDA(upload_tile_index(ctx, tiles));
 #undef CREATE_CUDA
   *out = ctx;
   return NGSD_OK;
@@ -218,7 +239,7 @@ int ngsd_destroy(ngsd_ctx *ctx) {
   cudaFree(ctx->d_tiles); cudaFree(ctx->d_partials); cudaFree(ctx->d_weights); cudaFree(ctx->d_chunk_ids);
   cudaFree(ctx->d_ent_word); cudaFree(ctx->d_ent_mask); cudaFree(ctx->d_cnt); cudaFree(ctx->d_split_begin); cudaFree(ctx->d_split_scale); cudaFree(ctx->d_sched);
   cudaFree(ctx->d_out); cudaFree(ctx->d_num); cudaFree(ctx->d_cntout);
-  cudaFree(ctx->d_cache);
+  cudaFree(ctx->d_cache); cudaFree(ctx->d_cnt_cache); cudaFree(ctx->d_ent_begin); cudaFree(ctx->d_tile_index);
   cudaFree(ctx->codes); cudaFree(ctx->d_wsite); cudaFree(ctx->d_word_layer); cudaFree(ctx->d_word_ids);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
@@ -619,7 +640,7 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   uint32_t maxw = 1;
   if (weighted)
     for (uint64_t b = 0; b < n_blocks; b++) maxw = std::max(maxw, block_counts[b]);
-  const uint64_t ent_max = ctx->cfg.pairwise_del ? ctx->NW * (weighted ? maxw : 1) : 0;
+  const uint64_t ent_max = ctx->cfg.pairwise_del ? std::max<uint64_t>(ctx->NW * (weighted ? maxw : 1), ctx->NW + 2 * n_blocks + 2) : 0;
   const uint64_t bytes_w = ctx->NC * SC * sizeof(double), bytes_c = ctx->NC * sizeof(uint32_t);
   const uint64_t bytes_e = ent_max * (sizeof(uint32_t) + sizeof(uint64_t));
   int rc = ensure_pinned(ctx, bytes_w + bytes_c + bytes_e + 64);
@@ -628,7 +649,52 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   uint64_t *h_em = (uint64_t *) ((char *) ctx->h_pin + bytes_w);
   uint32_t *h_c = (uint32_t *) ((char *) h_em + ent_max * sizeof(uint64_t));
   uint32_t *h_ew = h_c + ctx->NC;
-  if (weighted) {
+  // ---- bootstrap block cache -------------------------------------------------------------------------------------
+  // Resampling is by whole blocks (ngsDist.cpp:416-437), so num_r(i,j) = sum_b c_r[b] * G_b(i,j) with G_b the sum over
+  // the sites of source block b: compute the per-block partials ONCE (K splits = blocks) and every replicate is a
+  // weighted split reduction in the epilogue -- ~100x less work per replicate at C3 (SURVEY §7 design option (a)).
+  // It needs blocks that are whole site chunks and room for n_blocks partials; otherwise (and with ngsd_cfg.reserved
+  // bit 2, which benchmarks of the per-replicate weighted contraction set) the replicate is contracted directly.
+  const uint64_t em_ld = em_path ? ngsd_em_ld(ctx) : 0;
+  bool use_cache = false, build_cache = false;
+  if (weighted && !(ctx->cfg.reserved & 4) && !getenv("NGSD_NO_BLOCK_CACHE") && block_size % SC == 0 && n_blocks >= 2 &&
+      n_blocks < 0x7fffffffull / std::max<uint32_t>(ctx->n_tiles, 1)) {
+    const uint64_t need = em_path ? n_blocks * em_ld * em_ld : n_blocks * (uint64_t) ctx->n_tiles * NGSD_TILE_ELEMS;
+    // with --pairwise_del the per-block shared-site counts are cached next to the sums (one K3 split per block)
+    const uint64_t need_cnt = (ctx->cfg.pairwise_del && n_blocks <= 65535) ? n_blocks * (uint64_t) ctx->n_tiles * NGSD_TILE_ELEMS : 0;
+    if (ctx->cache_valid && ctx->cache_blocks == n_blocks && ctx->cache_bs == block_size) {
+      use_cache = true;
+    } else {
+      size_t fr = 0, tot = 0;
+      NGSD_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
+      const uint64_t avail = (uint64_t) fr + ctx->cache_doubles * sizeof(double) + ctx->cnt_cache_elems * sizeof(uint32_t);
+      if (need * sizeof(double) + need_cnt * sizeof(uint32_t) + ((uint64_t) 3 << 30) <= avail) {
+        if (need_cnt > ctx->cnt_cache_elems) {
+          cudaFree(ctx->d_cnt_cache);
+          ctx->d_cnt_cache = nullptr;
+          ctx->cnt_cache_elems = 0;
+          NGSD_CUDA(ctx, dev_alloc(&ctx->d_cnt_cache, need_cnt));
+          ctx->cnt_cache_elems = need_cnt;
+        }
+        if (need > ctx->cache_doubles) {
+          cudaFree(ctx->d_cache);
+          ctx->d_cache = nullptr;
+          ctx->cache_doubles = 0;
+          ctx->cache_valid = false;
+          NGSD_CUDA(ctx, dev_alloc(&ctx->d_cache, need));
+          ctx->cache_doubles = need;
+        }
+        use_cache = build_cache = true;
+      }
+    }
+  }
+
+  const bool need_site_weights = weighted && (!use_cache || ctx->planes == 2);   // cached replicates only need them for the c-vector
+  if (weighted && !need_site_weights) {
+    active_sites = 0;
+    for (uint64_t b = 0; b < n_blocks; b++) active_sites += block_counts[b] ? block_size : 0;
+  }
+  if (need_site_weights) {
     active_sites = 0;
     memset(h_w, 0, bytes_w);
     for (uint64_t b = 0; b < n_blocks; b++) {
@@ -638,7 +704,7 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
       active_sites += block_size;
     }
     n_chunks = 0;
-    for (uint64_t c = 0; c < NCu; c++) {
+    for (uint64_t c = 0; c < NCu && !use_cache; c++) {
       bool any = false;
       for (uint64_t k = 0; k < SC; k++) any |= h_w[c * SC + k] != 0.0;
       if (any) h_c[n_chunks++] = (uint32_t) c;
@@ -647,7 +713,7 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
     // class (stable), let every K split lie inside one class and carry the weight as a per-split scale: the inner loop
     // of k_dist_dmma then needs no per-site multiplies at all (DMMA and DMUL share one pipe).
     uniform_scale = (block_size % SC == 0) && !em_path;
-    if (uniform_scale) {
+    if (uniform_scale && !use_cache) {
       std::vector<uint32_t> sorted;
       sorted.reserve(n_chunks);
       class_end.clear();
@@ -661,7 +727,8 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
       memcpy(h_c, sorted.data(), n_chunks * sizeof(uint32_t));
     }
   }
-  if (ctx->cfg.pairwise_del) n_entries = build_count_entries(ctx, block_counts, n_blocks, block_size, maxw, h_ew, h_em);
+  const bool cnt_cacheable = use_cache && ctx->cfg.pairwise_del && n_blocks <= 65535 && ctx->d_cnt_cache != nullptr;
+  if (ctx->cfg.pairwise_del && !cnt_cacheable) n_entries = build_count_entries(ctx, block_counts, n_blocks, block_size, maxw, h_ew, h_em);
 
   if (ctx->n_tiles == 0) {   // a tile shard that owns nothing: all-zero contribution
     int rc0 = ensure_dist_buffers(ctx, 1);
@@ -677,33 +744,32 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
     ctx->timing = ngsd_timing();
     return NGSD_OK;
   }
-  // ---- bootstrap block cache -------------------------------------------------------------------------------------
-  // Resampling is by whole blocks (ngsDist.cpp:416-437), so num_r(i,j) = sum_b c_r[b] * G_b(i,j) with G_b the sum over
-  // the sites of source block b: compute the per-block partials ONCE (K splits = blocks) and every replicate is a
-  // weighted split reduction in the epilogue -- ~100x less work per replicate at C3 (SURVEY §7 design option (a)).
-  // It needs blocks that are whole site chunks and room for n_blocks partials; otherwise (and with ngsd_cfg.reserved
-  // bit 2, which benchmarks of the per-replicate weighted contraction set) the replicate is contracted directly.
-  const uint64_t em_ld = em_path ? ngsd_em_ld(ctx) : 0;
-  bool use_cache = false, build_cache = false;
-  if (weighted && !(ctx->cfg.reserved & 4) && !getenv("NGSD_NO_BLOCK_CACHE") && block_size % SC == 0 && n_blocks >= 2 &&
-      n_blocks < 0x7fffffffull / std::max<uint32_t>(ctx->n_tiles, 1)) {
-    const uint64_t need = em_path ? n_blocks * em_ld * em_ld : n_blocks * (uint64_t) ctx->n_tiles * NGSD_TILE_ELEMS;
-    if (ctx->cache_valid && ctx->cache_blocks == n_blocks && ctx->cache_bs == block_size) {
-      use_cache = true;
-    } else {
-      size_t fr = 0, tot = 0;
-      NGSD_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
-      const uint64_t avail = (uint64_t) fr + ctx->cache_doubles * sizeof(double);
-      if (need * sizeof(double) + ((uint64_t) 3 << 30) <= avail) {
-        if (need > ctx->cache_doubles) {
-          cudaFree(ctx->d_cache);
-          ctx->d_cache = nullptr;
-          ctx->cache_doubles = 0;
-          ctx->cache_valid = false;
-          NGSD_CUDA(ctx, dev_alloc(&ctx->d_cache, need));
-          ctx->cache_doubles = need;
+  // shared-site counts of the cached path: K3 with one split per source block, kept next to the per-block sums
+  const bool cnt_cached = use_cache && ctx->cfg.pairwise_del && n_blocks <= 65535 && ctx->d_cnt_cache != nullptr &&
+                          ctx->cnt_cache_elems >= n_blocks * (uint64_t) ctx->n_tiles * NGSD_TILE_ELEMS;
+  std::vector<uint32_t> ent_begin;
+  if (cnt_cached) {
+    n_entries = 0;
+    if (build_cache) {
+      ent_begin.resize(n_blocks + 1);
+      for (uint64_t b = 0; b < n_blocks; b++) {
+        ent_begin[b] = (uint32_t) n_entries;
+        uint64_t s0 = b * block_size, s1 = s0 + block_size;
+        while (s0 < s1) {   // the block's bits, word by word
+          const uint64_t w = s0 >> 6, lo = s0 & 63, hi = std::min<uint64_t>(64, lo + (s1 - s0));
+          h_ew[n_entries] = (uint32_t) w;
+          h_em[n_entries] = (hi == 64 ? ~0ull : ((1ull << hi) - 1)) & ~((1ull << lo) - 1);
+          n_entries++;
+          s0 += hi - lo;
         }
-        use_cache = build_cache = true;
+      }
+      ent_begin[n_blocks] = (uint32_t) n_entries;
+      if (n_blocks + 1 > ctx->ent_begin_cap) {
+        cudaFree(ctx->d_ent_begin);
+        ctx->d_ent_begin = nullptr;
+        ctx->ent_begin_cap = 0;
+        NGSD_CUDA(ctx, dev_alloc(&ctx->d_ent_begin, n_blocks + 1));
+        ctx->ent_begin_cap = n_blocks + 1;
       }
     }
   }
@@ -772,6 +838,7 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   }
   ctx->cur_partials = use_cache ? ctx->d_cache : ctx->d_partials;
   ctx->cur_split_w = use_cache ? ctx->d_split_scale : nullptr;
+  ctx->cur_cnt_cache = cnt_cached ? ctx->d_cnt_cache : nullptr;
 
   ctx->timing = ngsd_timing();
   // (pageable source: the copy is staged before the call returns, so `splits` may go out of scope afterwards)
@@ -779,7 +846,7 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   if (uniform_scale || use_cache)
     NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_split_scale, scales.data(), scales.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (weighted) {
-    if (!uniform_scale || ctx->planes == 2)   // per-site weights: scaled B fragments and/or the weighted c-vector
+    if (need_site_weights && (!uniform_scale || ctx->planes == 2))   // per-site weights: scaled B fragments and/or the weighted c-vector
       NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_weights, h_w, bytes_w, cudaMemcpyHostToDevice, ctx->stream));
     if (!use_cache) NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_chunk_ids, h_c, n_chunks * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   }
@@ -787,10 +854,13 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
     NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_ent_word, h_ew, n_entries * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_ent_mask, h_em, n_entries * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
   }
+  if (!ent_begin.empty())
+    NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_ent_begin, ent_begin.data(), ent_begin.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   int launches = 0;
   const bool do_count = ctx->cfg.pairwise_del != 0;
+  const bool run_count = do_count && !(cnt_cached && !build_cache);   // cached counts of this geometry are resident
   tick(ctx, 2);
-  if (do_count) NGSD_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));   // entry lists are on the device
+  if (run_count) NGSD_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));   // entry lists are on the device
   tick(ctx, 3);
   // K2 / K2b first, so that its persistent CTAs own every SM; K3 is then launched on the auxiliary stream and its
   // (small) CTAs co-reside with them: integer AND+POPC in the shadow of the FP64 contraction.
@@ -805,16 +875,18 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   } else {
     NGSD_CUDA(ctx, cudaMemsetAsync(ctx->d_partials, 0, (uint64_t) plan.n_units * NGSD_TILE_ELEMS * sizeof(double), ctx->stream));
   }
+  NGSD_CUDA(ctx, dbg_sync(ctx, "contraction"));
   tick(ctx, 4);
-  if (do_count) {
+  if (run_count) {
     NGSD_CUDA(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
     NGSD_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->aux_stream));
-    NGSD_CUDA(ctx, ngsd_launch_mask_count(ctx, n_entries, ctx->aux_stream));
+    NGSD_CUDA(ctx, ngsd_launch_mask_count(ctx, n_entries, ctx->aux_stream, cnt_cached ? (uint32_t) n_blocks : 0u));
     NGSD_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->aux_stream));
     NGSD_CUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->aux_stream));
     NGSD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
     launches += n_entries ? 1 : 0;
   }
+  NGSD_CUDA(ctx, dbg_sync(ctx, "mask count"));
   tick(ctx, 8);
   if (!em_path && ctx->planes == 2) {
     NGSD_CUDA(ctx, ngsd_launch_cvec(ctx, weighted, n_eff));
@@ -831,6 +903,7 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
     NGSD_CUDA(ctx, ngsd_launch_epilogue(ctx, ea));
     launches += 2;
   }
+  NGSD_CUDA(ctx, dbg_sync(ctx, "epilogue"));
   tick(ctx, 5);
   const uint64_t n2 = ctx->n_ind * ctx->n_ind;
   if (out) NGSD_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, n2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -839,7 +912,7 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   float ms;
   ctx->timing.count_ms = 0;
-  if (do_count) { cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ctx->timing.count_ms = ms; }   // overlaps dist_ms
+  if (run_count) { cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ctx->timing.count_ms = ms; }   // overlaps dist_ms
   cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->timing.dist_ms = ms;
   cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[5]); ctx->timing.epilogue_ms = ms;
   cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[5]); ctx->timing.total_ms = ms;
@@ -855,6 +928,7 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   }
   ctx->cur_partials = ctx->d_partials;
   ctx->cur_split_w = nullptr;
+  ctx->cur_cnt_cache = nullptr;
   return NGSD_OK;
 }
 
@@ -873,6 +947,7 @@ int ngsd_set_tile_shard(ngsd_ctx *ctx, uint32_t rank, uint32_t world) {
   ctx->n_diag_tiles = 0;
   for (auto &t : mine) ctx->n_diag_tiles += (t.ti == t.tj);
   if (!mine.empty()) NGSD_CUDA(ctx, cudaMemcpy(ctx->d_tiles, mine.data(), mine.size() * sizeof(ngsd_tile), cudaMemcpyHostToDevice));
+  NGSD_CUDA(ctx, upload_tile_index(ctx, mine));
   ctx->shard_rank = rank;
   ctx->shard_world = world;
   ctx->cache_valid = false;

@@ -293,6 +293,9 @@ struct EmEpiArgs {
   const double *partials;
   const double *split_w;      // [n_splits] weight of each split (bootstrap block cache) or nullptr
   const uint32_t *cnt;        // [n_pad][n_pad] or nullptr
+  const uint32_t *cnt_cache;  // per-block counts [n_splits][n_tiles128][4][64][64] (bootstrap block cache) or nullptr
+  const uint32_t *tile_index; // [RB][RB] position of the 128 x 128 tile (ti, tj) in K3's tile list
+  uint32_t n_tiles128, RB;
   double *out, *num;
   uint64_t *cntout;
   uint64_t n_ind, n_pad, ld, const_cnt, tot_sites;
@@ -321,6 +324,17 @@ __global__ void __launch_bounds__(256) k_epilogue_em(EmEpiArgs a) {
     for (uint32_t q = 0; q < a.n_splits; q++) num += a.partials[((uint64_t) q * a.ld + i) * a.ld + j];
   }
   uint64_t cnt = a.cnt ? (uint64_t) a.cnt[i * a.n_pad + j] : a.const_cnt;
+  if (a.cnt_cache) {          // sum_b c[b] * cnt_b(i,j) from the 128 x 128 tile list of K3 (row-major upper triangle in bands)
+    const uint32_t t = a.tile_index[(i >> 7) * a.RB + (j >> 7)];
+    const int rr = (int) (i & 127), cc = (int) (j & 127);
+    const uint32_t *pc = a.cnt_cache + ((uint64_t) t * 4 + (rr >> 6) * 2 + (cc >> 6)) * 4096 + (rr & 63) * 64 + (cc & 63);
+    const uint64_t cstride = (uint64_t) a.n_tiles128 * 4 * 4096;
+    cnt = 0;
+    for (uint32_t q = 0; q < a.n_splits; q++) {
+      const double w = a.split_w[q];
+      if (w != 0.0) cnt += (uint64_t) w * (uint64_t) pc[(uint64_t) q * cstride];
+    }
+  }
   if (a.num) a.num[i * a.n_ind + j] = a.num[j * a.n_ind + i] = num;
   if (a.cntout) a.cntout[i * a.n_ind + j] = a.cntout[j * a.n_ind + i] = cnt;
   if (a.tot_sites > 0) cnt = a.tot_sites;
@@ -390,7 +404,11 @@ cudaError_t ngsd_launch_epilogue_em(ngsd_ctx *ctx, uint32_t n_splits, uint64_t c
   EmEpiArgs a;
   a.partials = ctx->cur_partials;
   a.split_w = ctx->cur_split_w;
-  a.cnt = use_cnt ? ctx->d_cnt : nullptr;
+  a.cnt = (use_cnt && !ctx->cur_cnt_cache) ? ctx->d_cnt : nullptr;
+  a.cnt_cache = use_cnt ? ctx->cur_cnt_cache : nullptr;
+  a.tile_index = ctx->d_tile_index;
+  a.n_tiles128 = ctx->n_tiles;
+  a.RB = (uint32_t) ctx->RB;
   a.out = ctx->d_out;
   a.num = ctx->d_num;
   a.cntout = ctx->d_cntout;

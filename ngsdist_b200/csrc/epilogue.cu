@@ -12,6 +12,7 @@ struct EpiArgs {
   const double *split_w;      // [n_splits] weight of each split (bootstrap block cache) or nullptr
   const ngsd_tile *tiles;
   const uint32_t *cnt;        // [n_pad][n_pad] or nullptr
+  const uint32_t *cnt_cache;  // per-block counts [n_splits][n_tiles][4][64][64] (bootstrap block cache) or nullptr
   const double *cvec;         // [n_pad] 2-plane mode: weighted row sums of the B_2 plane, added for column j; or nullptr
   double *out, *num;          // [n_ind][n_ind]
   uint64_t *cntout;
@@ -73,6 +74,16 @@ __global__ void __launch_bounds__(256) k_epilogue(EpiArgs a) {
     if (i >= j || j >= a.n_ind) continue;
     const double num = (c ? s1 : s0) + (a.cvec ? a.cvec[j] : 0.0);
     uint64_t cnt = a.cnt ? (uint64_t) a.cnt[i * a.n_pad + j] : a.const_cnt;
+    if (a.cnt_cache) {        // sum_b c[b] * cnt_b(i,j): integers, exact
+      const int rr = row, cc = col0 + c;
+      const uint32_t *pc = a.cnt_cache + ((uint64_t) t * 4 + (rr >> 6) * 2 + (cc >> 6)) * 4096 + (rr & 63) * 64 + (cc & 63);
+      const uint64_t cstride = (uint64_t) a.n_tiles * 4 * 4096;
+      cnt = 0;
+      for (uint32_t q2 = 0; q2 < a.n_splits; q2++) {
+        const double w = a.split_w[q2];
+        if (w != 0.0) cnt += (uint64_t) w * (uint64_t) pc[(uint64_t) q2 * cstride];
+      }
+    }
     if (a.num) a.num[i * a.n_ind + j] = a.num[j * a.n_ind + i] = num;
     if (a.cntout) a.cntout[i * a.n_ind + j] = a.cntout[j * a.n_ind + i] = cnt;
     if (a.tot_sites > 0) cnt = a.tot_sites;
@@ -141,7 +152,8 @@ cudaError_t ngsd_launch_epilogue(ngsd_ctx *ctx, const ngsd_epilogue_args &e) {
   a.partials = ctx->cur_partials;
   a.split_w = ctx->cur_split_w;
   a.tiles = ctx->d_tiles;
-  a.cnt = e.use_cnt ? ctx->d_cnt : nullptr;
+  a.cnt = (e.use_cnt && !ctx->cur_cnt_cache) ? ctx->d_cnt : nullptr;
+  a.cnt_cache = e.use_cnt ? ctx->cur_cnt_cache : nullptr;
   a.cvec = ctx->planes == 2 ? ctx->d_cvec : nullptr;
   a.out = ctx->d_out;
   a.num = ctx->d_num;

@@ -18,6 +18,11 @@ struct CountArgs {
   uint32_t *cnt;              // [n_pad][n_pad], zeroed
   uint64_t NW, n_pad, n_entries;
   uint32_t n_splits;
+  // bootstrap block cache: split y = source block y, entries [ent_begin[y], ent_begin[y+1]); the per-block counts are
+  // stored (no atomics) to cache[((y * n_tiles + tile) * 4 + quadrant) * 4096 + row * 64 + col]
+  const uint32_t *ent_begin;
+  uint32_t *cache;
+  uint32_t n_tiles;
 };
 
 // grid (4 * n_tiles, n_splits): a CTA owns the 64 x 64 quadrant `blockIdx.x & 3` of tile `blockIdx.x >> 2`.
@@ -31,7 +36,8 @@ __global__ void __launch_bounds__(128, 8) k_mask_count(CountArgs a) {
   const ngsd_tile tl = a.tiles[blockIdx.x >> 2];
   const int qr = (blockIdx.x >> 1) & 1, qc = blockIdx.x & 1;
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-  const uint64_t e0 = (a.n_entries * blockIdx.y) / a.n_splits, e1 = (a.n_entries * (blockIdx.y + 1)) / a.n_splits;
+  const uint64_t e0 = a.ent_begin ? a.ent_begin[blockIdx.y] : (a.n_entries * blockIdx.y) / a.n_splits;
+  const uint64_t e1 = a.ent_begin ? a.ent_begin[blockIdx.y + 1] : (a.n_entries * (blockIdx.y + 1)) / a.n_splits;
   const uint64_t *ma = a.mask + (uint64_t) tl.ti * a.NW * 128 + qr * 64;
   const uint64_t *mb = a.mask + (uint64_t) tl.tj * a.NW * 128 + qc * 64;
   uint32_t acc[8][4];
@@ -69,6 +75,14 @@ __global__ void __launch_bounds__(128, 8) k_mask_count(CountArgs a) {
       }
     }
   }
+  if (a.cache) {
+    uint32_t *dst = a.cache + ((uint64_t) blockIdx.y * a.n_tiles * 4 + blockIdx.x) * 4096;
+#pragma unroll
+    for (int r = 0; r < 8; r++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) dst[(r * 8 + ty) * 64 + c * 16 + tx] = acc[r][c];
+    return;
+  }
 #pragma unroll
   for (int r = 0; r < 8; r++)
 #pragma unroll
@@ -80,10 +94,13 @@ __global__ void __launch_bounds__(128, 8) k_mask_count(CountArgs a) {
 
 }  // namespace
 
-cudaError_t ngsd_launch_mask_count(ngsd_ctx *ctx, uint64_t n_entries, cudaStream_t stream) {
-  cudaError_t e = cudaMemsetAsync(ctx->d_cnt, 0, ctx->n_pad * ctx->n_pad * sizeof(uint32_t), stream);
-  if (e != cudaSuccess) return e;
-  if (n_entries == 0) return cudaSuccess;
+cudaError_t ngsd_launch_mask_count(ngsd_ctx *ctx, uint64_t n_entries, cudaStream_t stream, uint32_t cache_blocks) {
+  cudaError_t e = cudaSuccess;
+  if (!cache_blocks) {
+    e = cudaMemsetAsync(ctx->d_cnt, 0, ctx->n_pad * ctx->n_pad * sizeof(uint32_t), stream);
+    if (e != cudaSuccess) return e;
+    if (n_entries == 0) return cudaSuccess;
+  }
   // same shared-memory carveout as k_dist_dmma, otherwise the SMs would have to drain before K3 could be placed on them
   e = cudaFuncSetAttribute(k_mask_count, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
   if (e != cudaSuccess) return e;
@@ -100,6 +117,14 @@ cudaError_t ngsd_launch_mask_count(ngsd_ctx *ctx, uint64_t n_entries, cudaStream
   uint64_t maxs = (n_entries + kEB - 1) / kEB;
   a.n_splits = (uint32_t) (want < 1 ? 1 : (want > maxs ? maxs : want));
   if (a.n_splits > 65535) a.n_splits = 65535;
+  a.ent_begin = nullptr;
+  a.cache = nullptr;
+  a.n_tiles = ctx->n_tiles;
+  if (cache_blocks) {          // one split per source block (gridDim.y <= 65535: checked by the caller)
+    a.n_splits = cache_blocks;
+    a.ent_begin = ctx->d_ent_begin;
+    a.cache = ctx->d_cnt_cache;
+  }
   k_mask_count<<<dim3(4 * ctx->n_tiles, a.n_splits), 128, 0, stream>>>(a);
   return cudaGetLastError();
 }

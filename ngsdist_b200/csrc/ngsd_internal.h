@@ -77,6 +77,7 @@ struct ngsd_ctx {
   int stage_next = 0;
   // distance workspaces (allocated lazily)
   ngsd_tile *d_tiles = nullptr; uint32_t n_tiles = 0;
+  uint32_t *d_tile_index = nullptr;            // [RB][RB] position of tile (ti, tj) in d_tiles (0xFFFFFFFF: not owned)
   double *d_partials = nullptr; uint64_t partial_slots = 0;
   // what the contraction launchers write and the epilogues read: d_partials, or the per-block cache below
   double *cur_partials = nullptr;
@@ -84,6 +85,9 @@ struct ngsd_ctx {
   // bootstrap block cache: per-block partial sums, computed once; every replicate is then a weighted sum of them
   double *d_cache = nullptr; uint64_t cache_doubles = 0, cache_blocks = 0, cache_bs = 0;
   bool cache_valid = false;
+  uint32_t *d_cnt_cache = nullptr; uint64_t cnt_cache_elems = 0;   // per-block shared-site counts [block][tile][4][64][64]
+  uint32_t *d_ent_begin = nullptr; uint64_t ent_begin_cap = 0;
+  const uint32_t *cur_cnt_cache = nullptr;     // set while the epilogue should take cnt from the block cache
   double *d_weights = nullptr;                 // [NC*8] per-site bootstrap weights
   uint32_t *d_chunk_ids = nullptr;             // [NC] active chunk list
   uint32_t *d_split_begin = nullptr; uint32_t split_cap = 0;
@@ -131,7 +135,7 @@ struct ngsd_dist_plan {
   int grid;
 };
 cudaError_t ngsd_launch_dist_dmma(ngsd_ctx *ctx, const ngsd_dist_plan &p);
-cudaError_t ngsd_launch_mask_count(ngsd_ctx *ctx, uint64_t n_entries, cudaStream_t stream);
+cudaError_t ngsd_launch_mask_count(ngsd_ctx *ctx, uint64_t n_entries, cudaStream_t stream, uint32_t cache_blocks = 0);
 struct ngsd_epilogue_args {
   uint32_t n_splits;
   uint64_t const_cnt;       // used when !pairwise_del
