@@ -436,8 +436,34 @@ static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n
   uint32_t maxw = 1;
   if (weighted)
     for (uint64_t b = 0; b < n_blocks; b++) maxw = std::max(maxw, block_counts[b]);
-  const uint32_t layers = (maxw + 126) / 127;                  // site weights are int8 operand bytes: <= 127 per layer
   const bool do_count = ctx->cfg.pairwise_del != 0;
+  // ---- bootstrap block cache (see ngsd_distances): per-block int32 partials, blocks = whole 64-site words ----
+  const uint64_t unit_ints = do_count ? 2 * NGSD_TILE_ELEMS : NGSD_TILE_ELEMS;
+  bool use_cache = false, build_cache = false;
+  if (weighted && !(ctx->cfg.reserved & 4) && !getenv("NGSD_NO_BLOCK_CACHE") && block_size % 64 == 0 && n_blocks >= 2 &&
+      ctx->n_tiles > 0 && n_blocks < 0x7fffffffull / ctx->n_tiles &&
+      (uint64_t) std::max(ctx->int_max_byte, 1) * block_size < 2147483647ull) {
+    const uint64_t need = (n_blocks * (uint64_t) ctx->n_tiles * unit_ints + 1) / 2;   // in doubles
+    if (ctx->cache_valid && ctx->cache_blocks == n_blocks && ctx->cache_bs == block_size) {
+      use_cache = true;
+    } else {
+      size_t fr = 0, tot = 0;
+      NGSD_CUDA(ctx, cudaMemGetInfo(&fr, &tot));
+      if (need * sizeof(double) + ((uint64_t) 3 << 30) <= (uint64_t) fr + ctx->cache_doubles * sizeof(double)) {
+        if (need > ctx->cache_doubles) {
+          cudaFree(ctx->d_cache);
+          ctx->d_cache = nullptr;
+          ctx->cache_doubles = 0;
+          ctx->cache_valid = false;
+          NGSD_CUDA(ctx, dev_alloc(&ctx->d_cache, need));
+          ctx->cache_doubles = need;
+        }
+        use_cache = build_cache = true;
+      }
+    }
+  }
+  if (use_cache) maxw = 1;                                     // the contraction (if any) runs unweighted, K splits = blocks
+  const uint32_t layers = (maxw + 126) / 127;                  // site weights are int8 operand bytes: <= 127 per layer
   const uint64_t ent_max = 0;   // the counts are a second int8 GEMM inside K2c: no K3 entry list
   const uint64_t bytes_w = (uint64_t) layers * nsp, bytes_ids = (uint64_t) layers * NW * sizeof(uint32_t);
   int rc = ensure_pinned(ctx, bytes_w + 2 * bytes_ids + ent_max * (sizeof(uint32_t) + sizeof(uint64_t)) + 256);
@@ -451,8 +477,12 @@ static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n
   // per-site weights (bootstrap multiplicities of ngsDist.cpp:416-437; 1 for replicate 0; 0 beyond the sites in use)
   uint64_t active_sites = n_eff;
   memset(h_w, 0, bytes_w);
-  if (!weighted) {
+  if (!weighted || use_cache) {
     memset(h_w, 1, ctx->n_sites);
+    if (weighted) {
+      active_sites = 0;
+      for (uint64_t b = 0; b < n_blocks; b++) active_sites += block_counts[b] ? block_size : 0;
+    }
   } else {
     active_sites = 0;
     for (uint64_t b = 0; b < n_blocks; b++) {
@@ -466,7 +496,11 @@ static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n
     }
   }
   uint64_t n_words = 0;
-  for (uint32_t l = 0; l < layers; l++)
+  if (use_cache) {                                             // identity word list over the blocks in use
+    n_words = n_blocks * (block_size / 64);
+    for (uint64_t w = 0; w < n_words && build_cache; w++) { h_ids[w] = (uint32_t) w; h_layer[w] = 0; }
+  }
+  for (uint32_t l = 0; l < layers && !use_cache; l++)
     for (uint64_t w = 0; w < NW; w++) {
       const uint64_t *p8 = (const uint64_t *) (h_w + (uint64_t) l * nsp + w * 64);
       if (p8[0] | p8[1] | p8[2] | p8[3] | p8[4] | p8[5] | p8[6] | p8[7]) { h_ids[n_words] = (uint32_t) w; h_layer[n_words] = l; n_words++; }
@@ -492,8 +526,17 @@ static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n
 
   // K splits of the word list; an int32 accumulator must hold max_byte * weight * sites of one split
   int grid = ctx->n_sm * ngsd_imma_ctas_per_sm();
-  std::vector<uint32_t> splits = plan_splits((uint32_t) n_words, ctx->n_tiles, (double) ctx->n_tiles, grid);
-  {
+  std::vector<uint32_t> splits;
+  std::vector<double> scales;
+  if (use_cache) {
+    splits.resize(n_blocks + 1);
+    for (uint64_t b = 0; b <= n_blocks; b++) splits[b] = (uint32_t) (b * (block_size / 64));
+    scales.resize(n_blocks);
+    for (uint64_t b = 0; b < n_blocks; b++) scales[b] = (double) block_counts[b];
+  } else {
+    splits = plan_splits((uint32_t) n_words, ctx->n_tiles, (double) ctx->n_tiles, grid);
+  }
+  if (!use_cache) {
     const uint64_t per_word = (uint64_t) std::max(ctx->int_max_byte, 1) * std::min<uint32_t>(maxw, 127) * 64;
     const uint32_t cap = (uint32_t) std::max<uint64_t>(1, 2147483647ull / per_word);
     std::vector<uint32_t> cut;
@@ -508,7 +551,7 @@ static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n
   const uint32_t n_splits = (uint32_t) splits.size() - 1;
   const uint64_t n_units = (uint64_t) n_splits * ctx->n_tiles;
   grid = (int) std::min<uint64_t>(grid, std::max<uint64_t>(n_units, 1));
-  rc = ensure_dist_buffers(ctx, do_count ? n_units + 1 : n_units / 2 + 1);   // int32 partials: sum tile (+ count tile) per unit
+  rc = ensure_dist_buffers(ctx, use_cache ? 1 : (do_count ? n_units + 1 : n_units / 2 + 1));   // int32 partials: sum tile (+ count tile) per unit
   if (rc) return rc;
   if (bytes_w > ctx->wsite_cap) {
     cudaFree(ctx->d_wsite);
@@ -537,17 +580,21 @@ static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n
     ctx->split_cap = (uint32_t) splits.size() + 64;
   }
 
+  ctx->cur_partials = use_cache ? ctx->d_cache : ctx->d_partials;      // (after every (re)allocation above)
+  ctx->cur_split_w = use_cache ? ctx->d_split_scale : nullptr;
   ctx->timing = ngsd_timing();
   NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_split_begin, splits.data(), splits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
-  NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_wsite, h_w, bytes_w, cudaMemcpyHostToDevice, ctx->stream));
-  if (n_words) {
+  if (use_cache) NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_split_scale, scales.data(), scales.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  const bool run_kernel = n_words && !(use_cache && !build_cache);
+  if (run_kernel) NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_wsite, h_w, bytes_w, cudaMemcpyHostToDevice, ctx->stream));
+  if (run_kernel) {
     NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_word_ids, h_ids, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
     NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_word_layer, h_layer, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   }
   int launches = 0;
   tick(ctx, 2);
   tick(ctx, 3);
-  if (n_words) {
+  if (run_kernel) {
     NGSD_CUDA(ctx, ngsd_launch_dist_imma(ctx, (uint32_t) n_units, grid, do_count));
     launches += do_count ? 2 : 1;
   }
@@ -569,8 +616,16 @@ static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n
   cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[5]); ctx->timing.total_ms = ms;
   ctx->timing.launches = launches;
   ctx->timing.dist_ctas = grid;
-  ctx->timing.dist_imma = (uint64_t) n_words * (do_count ? 10 : 8) * ctx->n_tiles * 128ull;   // 8 (+2 count) k-steps per word, 8 warps x 16 IMMA per k-step
+  ctx->timing.dist_imma = run_kernel ? (uint64_t) n_words * (do_count ? 10 : 8) * ctx->n_tiles * 128ull : 0;   // 8 (+2 count) k-steps per word, 8 warps x 16 IMMA per k-step
   ctx->timing.active_sites = active_sites;
+  ctx->timing.block_cache = use_cache ? (build_cache ? 1 : 2) : 0;
+  if (use_cache) {
+    ctx->cache_valid = true;
+    ctx->cache_blocks = n_blocks;
+    ctx->cache_bs = block_size;
+  }
+  ctx->cur_partials = ctx->d_partials;
+  ctx->cur_split_w = nullptr;
   return NGSD_OK;
 }
 

@@ -293,6 +293,7 @@ __global__ void k_imma_peak(int *out, int iters) {
 
 struct EpiIntArgs {
   const int32_t *partials;    // [n_splits][n_tiles][pstride] fragment order (sum tile, then count tile when in_kernel_cnt)
+  const double *split_w;      // [n_splits] integer weight of each split (bootstrap block cache) or nullptr
   uint32_t pstride;
   int in_kernel_cnt;
   const ngsd_tile *tiles;
@@ -317,11 +318,16 @@ __global__ void __launch_bounds__(256) k_epilogue_int(EpiIntArgs a) {
   const uint64_t stride = (uint64_t) a.n_tiles * (a.pstride / 4);
   long long s[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0};
   for (uint32_t q = 0; q < a.n_splits; q++) {
+    long long m = 1;
+    if (a.split_w) {                     // per-block partials x block multiplicities: integers, exact
+      m = (long long) a.split_w[q];
+      if (m == 0) continue;
+    }
     const int4 v = src[(uint64_t) q * stride];
-    s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+    s[0] += m * v.x; s[1] += m * v.y; s[2] += m * v.z; s[3] += m * v.w;
     if (a.in_kernel_cnt) {
       const int4 w = src[(uint64_t) q * stride + NGSD_TILE_ELEMS / 4];
-      c[0] += w.x; c[1] += w.y; c[2] += w.z; c[3] += w.w;
+      c[0] += m * w.x; c[1] += m * w.y; c[2] += m * w.z; c[3] += m * w.w;
     }
   }
 #pragma unroll
@@ -397,7 +403,7 @@ cudaError_t ngsd_launch_dist_imma(ngsd_ctx *ctx, uint32_t n_units, int grid, boo
   a.tiles = ctx->d_tiles;
   a.split_begin = ctx->d_split_begin;
   a.sched = ctx->d_sched;
-  a.partials = reinterpret_cast<int32_t *>(ctx->d_partials);
+  a.partials = reinterpret_cast<int32_t *>(ctx->cur_partials);
   a.NW = ctx->NW;
   a.n_tiles = ctx->n_tiles;
   a.n_units = n_units;
@@ -415,7 +421,8 @@ cudaError_t ngsd_launch_dist_imma(ngsd_ctx *ctx, uint32_t n_units, int grid, boo
 
 cudaError_t ngsd_launch_epilogue_int(ngsd_ctx *ctx, uint32_t n_splits, uint64_t const_cnt, bool use_cnt, bool in_kernel_cnt) {
   EpiIntArgs a;
-  a.partials = reinterpret_cast<const int32_t *>(ctx->d_partials);
+  a.partials = reinterpret_cast<const int32_t *>(ctx->cur_partials);
+  a.split_w = ctx->cur_split_w;
   a.pstride = in_kernel_cnt ? 2 * NGSD_TILE_ELEMS : NGSD_TILE_ELEMS;
   a.in_kernel_cnt = in_kernel_cnt ? 1 : 0;
   a.tiles = ctx->d_tiles;

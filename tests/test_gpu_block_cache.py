@@ -69,3 +69,58 @@ def test_block_cache_is_rebuilt_after_new_data_and_new_geometry():
         sm = np.concatenate([np.arange(b * bs, (b + 1) * bs) for b in range(len(c)) for _ in range(int(c[b]))])
         o = oracle.distances(P, indep=True, pairwise_del=True, evol_model=0, site_map=sm)
         assert_close(got["num"], o["num"])
+
+
+@pytest.mark.parametrize("pdel", [True, False])
+def test_block_cache_integer_path_is_exact(pdel):
+    """Called genotypes: per-block int32 partials (blocks = whole 64-site words) weighted in int64 -- identical to the
+    direct weighted contraction, cnt and (with --pairwise_del) num bit-exact against the oracle."""
+    n_ind, n_sites, bs, nrep = 200, 2000, 128, 3
+    raw = oracle.synth_raw(9, 0.1, n_ind, n_sites)
+    res = {}
+    for cache in (True, False):
+        p = nb().Params(n_ind=n_ind, n_sites=n_sites, in_probs=True, call_geno=True, pairwise_del=pdel, evol_model=0,
+                        n_boot_rep=nrep, boot_block_size=bs, seed=3, no_block_cache=not cache)
+        with nb().NgsDistB200(p) as g:
+            g.push_sites(raw)
+            g.frontend()
+            out, flags = [], []
+            for rep in range(nrep + 1):
+                if rep == 0:
+                    out.append(g.distances(want_num=True, want_cnt=True))
+                else:
+                    c, b = g.next_boot_counts()
+                    out.append(g.distances(c, b, want_num=True, want_cnt=True))
+                flags.append(g.timing().block_cache)
+            res[cache] = out
+        assert flags == ([0, 1, 2, 2] if cache else [0] * 4), flags
+    ora = oracle.run_job(raw, indep=True, call_geno=True, pairwise_del=pdel, evol_model=0, n_boot_rep=nrep, boot_block_size=bs, seed=3)
+    for rep in range(nrep + 1):
+        a, b, o = res[True][rep], res[False][rep], ora[rep]
+        assert np.array_equal(a["cnt"], b["cnt"]) and np.array_equal(a["cnt"], o["cnt"])
+        assert np.array_equal(a["num"], b["num"]) and np.array_equal(a["dist"], b["dist"], equal_nan=True)
+        if pdel:
+            assert np.array_equal(a["num"], o["num"])
+        else:
+            assert_close(a["num"], o["num"])
+
+
+def test_block_cache_first_call_weighted_with_large_multiplicities():
+    """No replicate-0 call before the first weighted one, multiplicities far above one int8 byte: the cached path weights
+    the per-block partials in int64, so it needs no weight layers and stays exact."""
+    n_ind, n_sites, bs = 130, 1280, 128
+    raw = oracle.synth_raw(3, 0.1, n_ind, n_sites)
+    c_big = np.array([300, 0, 1, 127, 128, 0, 5, 0, 2, 254], dtype=np.uint32)
+    got = {}
+    for cache in (True, False):
+        p = nb().Params(n_ind=n_ind, n_sites=n_sites, in_probs=True, call_geno=True, pairwise_del=True, evol_model=0,
+                        no_block_cache=not cache)
+        with nb().NgsDistB200(p) as g:
+            g.push_sites(raw)
+            got[cache] = g.distances(c_big, bs, want_num=True, want_cnt=True)
+            assert g.timing().block_cache == (1 if cache else 0)
+    for k in ("cnt", "num", "dist"):
+        assert np.array_equal(got[True][k], got[False][k], equal_nan=True), k
+    sm = np.concatenate([np.arange(b * bs, (b + 1) * bs) for b in range(len(c_big)) for _ in range(int(c_big[b]))])
+    o = oracle.distances(oracle.frontend(raw, call_geno=True), indep=True, pairwise_del=True, evol_model=0, site_map=sm)
+    assert np.array_equal(got[True]["cnt"], o["cnt"]) and np.array_equal(got[True]["num"], o["num"])

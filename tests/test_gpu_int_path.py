@@ -73,7 +73,8 @@ def test_large_multiplicities_use_weight_layers():
     """Block multiplicities above 127 (one int8 operand byte) are split into layers; linearity in the weights is exact."""
     n_ind, n_sites, bs = 130, 1280, 128
     raw = oracle.synth_raw(3, 0.1, n_ind, n_sites)
-    p = nb().Params(n_ind=n_ind, n_sites=n_sites, in_probs=True, call_geno=True, pairwise_del=True, evol_model=0)
+    p = nb().Params(n_ind=n_ind, n_sites=n_sites, in_probs=True, call_geno=True, pairwise_del=True, evol_model=0,
+                    no_block_cache=True)     # the direct weighted contraction is what splits weights into layers
     with nb().NgsDistB200(p) as g:
         g.push_sites(raw)
         nbk = n_sites // bs
