@@ -10,7 +10,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-fil
 echo "launch list rc=$?"
 $NCU -k regex:k_dist_dmma -s 3 -c 1 -f -o gpurun_out/${R}_dist_dmma_c2 $BENCH > gpurun_out/${R}_ncu1.log 2>&1
 echo "dist rc=$?"
-$NCU -k 'regex:k_frontend<' -s 3 -c 1 -f -o gpurun_out/${R}_frontend_c2 $BENCH > gpurun_out/${R}_ncu2.log 2>&1
+$NCU -k 'regex:k_frontend$' -s 3 -c 1 -f -o gpurun_out/${R}_frontend_c2 $BENCH > gpurun_out/${R}_ncu2.log 2>&1
 echo "frontend rc=$?"
 C3="python tools/bench_c3.py --n-sites 100000 --reps 1"
 $C3 > gpurun_out/${R}_plain_c3.log 2>&1 &&
