@@ -26,6 +26,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "ngsd_internal.h"
 
 namespace {
@@ -296,6 +298,7 @@ struct EpiIntArgs {
   const double *split_w;      // [n_splits] integer weight of each split (bootstrap block cache) or nullptr
   uint32_t pstride;
   int in_kernel_cnt;
+  int sum_row_major;          // sum tile written by dist_umma.cu: plain [128][128] instead of mma.sync fragment order
   const ngsd_tile *tiles;
   const uint32_t *cnt;        // [n_pad][n_pad] (K3) or nullptr
   double *out, *num;
@@ -323,7 +326,14 @@ __global__ void __launch_bounds__(256) k_epilogue_int(EpiIntArgs a) {
       m = (long long) a.split_w[q];
       if (m == 0) continue;
     }
-    const int4 v = src[(uint64_t) q * stride];
+    int4 v;
+    if (a.sum_row_major) {
+      const int32_t *base = a.partials + ((uint64_t) q * a.n_tiles + t) * a.pstride;
+      const int2 lo = *reinterpret_cast<const int2 *>(base + row0 * NGSD_TILE + col0), hi = *reinterpret_cast<const int2 *>(base + (row0 + 8) * NGSD_TILE + col0);
+      v = make_int4(lo.x, lo.y, hi.x, hi.y);
+    } else {
+      v = src[(uint64_t) q * stride];
+    }
     s[0] += m * v.x; s[1] += m * v.y; s[2] += m * v.z; s[3] += m * v.w;
     if (a.in_kernel_cnt) {
       const int4 w = src[(uint64_t) q * stride + NGSD_TILE_ELEMS / 4];
@@ -383,6 +393,12 @@ bool ngsd_int_lut(const double *score, bool pairwise_del, uint32_t lut[4], doubl
 
 int ngsd_imma_ctas_per_sm() { return NGSD_IMMA_CTAS; }
 
+// NGSD_IMMA_SYNC=1 keeps the mma.sync contraction (A/B comparison against the tcgen05 path of dist_umma.cu)
+bool ngsd_use_umma() {
+  static const bool off = getenv("NGSD_IMMA_SYNC") != nullptr;
+  return !off;
+}
+
 cudaError_t ngsd_launch_dist_imma(ngsd_ctx *ctx, uint32_t n_units, int grid, bool count) {
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
@@ -410,7 +426,12 @@ cudaError_t ngsd_launch_dist_imma(ngsd_ctx *ctx, uint32_t n_units, int grid, boo
   for (int k = 0; k < 4; k++) a.lut[k] = ctx->int_lut[k];
   cudaError_t e = cudaMemsetAsync(ctx->d_sched, 0, sizeof(uint32_t), ctx->stream);
   if (e != cudaSuccess) return e;
-  k_dist_imma<false><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a);
+  if (ngsd_use_umma()) {
+    e = ngsd_launch_dist_umma(ctx, n_units, std::min(grid, ctx->n_sm), a.pstride);
+    if (e != cudaSuccess) return e;
+  } else {
+    k_dist_imma<false><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a);
+  }
   if (count) {      // second pass of the same unit list: the shared-site counts
     e = cudaMemsetAsync(ctx->d_sched, 0, sizeof(uint32_t), ctx->stream);
     if (e != cudaSuccess) return e;
@@ -425,6 +446,7 @@ cudaError_t ngsd_launch_epilogue_int(ngsd_ctx *ctx, uint32_t n_splits, uint64_t 
   a.split_w = ctx->cur_split_w;
   a.pstride = in_kernel_cnt ? 2 * NGSD_TILE_ELEMS : NGSD_TILE_ELEMS;
   a.in_kernel_cnt = in_kernel_cnt ? 1 : 0;
+  a.sum_row_major = ngsd_use_umma() ? 1 : 0;
   a.tiles = ctx->d_tiles;
   a.cnt = (use_cnt && !in_kernel_cnt) ? ctx->d_cnt : nullptr;
   a.out = ctx->d_out;

@@ -1,0 +1,317 @@
+// K2c' dist_umma: the called-genotype contraction of dist_imma.cu on the 5th-generation tensor cores:
+// tcgen05.mma kind::i8 (SASS UTCIMMA), operands in shared memory, int32 accumulators in TMEM.
+//
+// Same arithmetic as dist_imma.cu (A_i[s][k] = w_s [c_i(s) == k], B_j[s][k] = S f(k, c_j(s)), K = 4 bytes per site,
+// exact int32 accumulation) and the same (K-split, tile) units, partial buffers and epilogue.  UMMA runs the int8 GEMM
+// 3.7x faster than mma.sync (tools/probe_utcimma.cu: 2.1e15 vs 5.7e14 MAC/s) but reads its operands from shared
+// memory, so the 16x expansion of the 2-bit codes has to go through the LSU: a CTA is a four-role pipeline
+//
+//   warp 0      producer   cp.async.bulk of the packed codes (2 x 2 KiB + 64 weight bytes per 64-site stage)
+//   warps 2-17  expanders  codes -> int8 operand tiles (2 x 32 KiB per stage) in the K-major, no-swizzle UMMA layout
+//                          (8-row x 16-byte core matrices; one STS.128 = 4 sites of one row), fence.proxy.async
+//   warp 1      MMA        one lane issues 8 x tcgen05.mma (128 x 128 x 32) per stage, tcgen05.commit frees the stage
+//   warps 18-21 epilogue   tcgen05.ld of a finished unit's 128 x 128 accumulator (two TMEM buffers: the next unit's
+//                          MMAs overlap the read-out), int32 partial tile written row-major
+//
+// all connected by mbarrier rings.  The expansion (ALU + shared-memory stores), not the tensor pipe, is the limit:
+// ~26 integer ops and one 16-byte store per 16 operand bytes.
+#include <math.h>
+#include <stdlib.h>
+
+#include "ngsd_internal.h"
+
+namespace {
+
+constexpr int kRaw = 4;                           // raw (packed codes) stages
+constexpr int kExp = 3;                           // expanded operand stages
+constexpr int kExpWarps = 16, kEpiWarps = 4;
+constexpr int kThreads = (2 + kExpWarps + kEpiWarps) * 32;
+constexpr int kCodeBytes = 4 * 128 * 4;           // [4 words][128 rows] uint32, one operand of one 64-site stage
+constexpr int kRawBytes = 2 * kCodeBytes + 64;    // A codes, B codes, 64 site weights
+constexpr int kOpBytes = 16 * 16 * 128;           // expanded operand: [16 site quads][16 row groups][8 rows][16 B] = 32 KiB
+constexpr int kExpBytes = 2 * kOpBytes;
+constexpr int kNBar = 2 * kRaw + 2 * kExp + 4;
+constexpr size_t kSmemBytes = (size_t) kRaw * kRawBytes + (size_t) kExp * kExpBytes + kNBar * 8 + (kRaw + kExp + 2) * 8 + 16 + 16 + 1024;
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {}
+}
+__device__ __forceinline__ void mbar_wait_sleep(uint64_t *bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) __nanosleep(100);
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// tcgen05.commit: the mbarrier gets one arrival when every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// K-major, SWIZZLE_NONE shared-memory matrix descriptor: start >> 4 [0,14), K-direction (leading) byte offset >> 4
+// [16,30), M/N-direction (stride, between 8-row groups) byte offset >> 4 [32,46), version 1 [46,48), layout 0 [61,64)
+__device__ __forceinline__ uint64_t umma_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t) ((saddr & 0x3FFFF) >> 4) | ((uint64_t) ((lbo_bytes >> 4) & 0x3FFF) << 16) | ((uint64_t) ((sbo_bytes >> 4) & 0x3FFF) << 32) |
+         ((uint64_t) 1 << 46);
+}
+__device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+
+struct UmmaArgs {
+  const uint32_t *codes;        // [RB][NW][4][128]
+  const uint8_t *wsite;         // [n_layers][NW * 64]
+  const uint32_t *word_ids, *word_layer;
+  const ngsd_tile *tiles;
+  const uint32_t *split_begin;
+  uint32_t *sched;
+  int32_t *partials;            // [n_units][pstride], sum tile row-major [128][128]
+  uint64_t NW;
+  uint32_t n_tiles, n_units, pstride;
+  uint32_t lut[4];
+};
+
+enum : uint32_t { kFirst = 1u, kLast = 2u, kExit = 8u };
+
+__global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char *raw = smem;                                         // kRaw x kRawBytes
+  unsigned char *exps = smem + (size_t) kRaw * kRawBytes;            // kExp x kExpBytes (16-byte aligned: kRawBytes % 16 == 0)
+  uint64_t *bars = reinterpret_cast<uint64_t *>(exps + (size_t) kExp * kExpBytes);
+  uint64_t *raw_full = bars, *raw_empty = raw_full + kRaw, *exp_full = raw_empty + kRaw, *exp_empty = exp_full + kExp;
+  uint64_t *acc_full = exp_empty + kExp, *acc_empty = acc_full + 2;
+  uint32_t *raw_meta = reinterpret_cast<uint32_t *>(bars + kNBar);    // [kRaw][2] = {unit, flags}
+  uint32_t *exp_meta = raw_meta + 2 * kRaw;                           // [kExp][2]
+  uint32_t *acc_meta = exp_meta + 2 * kExp;                           // [2][2]
+  uint32_t *lut = acc_meta + 4;                                       // [4]
+  uint32_t *tmem_slot = lut + 4;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kRaw; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kExpWarps); }
+    for (int s = 0; s < kExp; s++) { mbar_init(&exp_full[s], kExpWarps); mbar_init(&exp_empty[s], 1); }
+    for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 2); mbar_init(&acc_empty[s], kEpiWarps); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    lut[0] = a.lut[0]; lut[1] = a.lut[1]; lut[2] = a.lut[2]; lut[3] = a.lut[3];
+  }
+  if (warp == 1) {                                  // TMEM: two 128-column int32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== producer =====
+    if (lane == 0) {
+      int rs = 0;
+      uint32_t rph = 0;
+      for (;;) {
+        const uint32_t u = atomicAdd(a.sched, 1u);
+        if (u >= a.n_units) break;
+        const uint32_t q = u / a.n_tiles, t = u - q * a.n_tiles;
+        const ngsd_tile tl = a.tiles[t];
+        const uint32_t c0 = a.split_begin[q], c1 = a.split_begin[q + 1];
+        const uint32_t *Ab = a.codes + (uint64_t) tl.ti * a.NW * 512;
+        const uint32_t *Bb = a.codes + (uint64_t) tl.tj * a.NW * 512;
+        for (uint32_t c = c0; c < c1; c++) {
+          const uint64_t word = a.word_ids[c];
+          const uint8_t *wsrc = a.wsite + ((uint64_t) a.word_layer[c] * a.NW + word) * 64;
+          mbar_wait_sleep(&raw_empty[rs], rph ^ 1);
+          raw_meta[rs * 2] = u;
+          raw_meta[rs * 2 + 1] = (c == c0 ? kFirst : 0u) | (c + 1 == c1 ? kLast : 0u);
+          mbar_expect_tx(&raw_full[rs], kRawBytes);
+          unsigned char *dst = raw + (size_t) rs * kRawBytes;
+          bulk_g2s(dst, Ab + word * 512, kCodeBytes, &raw_full[rs]);
+          bulk_g2s(dst + kCodeBytes, Bb + word * 512, kCodeBytes, &raw_full[rs]);
+          bulk_g2s(dst + 2 * kCodeBytes, wsrc, 64, &raw_full[rs]);
+          if (++rs == kRaw) { rs = 0; rph ^= 1; }
+        }
+      }
+      mbar_wait_sleep(&raw_empty[rs], rph ^ 1);
+      raw_meta[rs * 2 + 1] = kExit;
+      mbar_arrive(&raw_full[rs]);
+    }
+  } else if (warp == 1) {
+    // ===== MMA issue (one lane) =====
+    if (lane == 0) {
+      // D = S32 (2 << 4), A = B = INT8 (1 << 7, 1 << 10), both K-major, N = 128 (>> 3 at [17,23)), M = 128 (>> 4 at [24,29))
+      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      int es = 0, ab = 0;
+      uint32_t eph = 0, aph[2] = {0, 0};
+      for (;;) {
+        mbar_wait(&exp_full[es], eph);
+        const uint32_t u = exp_meta[es * 2], fl = exp_meta[es * 2 + 1];
+        if (fl & kExit) {
+          mbar_wait(&acc_empty[ab], aph[ab] ^ 1);
+          acc_meta[ab * 2 + 1] = kExit;
+          mbar_arrive(&acc_full[ab]);
+          mbar_arrive(&acc_full[ab]);
+          break;
+        }
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        if (fl & kFirst) {
+          mbar_wait(&acc_empty[ab], aph[ab] ^ 1);                    // the epilogue has drained this accumulator
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        }
+        const uint32_t sa = smem_u32(exps + (size_t) es * kExpBytes), sb = sa + kOpBytes;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {                               // 8 sites = K 32 per instruction; 2 site quads of 2 KiB each
+          const uint64_t da = umma_desc(sa + j * 2 * 2048, 2048, 128);
+          const uint64_t db = umma_desc(sb + j * 2 * 2048, 2048, 128);
+          umma_i8(tmem + (uint32_t) ab * 128u, da, db, idesc, ((fl & kFirst) && j == 0) ? 0u : 1u);
+        }
+        umma_commit(&exp_empty[es]);                                 // stage reusable once these MMAs have read it
+        if (fl & kLast) {
+          acc_meta[ab * 2] = u;
+          acc_meta[ab * 2 + 1] = 0;
+          umma_commit(&acc_full[ab]);                                // accumulator complete ...
+          mbar_arrive(&acc_full[ab]);                                // ... and its meta word published
+          aph[ab] ^= 1;
+          ab ^= 1;
+        }
+        if (++es == kExp) { es = 0; eph ^= 1; }
+      }
+    }
+  } else if (warp < 2 + kExpWarps) {
+    // ===== expanders: 512 threads, thread -> (row r, byte q0 of each of the 4 code words) of both operands =====
+    const int te = threadIdx.x - 64, r = te & 127, q0 = te >> 7;
+    const uint32_t unit_off = (uint32_t) (r >> 3) * 128 + (uint32_t) (r & 7) * 16;
+    int rs = 0, es = 0;
+    uint32_t rph = 0, eph = 0;
+    for (;;) {
+      mbar_wait(&raw_full[rs], rph);
+      const uint32_t u = raw_meta[rs * 2], fl = raw_meta[rs * 2 + 1];
+      mbar_wait(&exp_empty[es], eph ^ 1);
+      if (fl & kExit) {
+        if (te == 0) exp_meta[es * 2 + 1] = kExit;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&exp_full[es]);
+        break;
+      }
+      const unsigned char *rawS = raw + (size_t) rs * kRawBytes;
+      const uint32_t *cA = reinterpret_cast<const uint32_t *>(rawS) + r, *cB = reinterpret_cast<const uint32_t *>(rawS + kCodeBytes) + r;
+      const uint32_t *W32 = reinterpret_cast<const uint32_t *>(rawS + 2 * kCodeBytes) + q0;
+      unsigned char *eA = exps + (size_t) es * kExpBytes + unit_off, *eB = eA + kOpBytes;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {                                 // code word i: sites 16 i + 4 q0 .. + 3 = site quad 4 i + q0
+        const uint32_t x = (cA[i * 128] >> (8 * q0)) & 0xFFu, y = (cB[i * 128] >> (8 * q0)) & 0xFFu;
+        const uint32_t ww = W32[i * 4];
+        uint4 va, vb;
+        va.x = __funnelshift_l(0u, ww & 0xFFu, (x << 3) & 0x18u);
+        va.y = __funnelshift_l(0u, (ww >> 8) & 0xFFu, (x << 1) & 0x18u);
+        va.z = __funnelshift_l(0u, (ww >> 16) & 0xFFu, (x >> 1) & 0x18u);
+        va.w = __funnelshift_l(0u, ww >> 24, (x >> 3) & 0x18u);
+        vb.x = lut[y & 3u];
+        vb.y = lut[(y >> 2) & 3u];
+        vb.z = lut[(y >> 4) & 3u];
+        vb.w = lut[y >> 6];
+        const uint32_t off = (uint32_t) (4 * i + q0) * 2048;
+        *reinterpret_cast<uint4 *>(eA + off) = va;
+        *reinterpret_cast<uint4 *>(eB + off) = vb;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the UMMA (async) proxy
+      if (te == 0) { exp_meta[es * 2] = u; exp_meta[es * 2 + 1] = fl; }
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(&exp_full[es]); mbar_arrive(&raw_empty[rs]); }
+      if (++rs == kRaw) { rs = 0; rph ^= 1; }
+      if (++es == kExp) { es = 0; eph ^= 1; }
+    }
+  } else {
+    // ===== epilogue: a warp can read the 32 TMEM lanes (= tile rows) of its quadrant warp % 4 =====
+    const int qd = warp & 3;
+    int ab = 0;
+    uint32_t aph[2] = {0, 0};
+    for (;;) {
+      mbar_wait(&acc_full[ab], aph[ab]);
+      const uint32_t u = acc_meta[ab * 2], fl = acc_meta[ab * 2 + 1];
+      if (fl & kExit) break;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      int4 *dst = reinterpret_cast<int4 *>(a.partials + (uint64_t) u * a.pstride + (uint64_t) (qd * 32 + lane) * 128);
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t v[32];
+        const uint32_t taddr = tmem + ((uint32_t) (qd * 32) << 16) + (uint32_t) (ab * 128 + c0);
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+            : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+              "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+              "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+              "=r"(v[31])
+            : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+        for (int k = 0; k < 8; k++) dst[c0 / 4 + k] = make_int4((int) v[4 * k], (int) v[4 * k + 1], (int) v[4 * k + 2], (int) v[4 * k + 3]);
+      }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[ab]);
+      aph[ab] ^= 1;
+      ab ^= 1;
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+}
+
+}  // namespace
+
+cudaError_t ngsd_launch_dist_umma(ngsd_ctx *ctx, uint32_t n_units, int grid, uint32_t pstride) {
+  static bool attr_set[64] = {};
+  if (!attr_set[ctx->device & 63]) {
+    cudaError_t e = cudaFuncSetAttribute((const void *) k_dist_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set[ctx->device & 63] = true;
+  }
+  UmmaArgs a;
+  a.codes = ctx->codes;
+  a.wsite = ctx->d_wsite;
+  a.word_ids = ctx->d_word_ids;
+  a.word_layer = ctx->d_word_layer;
+  a.tiles = ctx->d_tiles;
+  a.split_begin = ctx->d_split_begin;
+  a.sched = ctx->d_sched;
+  a.partials = reinterpret_cast<int32_t *>(ctx->cur_partials);
+  a.NW = ctx->NW;
+  a.n_tiles = ctx->n_tiles;
+  a.n_units = n_units;
+  a.pstride = pstride;
+  for (int k = 0; k < 4; k++) a.lut[k] = ctx->int_lut[k];
+  cudaError_t e = cudaMemsetAsync(ctx->d_sched, 0, sizeof(uint32_t), ctx->stream);
+  if (e != cudaSuccess) return e;
+  k_dist_umma<<<grid, kThreads, kSmemBytes, ctx->stream>>>(a);
+  return cudaGetLastError();
+}
