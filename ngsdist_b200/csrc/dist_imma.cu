@@ -336,7 +336,14 @@ __global__ void __launch_bounds__(256) k_epilogue_int(EpiIntArgs a) {
     }
     s[0] += m * v.x; s[1] += m * v.y; s[2] += m * v.z; s[3] += m * v.w;
     if (a.in_kernel_cnt) {
-      const int4 w = src[(uint64_t) q * stride + NGSD_TILE_ELEMS / 4];
+      int4 w;
+      if (a.sum_row_major) {
+        const int32_t *base = a.partials + ((uint64_t) q * a.n_tiles + t) * a.pstride + NGSD_TILE_ELEMS;
+        const int2 lo = *reinterpret_cast<const int2 *>(base + row0 * NGSD_TILE + col0), hi = *reinterpret_cast<const int2 *>(base + (row0 + 8) * NGSD_TILE + col0);
+        w = make_int4(lo.x, lo.y, hi.x, hi.y);
+      } else {
+        w = src[(uint64_t) q * stride + NGSD_TILE_ELEMS / 4];
+      }
       c[0] += m * w.x; c[1] += m * w.y; c[2] += m * w.z; c[3] += m * w.w;
     }
   }
@@ -427,11 +434,14 @@ cudaError_t ngsd_launch_dist_imma(ngsd_ctx *ctx, uint32_t n_units, int grid, boo
   cudaError_t e = cudaMemsetAsync(ctx->d_sched, 0, sizeof(uint32_t), ctx->stream);
   if (e != cudaSuccess) return e;
   if (ngsd_use_umma()) {
-    e = ngsd_launch_dist_umma(ctx, n_units, std::min(grid, ctx->n_sm), a.pstride);
-    if (e != cudaSuccess) return e;
-  } else {
-    k_dist_imma<false><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a);
+    e = ngsd_launch_dist_umma(ctx, n_units, std::min(grid, ctx->n_sm), a.pstride, false);
+    if (e == cudaSuccess && count) {
+      e = cudaMemsetAsync(ctx->d_sched, 0, sizeof(uint32_t), ctx->stream);
+      if (e == cudaSuccess) e = ngsd_launch_dist_umma(ctx, n_units, std::min(grid, ctx->n_sm), a.pstride, true);
+    }
+    return e;
   }
+  k_dist_imma<false><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a);
   if (count) {      // second pass of the same unit list: the shared-site counts
     e = cudaMemsetAsync(ctx->d_sched, 0, sizeof(uint32_t), ctx->stream);
     if (e != cudaSuccess) return e;

@@ -27,9 +27,10 @@ constexpr int kExp = 3;                           // expanded operand stages
 constexpr int kExpWarps = 16, kEpiWarps = 4;
 constexpr int kThreads = (2 + kExpWarps + kEpiWarps) * 32;
 constexpr int kCodeBytes = 4 * 128 * 4;           // [4 words][128 rows] uint32, one operand of one 64-site stage
-constexpr int kRawBytes = 2 * kCodeBytes + 64;    // A codes, B codes, 64 site weights
+constexpr int kMaskBytes = 128 * 8;               // presence bits of one operand of one stage (count pass)
+constexpr int kRawBytes = 2 * kCodeBytes + 64;    // A codes, B codes, 64 site weights (count pass: 2 masks + weights, smaller)
 constexpr int kOpBytes = 16 * 16 * 128;           // expanded operand: [16 site quads][16 row groups][8 rows][16 B] = 32 KiB
-constexpr int kExpBytes = 2 * kOpBytes;
+constexpr int kExpBytes = 2 * kOpBytes;           // (count pass: one byte per site, [4 x 16 sites][16][8][16 B] = 8 KiB per operand)
 constexpr int kNBar = 2 * kRaw + 2 * kExp + 4;
 constexpr size_t kSmemBytes = (size_t) kRaw * kRawBytes + (size_t) kExp * kExpBytes + kNBar * 8 + (kRaw + kExp + 2) * 8 + 16 + 16 + 1024;
 
@@ -90,6 +91,7 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t d
 
 struct UmmaArgs {
   const uint32_t *codes;        // [RB][NW][4][128]
+  const uint64_t *mask;         // [RB][NW][128] presence bits (count pass)
   const uint8_t *wsite;         // [n_layers][NW * 64]
   const uint32_t *word_ids, *word_layer;
   const ngsd_tile *tiles;
@@ -103,7 +105,15 @@ struct UmmaArgs {
 
 enum : uint32_t { kFirst = 1u, kLast = 2u, kExit = 8u };
 
+// COUNT = true: the same pipeline computes the shared-site counts of --pairwise_del, cnt(i,j) = sum_s w_s m_i(s) m_j(s), as an
+// int8 GEMM with ONE byte per site (A' = w_s m_i(s), B' = m_j(s) from the presence masks; 2 MMAs per 64-site stage) and
+// writes them as the second tile of the unit's slot.
+template <bool COUNT>
 __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
+  constexpr int kStageRaw = COUNT ? 2 * kMaskBytes + 64 : kRawBytes;
+  constexpr int kOffW = COUNT ? 2 * kMaskBytes : 2 * kCodeBytes;
+  constexpr int kOp = COUNT ? kOpBytes / 4 : kOpBytes;              // expanded bytes per operand per stage
+  constexpr int kMmas = COUNT ? 2 : 8;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *raw = smem;                                         // kRaw x kRawBytes
   unsigned char *exps = smem + (size_t) kRaw * kRawBytes;            // kExp x kExpBytes (16-byte aligned: kRawBytes % 16 == 0)
@@ -115,6 +125,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
   uint32_t *acc_meta = exp_meta + 2 * kExp;                           // [2][2]
   uint32_t *lut = acc_meta + 4;                                       // [4]
   uint32_t *tmem_slot = lut + 4;
+  uint32_t *lut16 = tmem_slot + 4;                                    // [16] presence nibble -> 0x01 bytes (count pass)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
@@ -123,6 +134,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
     for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 2); mbar_init(&acc_empty[s], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     lut[0] = a.lut[0]; lut[1] = a.lut[1]; lut[2] = a.lut[2]; lut[3] = a.lut[3];
+  }
+  if (COUNT && threadIdx.x >= 32 && threadIdx.x < 48) {
+    const uint32_t n = threadIdx.x - 32;
+    lut16[n] = (n & 1u) | ((n & 2u) << 7) | ((n & 4u) << 14) | ((n & 8u) << 21);
   }
   if (warp == 1) {                                  // TMEM: two 128-column int32 accumulators
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
@@ -152,11 +167,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
           mbar_wait_sleep(&raw_empty[rs], rph ^ 1);
           raw_meta[rs * 2] = u;
           raw_meta[rs * 2 + 1] = (c == c0 ? kFirst : 0u) | (c + 1 == c1 ? kLast : 0u);
-          mbar_expect_tx(&raw_full[rs], kRawBytes);
+          mbar_expect_tx(&raw_full[rs], kStageRaw);
           unsigned char *dst = raw + (size_t) rs * kRawBytes;
-          bulk_g2s(dst, Ab + word * 512, kCodeBytes, &raw_full[rs]);
-          bulk_g2s(dst + kCodeBytes, Bb + word * 512, kCodeBytes, &raw_full[rs]);
-          bulk_g2s(dst + 2 * kCodeBytes, wsrc, 64, &raw_full[rs]);
+          if (COUNT) {
+            bulk_g2s(dst, a.mask + ((uint64_t) tl.ti * a.NW + word) * 128, kMaskBytes, &raw_full[rs]);
+            bulk_g2s(dst + kMaskBytes, a.mask + ((uint64_t) tl.tj * a.NW + word) * 128, kMaskBytes, &raw_full[rs]);
+          } else {
+            bulk_g2s(dst, Ab + word * 512, kCodeBytes, &raw_full[rs]);
+            bulk_g2s(dst + kCodeBytes, Bb + word * 512, kCodeBytes, &raw_full[rs]);
+          }
+          bulk_g2s(dst + kOffW, wsrc, 64, &raw_full[rs]);
           if (++rs == kRaw) { rs = 0; rph ^= 1; }
         }
       }
@@ -186,9 +206,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
           mbar_wait(&acc_empty[ab], aph[ab] ^ 1);                    // the epilogue has drained this accumulator
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        const uint32_t sa = smem_u32(exps + (size_t) es * kExpBytes), sb = sa + kOpBytes;
+        const uint32_t sa = smem_u32(exps + (size_t) es * kExpBytes), sb = sa + kOp;
 #pragma unroll
-        for (int j = 0; j < 8; j++) {                               // 8 sites = K 32 per instruction; 2 site quads of 2 KiB each
+        for (int j = 0; j < kMmas; j++) {                           // K 32 per instruction = two 16-byte chunks of 2 KiB each
           const uint64_t da = umma_desc(sa + j * 2 * 2048, 2048, 128);
           const uint64_t db = umma_desc(sb + j * 2 * 2048, 2048, 128);
           umma_i8(tmem + (uint32_t) ab * 128u, da, db, idesc, ((fl & kFirst) && j == 0) ? 0u : 1u);
@@ -222,6 +242,32 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
         break;
       }
       const unsigned char *rawS = raw + (size_t) rs * kRawBytes;
+      if (COUNT) {
+        // one byte per site: thread (r, q0) expands the 16 presence bits 16 q0 .. 16 q0 + 15 of its row of both operands
+        // into one 16-byte unit each (chunk q0 of the [4][16][8][16 B] operand); A bytes carry the site weights
+        const uint32_t ma = reinterpret_cast<const uint32_t *>(rawS)[r * 2 + (q0 >> 1)] >> (16 * (q0 & 1));
+        const uint32_t mb = reinterpret_cast<const uint32_t *>(rawS + kMaskBytes)[r * 2 + (q0 >> 1)] >> (16 * (q0 & 1));
+        const uint4 ww = *reinterpret_cast<const uint4 *>(rawS + kOffW + 16 * q0);
+        uint4 va, vb;
+        va.x = (lut16[ma & 15u] * 0xFFu) & ww.x;
+        va.y = (lut16[(ma >> 4) & 15u] * 0xFFu) & ww.y;
+        va.z = (lut16[(ma >> 8) & 15u] * 0xFFu) & ww.z;
+        va.w = (lut16[(ma >> 12) & 15u] * 0xFFu) & ww.w;
+        vb.x = lut16[mb & 15u];
+        vb.y = lut16[(mb >> 4) & 15u];
+        vb.z = lut16[(mb >> 8) & 15u];
+        vb.w = lut16[(mb >> 12) & 15u];
+        unsigned char *eA = exps + (size_t) es * kExpBytes + unit_off + (uint32_t) q0 * 2048;
+        *reinterpret_cast<uint4 *>(eA) = va;
+        *reinterpret_cast<uint4 *>(eA + kOp) = vb;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        if (te == 0) { exp_meta[es * 2] = u; exp_meta[es * 2 + 1] = fl; }
+        __syncwarp();
+        if (lane == 0) { mbar_arrive(&exp_full[es]); mbar_arrive(&raw_empty[rs]); }
+        if (++rs == kRaw) { rs = 0; rph ^= 1; }
+        if (++es == kExp) { es = 0; eph ^= 1; }
+        continue;
+      }
       const uint32_t *cA = reinterpret_cast<const uint32_t *>(rawS) + r, *cB = reinterpret_cast<const uint32_t *>(rawS + kCodeBytes) + r;
       const uint32_t *W32 = reinterpret_cast<const uint32_t *>(rawS + 2 * kCodeBytes) + q0;
       unsigned char *eA = exps + (size_t) es * kExpBytes + unit_off, *eB = eA + kOpBytes;
@@ -259,7 +305,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
       const uint32_t u = acc_meta[ab * 2], fl = acc_meta[ab * 2 + 1];
       if (fl & kExit) break;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      int4 *dst = reinterpret_cast<int4 *>(a.partials + (uint64_t) u * a.pstride + (uint64_t) (qd * 32 + lane) * 128);
+      int4 *dst = reinterpret_cast<int4 *>(a.partials + (uint64_t) u * a.pstride + (COUNT ? NGSD_TILE_ELEMS : 0) + (uint64_t) (qd * 32 + lane) * 128);
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
         uint32_t v[32];
@@ -289,15 +335,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
 
 }  // namespace
 
-cudaError_t ngsd_launch_dist_umma(ngsd_ctx *ctx, uint32_t n_units, int grid, uint32_t pstride) {
+cudaError_t ngsd_launch_dist_umma(ngsd_ctx *ctx, uint32_t n_units, int grid, uint32_t pstride, bool count) {
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
-    cudaError_t e = cudaFuncSetAttribute((const void *) k_dist_umma, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBytes);
-    if (e != cudaSuccess) return e;
+    const void *fns[2] = {(const void *) k_dist_umma<false>, (const void *) k_dist_umma<true>};
+    for (const void *f : fns) {
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBytes);
+      if (e != cudaSuccess) return e;
+    }
     attr_set[ctx->device & 63] = true;
   }
   UmmaArgs a;
   a.codes = ctx->codes;
+  a.mask = ctx->mask;
   a.wsite = ctx->d_wsite;
   a.word_ids = ctx->d_word_ids;
   a.word_layer = ctx->d_word_layer;
@@ -312,6 +362,9 @@ cudaError_t ngsd_launch_dist_umma(ngsd_ctx *ctx, uint32_t n_units, int grid, uin
   for (int k = 0; k < 4; k++) a.lut[k] = ctx->int_lut[k];
   cudaError_t e = cudaMemsetAsync(ctx->d_sched, 0, sizeof(uint32_t), ctx->stream);
   if (e != cudaSuccess) return e;
-  k_dist_umma<<<grid, kThreads, kSmemBytes, ctx->stream>>>(a);
+  if (count)
+    k_dist_umma<true><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a);
+  else
+    k_dist_umma<false><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a);
   return cudaGetLastError();
 }

@@ -155,5 +155,5 @@ bool ngsd_int_lut(const double *score, bool pairwise_del, uint32_t lut[4], doubl
 cudaError_t ngsd_launch_dist_imma(ngsd_ctx *ctx, uint32_t n_units, int grid, bool count);
 int ngsd_imma_ctas_per_sm();
 bool ngsd_use_umma();
-cudaError_t ngsd_launch_dist_umma(ngsd_ctx *ctx, uint32_t n_units, int grid, uint32_t pstride);   // dist_umma.cu (tcgen05)
+cudaError_t ngsd_launch_dist_umma(ngsd_ctx *ctx, uint32_t n_units, int grid, uint32_t pstride, bool count);   // dist_umma.cu (tcgen05)
 cudaError_t ngsd_launch_epilogue_int(ngsd_ctx *ctx, uint32_t n_splits, uint64_t const_cnt, bool use_cnt, bool in_kernel_cnt);
