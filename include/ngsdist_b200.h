@@ -163,6 +163,7 @@ NGSD_API int ngsd_get_timing(const ngsd_ctx *ctx, ngsd_timing *t);
 NGSD_API void *ngsd_stream(ngsd_ctx *ctx);                       /* cudaStream_t */
 NGSD_API int ngsd_probe_fp64_tflops(int device, double *dmma_tflops);
 NGSD_API int ngsd_probe_int8_tmacs(int device, double *imma_tmacs);   /* mma.sync int8 (IMMA.16832) issue-rate ceiling, 1e12 MAC/s */
+NGSD_API int ngsd_probe_umma_tmacs(int device, double *umma_tmacs);   /* tcgen05.mma kind::i8 (UTCIMMA) issue-rate ceiling, 1e12 MAC/s */
 NGSD_API void *ngsd_host_alloc(uint64_t bytes);                  /* pinned host memory for push/out buffers */
 NGSD_API void ngsd_host_free(void *p);
 NGSD_API int ngsd_abi_version(void);

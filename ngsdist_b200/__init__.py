@@ -4,8 +4,8 @@ The product is the C-ABI shared library `libngsdist_b200.so` (include/ngsdist_b2
 this package is a thin ctypes mirror of it for tests and bench.py.  There is no CPU fallback: importing
 works without a GPU, but every compute entry point fails loudly when the library or a CUDA device is missing.
 """
-from .api import (NgsDistError, Params, NgsDistB200, Timing, lib, lib_path, build_library, taus_block_counts, probe_fp64_tflops, probe_int8_tmacs,
+from .api import (NgsDistError, Params, NgsDistB200, Timing, lib, lib_path, build_library, taus_block_counts, probe_fp64_tflops, probe_int8_tmacs, probe_umma_tmacs,
                   ABI_SYMBOLS)
 
 __all__ = ["NgsDistError", "Params", "NgsDistB200", "Timing", "lib", "lib_path", "build_library", "taus_block_counts",
-           "probe_fp64_tflops", "probe_int8_tmacs", "ABI_SYMBOLS"]
+           "probe_fp64_tflops", "probe_int8_tmacs", "probe_umma_tmacs", "ABI_SYMBOLS"]

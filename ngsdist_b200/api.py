@@ -19,7 +19,7 @@ ABI_SYMBOLS = [
     "ngsd_abi_version", "ngsd_default_cfg", "ngsd_create", "ngsd_destroy", "ngsd_last_error", "ngsd_push_sites",
     "ngsd_push_sites_device", "ngsd_push_genotypes", "ngsd_frontend", "ngsd_distances", "ngsd_taus_seed", "ngsd_taus_get",
     "ngsd_boot_block_counts", "ngsd_get_posteriors", "ngsd_synth_raw_device", "ngsd_get_timing", "ngsd_stream",
-    "ngsd_probe_fp64_tflops", "ngsd_probe_int8_tmacs", "ngsd_host_alloc", "ngsd_host_free", "ngsd_set_tile_shard", "ngsd_device_results", "ngsd_finish",
+    "ngsd_probe_fp64_tflops", "ngsd_probe_int8_tmacs", "ngsd_probe_umma_tmacs", "ngsd_host_alloc", "ngsd_host_free", "ngsd_set_tile_shard", "ngsd_device_results", "ngsd_finish",
 ]
 
 
@@ -97,6 +97,7 @@ def lib():
     L.ngsd_stream.restype = vp
     L.ngsd_probe_fp64_tflops.argtypes = [i32, C.POINTER(dbl)]
     L.ngsd_probe_int8_tmacs.argtypes = [i32, C.POINTER(dbl)]
+    L.ngsd_probe_umma_tmacs.argtypes = [i32, C.POINTER(dbl)]
     L.ngsd_host_alloc.argtypes = [u64]
     L.ngsd_host_alloc.restype = vp
     L.ngsd_host_free.argtypes = [vp]
@@ -105,7 +106,7 @@ def lib():
     L.ngsd_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.ngsd_finish.argtypes = [vp, vp]
     for name in ("ngsd_create", "ngsd_destroy", "ngsd_push_sites", "ngsd_push_sites_device", "ngsd_push_genotypes", "ngsd_frontend",
-                 "ngsd_distances", "ngsd_get_posteriors", "ngsd_synth_raw_device", "ngsd_get_timing", "ngsd_probe_fp64_tflops", "ngsd_probe_int8_tmacs",
+                 "ngsd_distances", "ngsd_get_posteriors", "ngsd_synth_raw_device", "ngsd_get_timing", "ngsd_probe_fp64_tflops", "ngsd_probe_int8_tmacs", "ngsd_probe_umma_tmacs",
                  "ngsd_set_tile_shard", "ngsd_device_results", "ngsd_finish"):
         getattr(L, name).restype = i32
     _lib = L
@@ -171,6 +172,14 @@ def probe_fp64_tflops(device=0):
     rc = lib().ngsd_probe_fp64_tflops(device, C.byref(v))
     if rc:
         raise NgsDistError(rc, "FP64 probe failed")
+    return v.value
+
+
+def probe_umma_tmacs(device=0):
+    v = C.c_double(0)
+    rc = lib().ngsd_probe_umma_tmacs(device, C.byref(v))
+    if rc:
+        raise NgsDistError(rc, "tcgen05 int8 probe failed")
     return v.value
 
 

@@ -333,7 +333,64 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
   if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
 }
 
+// register / smem-resident UMMA loop: the int8 tensor issue-rate ceiling through tcgen05 (roofline denominator of K2c')
+__global__ void __launch_bounds__(128, 1) k_umma_peak(int iters) {
+  __shared__ __align__(128) unsigned char sA[2 * 16 * 128];
+  __shared__ __align__(128) unsigned char sB[2 * 16 * 128];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t slot;
+  const int warp = threadIdx.x >> 5;
+  for (int e = threadIdx.x; e < 4096; e += 128) { sA[e] = (unsigned char) (e * 7); sB[e] = (unsigned char) (e * 13); }
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  if (warp == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&slot)), "r"(128u) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = slot;
+  if (threadIdx.x == 0) {
+    const uint64_t da = umma_desc(smem_u32(sA), 2048, 128), db = umma_desc(smem_u32(sB), 2048, 128);
+    const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+    for (int it = 0; it < iters; it++) umma_i8(tmem, da, db, idesc, it ? 1u : 0u);
+    umma_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(128u) : "memory");
+}
+
 }  // namespace
+
+extern "C" int ngsd_probe_umma_tmacs(int device, double *umma_tmacs) {
+  if (cudaSetDevice(device) != cudaSuccess) return NGSD_ERR_CUDA;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return NGSD_ERR_CUDA;
+  const int iters = 1 << 15, nsm = prop.multiProcessorCount;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  float best = 1e30f;
+  for (int r = 0; r < 4; r++) {
+    cudaEventRecord(e0);
+    k_umma_peak<<<nsm, 128>>>(iters);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) return NGSD_ERR_CUDA;
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (r > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *umma_tmacs = (double) nsm * iters * (128.0 * 128 * 32) / (best * 1e-3) * 1e-12;
+  return NGSD_OK;
+}
 
 cudaError_t ngsd_launch_dist_umma(ngsd_ctx *ctx, uint32_t n_units, int grid, uint32_t pstride, bool count) {
   static bool attr_set[64] = {};
