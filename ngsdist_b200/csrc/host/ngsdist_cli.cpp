@@ -301,7 +301,19 @@ static int selftest_io(uint64_t n) {
   return bad ? 1 : 0;
 }
 
+// NGSD_CLI_TIMING=1: wall-clock stamps of the phases on stderr (development aid)
+static void stamp(const char *what) {
+  static const bool on = getenv("NGSD_CLI_TIMING") != nullptr;
+  static struct timespec t0 = {0, 0};
+  if (!on) return;
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  if (t0.tv_sec == 0 && t0.tv_nsec == 0) t0 = t;
+  fprintf(stderr, "[timing] %-28s %8.3f s\n", what, (double) (t.tv_sec - t0.tv_sec) + 1e-9 * (double) (t.tv_nsec - t0.tv_nsec));
+}
+
 int main(int argc, char **argv) {
+  stamp("start");
   if (argc >= 2 && strcmp(argv[1], "--selftest_io") == 0) return selftest_io(argc >= 3 ? (uint64_t) atol(argv[2]) : 1000000);
   Pars p;
   parse_args(&p, argc, argv);
@@ -353,6 +365,7 @@ int main(int argc, char **argv) {
   cfg.device = p.device;
   ngsd_ctx *ctx = nullptr;
   if (ngsd_create(&cfg, &ctx)) die(cfg.evol_model > 2 ? "gen_dist" : "main", ngsd_last_error(nullptr));
+  stamp("context created");
 
   // ---- read + front end, chunk by chunk (replaces read_geno + ngsDist.cpp:161-174) ----
   // A reader thread fills one of two pinned chunk buffers (file read / inflate, text parsing on --n_threads threads)
@@ -514,6 +527,7 @@ int main(int argc, char **argv) {
   for (auto &sl : slots)
     if (sl.raw) ngsd_host_free(sl.raw);
   if (ngsd_frontend(ctx)) die("read_geno", ngsd_last_error(ctx));
+  stamp("input read + front end");
 
   if (p.verbose >= 2) fprintf(stderr, "==> Setting seed for random number generator\n");
   uint32_t rng[3];
@@ -552,12 +566,15 @@ int main(int argc, char **argv) {
           fprintf(stderr, "\tDistance of %f from %lu valid sites (%f) between %s (ind %lu) and %s (ind %lu)!\n", num[i1 * p.n_ind + i2],
                   cnt[i1 * p.n_ind + i2], num[i1 * p.n_ind + i2] / (double) cnt[i1 * p.n_ind + i2], labels[i1].c_str(), i1,
                   labels[i2].c_str(), i2);
+    if (rep == 0) stamp("first matrix computed");
     if (p.verbose >= 2) fprintf(stderr, "> Printing distance matrix\n");
     write_matrix(out_fh, labels, dist.data(), p.n_ind, p.n_threads);
   }
   fclose(out_fh);
+  stamp("all matrices written");
   if (p.verbose >= 1) fprintf(stderr, "==> Freeing memory...\n");
   ngsd_destroy(ctx);
+  stamp("context destroyed");
   if (p.verbose >= 1) fprintf(stderr, "Done!\n");
   return 0;
 }

@@ -5,9 +5,21 @@ import numpy as np
 import pytest
 
 import oracle
-from test_gpu_parity import assert_close, nb
+from test_gpu_parity import RTOL, nb
 
 pytestmark = pytest.mark.gpu
+
+
+def assert_close(got, want, what="", n_sites=1):
+    """1e-9 relative, with an absolute floor of 1e-15 per site: the two-plane (sum-to-one) evaluation of a site term has
+    ~1e-16 ABSOLUTE error, which is a large RELATIVE error only for pairs whose whole sum is ~1e-9 or less (a few sites of
+    near-identical sharp posteriors) -- five orders of magnitude below the 10 decimals the writer prints."""
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    both_nan = np.isnan(got) & np.isnan(want)
+    both_inf = np.isinf(got) & np.isinf(want) & (np.sign(got) == np.sign(want))
+    with np.errstate(invalid="ignore"):
+        ok = both_nan | both_inf | (np.abs(got - want) <= RTOL * np.abs(want) + 1e-15 * n_sites)
+    assert ok.all(), "%s: %d mismatches" % (what, (~ok).sum())
 
 MODES = {
     "indep": dict(indep_geno=True),
@@ -37,7 +49,7 @@ def test_edge_shapes(mode, n_ind, n_sites):
         o = oracle.run_job(raw, evol_model=model, **ora_kw(pk))[0]
         assert r["dist"].shape == (n_ind, n_ind)
         assert np.array_equal(r["cnt"], o["cnt"])
-        assert_close(r["num"], o["num"], "%s %dx%d num" % (mode, n_ind, n_sites))
+        assert_close(r["num"], o["num"], "%s %dx%d num" % (mode, n_ind, n_sites), n_sites)
         assert_close(r["dist"], o["dist"], "%s %dx%d dist m%d" % (mode, n_ind, n_sites, model))
         assert (np.diag(r["dist"]) == 0).all()
 

@@ -25,15 +25,20 @@ print("wrote %s (%.2f GB) in %.1f s" % (path, os.path.getsize(path) / 1e9, time.
 threads = os.cpu_count() or 1
 flags = args.flags.split()
 
+last_stamps = [""]
+
 def run(binary, n_sites, out):
     cmd = [binary, "--geno", path, "--n_ind", str(args.n_ind), "--n_sites", str(n_sites), "--out", out, "--n_threads", str(threads),
            "--verbose", "0"] + flags
     t = time.perf_counter()
-    subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
-    return time.perf_counter() - t
+    r = subprocess.run(cmd, check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE, text=True, env=dict(os.environ, NGSD_CLI_TIMING="1"))
+    dt = time.perf_counter() - t
+    last_stamps[0] = "".join(l + "\n" for l in r.stderr.splitlines() if l.startswith("[timing]"))
+    return dt
 
 ours = [run(cli, args.n_sites, os.path.join(work, "ours.dist")) for _ in range(3)]
-print("ngsdist_b200/bin/ngsDist: %s s wall (3 runs; first includes CUDA context creation + cold page cache effects)" % ", ".join("%.2f" % t for t in ours))
+print("ngsdist_b200/bin/ngsDist: %s s wall (3 runs; every run pays CUDA initialisation + context creation, which depends on the box: see the stamps)" % ", ".join("%.2f" % t for t in ours))
+print("phases of the last run:\n" + last_stamps[0], end="")
 pairs = args.n_ind * (args.n_ind - 1) // 2
 if oracle.have_ref():
     ref_sites = args.ref_sites or args.n_sites
