@@ -23,7 +23,7 @@ PY
 echo
 echo "## Full captures (\`ncu --set full --clock-control none --import-source on\`)"
 echo
-for f in dist_dmma_c2 frontend_c2 dist_dmma_weighted_c3 mask_count_c3 dist_em dist_imma frontend_codes; do
+for f in dist_dmma_c2 frontend_c2 dist_dmma_weighted_c3 mask_count_c3 dist_em dist_umma dist_imma frontend_codes; do
   if [ -f gpurun_out/${R}_$f.ncu-rep ]; then
     python tools/ncu_summary.py gpurun_out/${R}_$f.ncu-rep
     ncu -i gpurun_out/${R}_$f.ncu-rep --page raw --csv > profiles/${R}_${f}_raw.csv 2>/dev/null
