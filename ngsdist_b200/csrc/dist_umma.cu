@@ -13,8 +13,8 @@
 //   warps 18-21 epilogue   tcgen05.ld of a finished unit's 128 x 128 accumulator (two TMEM buffers: the next unit's
 //                          MMAs overlap the read-out), int32 partial tile written row-major
 //
-// all connected by mbarrier rings.  The expansion (ALU + shared-memory stores), not the tensor pipe, is the limit:
-// ~26 integer ops and one 16-byte store per 16 operand bytes.
+// all connected by mbarrier rings.  Shared-memory bandwidth (expansion stores + UMMA operand reads), not the tensor pipe,
+// is the limit; the expansion itself is ~12 integer ops and one 16-byte store per 16 operand bytes.
 #include <math.h>
 #include <stdlib.h>
 
@@ -228,6 +228,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
   } else if (warp < 2 + kExpWarps) {
     // ===== expanders: 512 threads, thread -> (row r, byte q0 of each of the 4 code words) of both operands =====
     const int te = threadIdx.x - 64, r = te & 127, q0 = te >> 7;
+    uint32_t rowk[4];                                               // row k of the S * f table: byte c = S f(k, c)
+#pragma unroll
+    for (int k = 0; k < 4; k++)
+      rowk[k] = ((a.lut[0] >> (8 * k)) & 0xFFu) | (((a.lut[1] >> (8 * k)) & 0xFFu) << 8) | (((a.lut[2] >> (8 * k)) & 0xFFu) << 16) |
+                (((a.lut[3] >> (8 * k)) & 0xFFu) << 24);
     const uint32_t unit_off = (uint32_t) (r >> 3) * 128 + (uint32_t) (r & 7) * 16;
     int rs = 0, es = 0;
     uint32_t rph = 0, eph = 0;
@@ -271,19 +276,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
       const uint32_t *cA = reinterpret_cast<const uint32_t *>(rawS) + r, *cB = reinterpret_cast<const uint32_t *>(rawS + kCodeBytes) + r;
       const uint32_t *W32 = reinterpret_cast<const uint32_t *>(rawS + 2 * kCodeBytes) + q0;
       unsigned char *eA = exps + (size_t) es * kExpBytes + unit_off, *eB = eA + kOpBytes;
+      // The K order inside a 16-byte unit is free as long as both operands use it: PLANE-major here (word k = plane k of the
+      // unit's 4 sites), because then one byte-permute builds a whole word.  With sel = the 4 codes spread to the 4 selector
+      // nibbles, PRMT(T_k, sel) picks byte c_j of T_k for site j:  T_k = 0xFF << 8k gives the one-hot plane k of A (AND the
+      // 4 weight bytes), T_k = row k of the S * f table gives plane k of B.  No table loads, ~24 integer ops per unit pair.
 #pragma unroll
       for (int i = 0; i < 4; i++) {                                 // code word i: sites 16 i + 4 q0 .. + 3 = site quad 4 i + q0
         const uint32_t x = (cA[i * 128] >> (8 * q0)) & 0xFFu, y = (cB[i * 128] >> (8 * q0)) & 0xFFu;
         const uint32_t ww = W32[i * 4];
+        uint32_t sx = (x | (x << 4)) & 0x0F0Fu, sy = (y | (y << 4)) & 0x0F0Fu;
+        sx = (sx | (sx << 2)) & 0x3333u;
+        sy = (sy | (sy << 2)) & 0x3333u;
         uint4 va, vb;
-        va.x = __funnelshift_l(0u, ww & 0xFFu, (x << 3) & 0x18u);
-        va.y = __funnelshift_l(0u, (ww >> 8) & 0xFFu, (x << 1) & 0x18u);
-        va.z = __funnelshift_l(0u, (ww >> 16) & 0xFFu, (x >> 1) & 0x18u);
-        va.w = __funnelshift_l(0u, ww >> 24, (x >> 3) & 0x18u);
-        vb.x = lut[y & 3u];
-        vb.y = lut[(y >> 2) & 3u];
-        vb.z = lut[(y >> 4) & 3u];
-        vb.w = lut[y >> 6];
+        va.x = __byte_perm(0x000000FFu, 0u, sx) & ww;
+        va.y = __byte_perm(0x0000FF00u, 0u, sx) & ww;
+        va.z = __byte_perm(0x00FF0000u, 0u, sx) & ww;
+        va.w = __byte_perm(0xFF000000u, 0u, sx) & ww;
+        vb.x = __byte_perm(rowk[0], 0u, sy);
+        vb.y = __byte_perm(rowk[1], 0u, sy);
+        vb.z = __byte_perm(rowk[2], 0u, sy);
+        vb.w = __byte_perm(rowk[3], 0u, sy);
         const uint32_t off = (uint32_t) (4 * i + q0) * 2048;
         *reinterpret_cast<uint4 *>(eA + off) = va;
         *reinterpret_cast<uint4 *>(eB + off) = vb;
