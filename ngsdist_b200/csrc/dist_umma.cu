@@ -161,10 +161,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
         const uint32_t c0 = a.split_begin[q], c1 = a.split_begin[q + 1];
         const uint32_t *Ab = a.codes + (uint64_t) tl.ti * a.NW * 512;
         const uint32_t *Bb = a.codes + (uint64_t) tl.tj * a.NW * 512;
+        uint32_t nword = a.word_ids[c0], nlayer = a.word_layer[c0];
         for (uint32_t c = c0; c < c1; c++) {
-          const uint64_t word = a.word_ids[c];
-          const uint8_t *wsrc = a.wsite + ((uint64_t) a.word_layer[c] * a.NW + word) * 64;
-          mbar_wait_sleep(&raw_empty[rs], rph ^ 1);
+          const uint64_t word = nword;
+          const uint8_t *wsrc = a.wsite + ((uint64_t) nlayer * a.NW + word) * 64;
+          if (c + 1 < c1) { nword = a.word_ids[c + 1]; nlayer = a.word_layer[c + 1]; }   // next entry's loads fly during the wait below
+          mbar_wait(&raw_empty[rs], rph ^ 1);
           raw_meta[rs * 2] = u;
           raw_meta[rs * 2 + 1] = (c == c0 ? kFirst : 0u) | (c + 1 == c1 ? kLast : 0u);
           mbar_expect_tx(&raw_full[rs], kStageRaw);
