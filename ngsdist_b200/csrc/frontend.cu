@@ -332,17 +332,48 @@ __global__ void __launch_bounds__(512, 2) k_frontend_codes(FrontCfg c, const dou
     }
   }
   unsigned cbits = 0xFF;                  // 2 bits per site; 3 = missing / padding
-  unsigned need_exact = 0;                // sites the fast test could not decide (near-ties, corner cases): rare
+  unsigned need_fp = 0;                   // sites the integer test below could not decide
+  unsigned need_exact = 0;                // sites the FP64 fast test could not decide (near-ties, corner cases): rare
   int bad = 0;
+  // Level 1 (normal-scale input, default thresholds: every triple ends up called or missing).  Non-negative finite
+  // doubles order like their bit patterns, so the first strict maximum is decided on the high words alone whenever the
+  // maximum's high word is >= 2 above the runner-up's (relative gap >= 2^-20, far outside the 1e-9 near-tie band of
+  // called_code_fast); an all-equal positive normal triple is missing data (max_pp = -1 < N_thresh = 0,
+  // gen_func.cpp:895-905).  Anything else -- negatives, NaN, inf, zeros, denormals, close calls -- goes to level 2.
+  const bool level1 = !codes && !c.in_log && c.N_thresh == 0.0 && c.call_thresh == 0.0;
 #pragma unroll
   for (int q = 0; q < 4; q++) {
     const uint64_t sl = s_local0 + q;
     if (i < n_ind && sl < n) {
-      unsigned cg;
+      unsigned cg = 3u;
       if (codes) {
         cg = gc[q] < 0 ? 3u : (unsigned) gc[q];                      // read_data.cpp:88-95: -1 = missing
         if (gc[q] > 2) { bad |= 2; cg = 3u; }
-      } else if (!called_code_fast(c, A[q][0], A[q][1], A[q][2], cg)) {
+      } else if (level1) {
+        const unsigned h0 = (unsigned) __double2hiint(A[q][0]), h1 = (unsigned) __double2hiint(A[q][1]),
+                       h2 = (unsigned) __double2hiint(A[q][2]);
+        const unsigned m01 = max(h0, h1), mx = max(m01, h2), second = max(min(h0, h1), min(m01, h2));
+        const unsigned lo_diff = ((unsigned) __double2loint(A[q][0]) ^ (unsigned) __double2loint(A[q][1])) |
+                                 ((unsigned) __double2loint(A[q][1]) ^ (unsigned) __double2loint(A[q][2])) | (h0 ^ h1) | (h1 ^ h2);
+        if (mx < 0x7FF00000u && mx - second >= 2u) {
+          cg = h2 == mx ? 2u : (h1 == mx ? 1u : 0u);
+        } else if (lo_diff == 0u && h0 - 0x00100000u < 0x7FE00000u) {
+          cg = 3u;
+        } else {
+          need_fp |= 1u << q;
+        }
+      } else {
+        need_fp |= 1u << q;
+      }
+      cbits = (cbits & ~(3u << (2 * q))) | (cg << (2 * q));
+    }
+  }
+  if (need_fp) {                          // level 2: the FP64 test with the reference's tie / threshold semantics
+#pragma unroll
+    for (int q = 0; q < 4; q++) {
+      if (!((need_fp >> q) & 1u)) continue;
+      unsigned cg;
+      if (!called_code_fast(c, A[q][0], A[q][1], A[q][2], cg)) {
         need_exact |= 1u << q;
         cg = 3u;
       }
@@ -359,21 +390,25 @@ __global__ void __launch_bounds__(512, 2) k_frontend_codes(FrontCfg c, const dou
     }
   }
   if (bad) atomicOr(err, bad);
-  cod[ty][tx] = cbits;
+  // presence nibble of this thread's 4 sites (miss_data of gen_func.cpp:862-868: exactly the code-3 entries)
+  unsigned pres = ~(cbits & (cbits >> 1)) & 0x55u;
+  pres = (pres | (pres >> 1)) & 0x33u;
+  pres = (pres | (pres >> 2)) & 0x0Fu;
+  cod[ty][tx] = cbits | (pres << 8);
   __syncthreads();
   const uint64_t rb = i >> 7, r = i & 127;
   if (ty < 4) {                           // word ty of this individual: sites 16 ty .. 16 ty + 15 of the 64-site word
-    const unsigned w = cod[4 * ty][tx] | (cod[4 * ty + 1][tx] << 8) | (cod[4 * ty + 2][tx] << 16) | (cod[4 * ty + 3][tx] << 24);
+    const unsigned w = (cod[4 * ty][tx] & 0xFFu) | ((cod[4 * ty + 1][tx] & 0xFFu) << 8) | ((cod[4 * ty + 2][tx] & 0xFFu) << 16) |
+                       (cod[4 * ty + 3][tx] << 24);
     codes_out[((rb * NW + word) * 4 + ty) * 128 + r] = w;
-  } else if (ty == 4) {                   // presence mask (miss_data of gen_func.cpp:862-868: exactly the code-3 entries)
-    uint64_t m = 0;
+  } else if (ty == 4) {                   // presence mask word: 16 nibbles
+    unsigned mlo = 0, mhi = 0;
 #pragma unroll
-    for (int k = 0; k < 16; k++) {
-      const unsigned cb = cod[k][tx];
-#pragma unroll
-      for (int q = 0; q < 4; q++) m |= (uint64_t) (((cb >> (2 * q)) & 3u) != 3u) << (4 * k + q);
+    for (int k = 0; k < 8; k++) {
+      mlo |= ((cod[k][tx] >> 8) & 0xFu) << (4 * k);
+      mhi |= ((cod[k + 8][tx] >> 8) & 0xFu) << (4 * k);
     }
-    mask[(rb * NW + word) * 128 + r] = m;
+    mask[(rb * NW + word) * 128 + r] = ((uint64_t) mhi << 32) | mlo;
   }
 }
 

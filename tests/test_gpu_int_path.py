@@ -106,3 +106,34 @@ def test_soft_thresholds_fall_back_to_fp64_planes():
     r = run(raw, in_probs=True, **kw)[0]
     o = oracle.run_job(raw, indep=True, **kw)[0]
     assert np.array_equal(r["cnt"], o["cnt"]) and np.array_equal(r["num"], o["num"])
+
+
+def test_call_decisions_at_the_fast_test_boundaries():
+    """The code kernel decides calls on the doubles' high words when the maximum is clear, on an FP64 test when it is
+    close, and with the reference's log-space sequence (gen_func.cpp:886-914) at near-ties: triples sitting on every one of
+    those boundaries must still come out as the reference calls them."""
+    def bump(x, k):              # k units in the high 32-bit word (k * 2^32 ulps)
+        return (np.array([x], dtype=np.float64).view(np.uint64) + np.uint64(k << 32)).view(np.float64)[0]
+    base = [0.2, 0.3, 0.45, 1e-300, 3e-310, 1e300, 1.0]
+    triples = []
+    for b in base:
+        for k in (0, 1, 2, 3):
+            hi = bump(b, k)
+            triples += [(hi, b, b * 0.5), (b, hi, b * 0.5), (b * 0.5, b, hi), (hi, b, b), (b, b, hi), (b, hi, hi)]
+        triples += [(b, b, b), (b, b, 0.0), (0.0, b, 0.0), (np.nextafter(b, 1e308), b, b), (b, np.nextafter(b, 1e308), 0.0),
+                    (b * (1 + 5e-10), b, 0.1 * b), (b, b * (1 + 2e-9), 0.1 * b), (-0.0, b, 0.0)]
+    triples += [(0.0, 0.0, 0.0), (5e-324, 0.0, 0.0), (5e-324, 5e-324, 5e-324), (1.7e308, 1.7e308, 1.0), (1.7e308, 1.6e308, 1.7e308)]
+    rng = np.random.RandomState(4)
+    n_ind, n_sites = 37, 200
+    raw = oracle.synth_raw(5, 0.1, n_ind, n_sites)
+    for k, t in enumerate(triples):
+        raw[rng.randint(n_sites), rng.randint(n_ind)] = t
+        raw[k % n_sites, k % n_ind] = t
+    P = oracle.frontend(raw, call_geno=True)
+    p = nb().Params(n_ind=n_ind, n_sites=n_sites, in_probs=True, call_geno=True, pairwise_del=True)
+    with nb().NgsDistB200(p) as g:
+        g.push_sites(raw)
+        g.frontend()
+        Pg, mg = g.posteriors()
+    assert np.array_equal(Pg, P)
+    assert np.array_equal(mg, 1 - oracle.miss_mask(P))
