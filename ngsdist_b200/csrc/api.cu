@@ -98,7 +98,26 @@ cudaError_t upload_tile_index(ngsd_ctx *ctx, const std::vector<ngsd_tile> &tiles
     cudaError_t e = cudaMalloc((void **) &ctx->d_tile_index, idx.size() * sizeof(uint32_t));
     if (e != cudaSuccess) return e;
   }
-  return cudaMemcpy(ctx->d_tile_index, idx.data(), idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  cudaError_t e = cudaMemcpy(ctx->d_tile_index, idx.data(), idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) return e;
+  // tiles of one row block share their A operand: dist_umma.cu contracts them two at a time (one 128 x 256 MMA)
+  std::vector<uint32_t> pairs;
+  for (size_t t = 0; t < tiles.size();) {
+    if (t + 1 < tiles.size() && tiles[t + 1].ti == tiles[t].ti) {
+      pairs.push_back((uint32_t) t); pairs.push_back((uint32_t) t + 1);
+      t += 2;
+    } else {
+      pairs.push_back((uint32_t) t); pairs.push_back(0xFFFFFFFFu);
+      t += 1;
+    }
+  }
+  ctx->n_pairs = (uint32_t) (pairs.size() / 2);
+  if (!ctx->d_pairs) {
+    e = cudaMalloc((void **) &ctx->d_pairs, (ctx->RB * (ctx->RB + 1) + 2) * sizeof(uint32_t));
+    if (e != cudaSuccess) return e;
+  }
+  if (pairs.empty()) return cudaSuccess;
+  return cudaMemcpy(ctx->d_pairs, pairs.data(), pairs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
 }
 
 }  // namespace
@@ -239,7 +258,7 @@ int ngsd_destroy(ngsd_ctx *ctx) {
   cudaFree(ctx->d_tiles); cudaFree(ctx->d_partials); cudaFree(ctx->d_weights); cudaFree(ctx->d_chunk_ids);
   cudaFree(ctx->d_ent_word); cudaFree(ctx->d_ent_mask); cudaFree(ctx->d_cnt); cudaFree(ctx->d_split_begin); cudaFree(ctx->d_split_scale); cudaFree(ctx->d_sched);
   cudaFree(ctx->d_out); cudaFree(ctx->d_num); cudaFree(ctx->d_cntout);
-  cudaFree(ctx->d_cache); cudaFree(ctx->d_cnt_cache); cudaFree(ctx->d_ent_begin); cudaFree(ctx->d_tile_index);
+  cudaFree(ctx->d_cache); cudaFree(ctx->d_cnt_cache); cudaFree(ctx->d_ent_begin); cudaFree(ctx->d_tile_index); cudaFree(ctx->d_pairs);
   cudaFree(ctx->codes); cudaFree(ctx->d_wsite); cudaFree(ctx->d_word_layer); cudaFree(ctx->d_word_ids);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
   for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);

@@ -6,15 +6,17 @@
 // 3.7x faster than mma.sync (tools/probe_utcimma.cu: 2.1e15 vs 5.7e14 MAC/s) but reads its operands from shared
 // memory, so the 16x expansion of the 2-bit codes has to go through the LSU: a CTA is a four-role pipeline
 //
-//   warp 0      producer   cp.async.bulk of the packed codes (2 x 2 KiB + 64 weight bytes per 64-site stage)
-//   warps 2-17  expanders  codes -> int8 operand tiles (2 x 32 KiB per stage) in the K-major, no-swizzle UMMA layout
+//   warp 0      producer   cp.async.bulk of the packed codes (3 x 2 KiB + 64 weight bytes per 64-site stage)
+//   warps 2-17  expanders  codes -> int8 operand tiles (32 + 64 KiB per stage) in the K-major, no-swizzle UMMA layout
 //                          (8-row x 16-byte core matrices; one STS.128 = 4 sites of one row), fence.proxy.async
-//   warp 1      MMA        one lane issues 8 x tcgen05.mma (128 x 128 x 32) per stage, tcgen05.commit frees the stage
-//   warps 18-21 epilogue   tcgen05.ld of a finished unit's 128 x 128 accumulator (two TMEM buffers: the next unit's
-//                          MMAs overlap the read-out), int32 partial tile written row-major
+//   warp 1      MMA        one lane issues 8 x tcgen05.mma (128 x 256 x 32) per stage, tcgen05.commit frees the stage
+//   warps 18-21 epilogue   tcgen05.ld of a finished unit's 128 x 256 accumulator (two TMEM buffers: the next unit's
+//                          MMAs overlap the read-out), int32 partial tiles written row-major
 //
 // all connected by mbarrier rings.  Shared-memory bandwidth (expansion stores + UMMA operand reads), not the tensor pipe,
-// is the limit; the expansion itself is ~12 integer ops and one 16-byte store per 16 operand bytes.
+// is the limit; the expansion itself is ~12 integer ops and one 16-byte store per 16 operand bytes.  To spend less of it
+// per MAC a unit is a PAIR of output tiles of one row block (api.cu: d_pairs): they share the A operand, so one stage
+// expands 3 x 128 rows for 128 x 256 pairs instead of 2 x 128 rows for 128 x 128 (the odd tile of a row runs alone, N = 128).
 #include <math.h>
 #include <stdlib.h>
 
@@ -23,14 +25,14 @@
 namespace {
 
 constexpr int kRaw = 4;                           // raw (packed codes) stages
-constexpr int kExp = 3;                           // expanded operand stages
+constexpr int kExp = 2;                           // expanded operand stages
 constexpr int kExpWarps = 16, kEpiWarps = 4;
 constexpr int kThreads = (2 + kExpWarps + kEpiWarps) * 32;
 constexpr int kCodeBytes = 4 * 128 * 4;           // [4 words][128 rows] uint32, one operand of one 64-site stage
 constexpr int kMaskBytes = 128 * 8;               // presence bits of one operand of one stage (count pass)
-constexpr int kRawBytes = 2 * kCodeBytes + 64;    // A codes, B codes, 64 site weights (count pass: 2 masks + weights, smaller)
-constexpr int kOpBytes = 16 * 16 * 128;           // expanded operand: [16 site quads][16 row groups][8 rows][16 B] = 32 KiB
-constexpr int kExpBytes = 2 * kOpBytes;           // (count pass: one byte per site, [4 x 16 sites][16][8][16 B] = 8 KiB per operand)
+constexpr int kRawBytes = 3 * kCodeBytes + 64;    // A codes, B codes of the two tiles, 64 site weights (count pass: 3 masks + weights, smaller)
+constexpr int kOpBytes = 16 * 16 * 128;           // expanded A operand: [16 site quads][16 row groups][8 rows][16 B] = 32 KiB
+constexpr int kExpBytes = 3 * kOpBytes;           // A + B, B = [16 site quads][32 row groups][8 rows][16 B] (count pass: one byte per site, a quarter of it)
 constexpr int kNBar = 2 * kRaw + 2 * kExp + 4;
 constexpr size_t kSmemBytes = (size_t) kRaw * kRawBytes + (size_t) kExp * kExpBytes + kNBar * 8 + (kRaw + kExp + 2) * 8 + 16 + 16 + 1024;
 
@@ -92,6 +94,7 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t d
 struct UmmaArgs {
   const uint32_t *codes;        // [RB][NW][4][128]
   const uint64_t *mask;         // [RB][NW][128] presence bits (count pass)
+  const uint32_t *pairs;        // [n_pairs][2] tile positions of a unit (second 0xFFFFFFFF: single tile)
   const uint8_t *wsite;         // [n_layers][NW * 64]
   const uint32_t *word_ids, *word_layer;
   const ngsd_tile *tiles;
@@ -99,20 +102,21 @@ struct UmmaArgs {
   uint32_t *sched;
   int32_t *partials;            // [n_units][pstride], sum tile row-major [128][128]
   uint64_t NW;
-  uint32_t n_tiles, n_units, pstride;
+  uint32_t n_tiles, n_pairs, n_units, pstride;   // n_units = splits x n_pairs
   uint32_t lut[4];
 };
 
-enum : uint32_t { kFirst = 1u, kLast = 2u, kExit = 8u };
+enum : uint32_t { kFirst = 1u, kLast = 2u, kPair = 4u, kExit = 8u };
 
 // COUNT = true: the same pipeline computes the shared-site counts of --pairwise_del, cnt(i,j) = sum_s w_s m_i(s) m_j(s), as an
 // int8 GEMM with ONE byte per site (A' = w_s m_i(s), B' = m_j(s) from the presence masks; 2 MMAs per 64-site stage) and
 // writes them as the second tile of the unit's slot.
 template <bool COUNT>
 __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
-  constexpr int kStageRaw = COUNT ? 2 * kMaskBytes + 64 : kRawBytes;
-  constexpr int kOffW = COUNT ? 2 * kMaskBytes : 2 * kCodeBytes;
-  constexpr int kOp = COUNT ? kOpBytes / 4 : kOpBytes;              // expanded bytes per operand per stage
+  constexpr int kIn = COUNT ? kMaskBytes : kCodeBytes;               // packed bytes of one 128-row operand of one stage
+  constexpr int kOffW = 3 * kIn;
+  constexpr int kOp = COUNT ? kOpBytes / 4 : kOpBytes;              // expanded bytes of A (B: twice that) per stage
+  constexpr int kBChunk = 4096;                       // B: bytes between 16-byte K chunks (32 row groups x 128 B)
   constexpr int kMmas = COUNT ? 2 : 8;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *raw = smem;                                         // kRaw x kRawBytes
@@ -139,8 +143,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
     const uint32_t n = threadIdx.x - 32;
     lut16[n] = (n & 1u) | ((n & 2u) << 7) | ((n & 4u) << 14) | ((n & 8u) << 21);
   }
-  if (warp == 1) {                                  // TMEM: two 128-column int32 accumulators
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u) : "memory");
+  if (warp == 1) {                                  // TMEM: two 256-column int32 accumulators (all 512 columns; one CTA per SM)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -156,11 +160,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
       for (;;) {
         const uint32_t u = atomicAdd(a.sched, 1u);
         if (u >= a.n_units) break;
-        const uint32_t q = u / a.n_tiles, t = u - q * a.n_tiles;
-        const ngsd_tile tl = a.tiles[t];
+        const uint32_t q = u / a.n_pairs, p = u - q * a.n_pairs;
+        const uint32_t t0 = a.pairs[2 * p], t1 = a.pairs[2 * p + 1];
+        const bool paired = t1 != 0xFFFFFFFFu;
+        const ngsd_tile tl = a.tiles[t0];
+        const uint32_t tj1 = paired ? a.tiles[t1].tj : tl.tj;
         const uint32_t c0 = a.split_begin[q], c1 = a.split_begin[q + 1];
         const uint32_t *Ab = a.codes + (uint64_t) tl.ti * a.NW * 512;
         const uint32_t *Bb = a.codes + (uint64_t) tl.tj * a.NW * 512;
+        const uint32_t *B1b = a.codes + (uint64_t) tj1 * a.NW * 512;
         uint32_t nword = a.word_ids[c0], nlayer = a.word_layer[c0];
         for (uint32_t c = c0; c < c1; c++) {
           const uint64_t word = nword;
@@ -168,15 +176,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
           if (c + 1 < c1) { nword = a.word_ids[c + 1]; nlayer = a.word_layer[c + 1]; }   // next entry's loads fly during the wait below
           mbar_wait(&raw_empty[rs], rph ^ 1);
           raw_meta[rs * 2] = u;
-          raw_meta[rs * 2 + 1] = (c == c0 ? kFirst : 0u) | (c + 1 == c1 ? kLast : 0u);
-          mbar_expect_tx(&raw_full[rs], kStageRaw);
+          raw_meta[rs * 2 + 1] = (c == c0 ? kFirst : 0u) | (c + 1 == c1 ? kLast : 0u) | (paired ? kPair : 0u);
+          mbar_expect_tx(&raw_full[rs], (paired ? 3 : 2) * kIn + 64);
           unsigned char *dst = raw + (size_t) rs * kRawBytes;
           if (COUNT) {
             bulk_g2s(dst, a.mask + ((uint64_t) tl.ti * a.NW + word) * 128, kMaskBytes, &raw_full[rs]);
             bulk_g2s(dst + kMaskBytes, a.mask + ((uint64_t) tl.tj * a.NW + word) * 128, kMaskBytes, &raw_full[rs]);
+            if (paired) bulk_g2s(dst + 2 * kMaskBytes, a.mask + ((uint64_t) tj1 * a.NW + word) * 128, kMaskBytes, &raw_full[rs]);
           } else {
             bulk_g2s(dst, Ab + word * 512, kCodeBytes, &raw_full[rs]);
             bulk_g2s(dst + kCodeBytes, Bb + word * 512, kCodeBytes, &raw_full[rs]);
+            if (paired) bulk_g2s(dst + 2 * kCodeBytes, B1b + word * 512, kCodeBytes, &raw_full[rs]);
           }
           bulk_g2s(dst + kOffW, wsrc, 64, &raw_full[rs]);
           if (++rs == kRaw) { rs = 0; rph ^= 1; }
@@ -189,8 +199,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
   } else if (warp == 1) {
     // ===== MMA issue (one lane) =====
     if (lane == 0) {
-      // D = S32 (2 << 4), A = B = INT8 (1 << 7, 1 << 10), both K-major, N = 128 (>> 3 at [17,23)), M = 128 (>> 4 at [24,29))
-      const uint32_t idesc = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      // D = S32 (2 << 4), A = B = INT8 (1 << 7, 1 << 10), both K-major, N (>> 3 at [17,23)), M = 128 (>> 4 at [24,29))
+      const uint32_t idesc1 = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+      const uint32_t idesc2 = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
       int es = 0, ab = 0;
       uint32_t eph = 0, aph[2] = {0, 0};
       for (;;) {
@@ -209,16 +220,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
         const uint32_t sa = smem_u32(exps + (size_t) es * kExpBytes), sb = sa + kOp;
+        const uint32_t idesc = (fl & kPair) ? idesc2 : idesc1;
 #pragma unroll
-        for (int j = 0; j < kMmas; j++) {                           // K 32 per instruction = two 16-byte chunks of 2 KiB each
+        for (int j = 0; j < kMmas; j++) {                           // K 32 per instruction = two 16-byte chunks (A: 2 KiB apart, B: 4 KiB)
           const uint64_t da = umma_desc(sa + j * 2 * 2048, 2048, 128);
-          const uint64_t db = umma_desc(sb + j * 2 * 2048, 2048, 128);
-          umma_i8(tmem + (uint32_t) ab * 128u, da, db, idesc, ((fl & kFirst) && j == 0) ? 0u : 1u);
+          const uint64_t db = umma_desc(sb + j * 2 * kBChunk, kBChunk, 128);
+          umma_i8(tmem + (uint32_t) ab * 256u, da, db, idesc, ((fl & kFirst) && j == 0) ? 0u : 1u);
         }
         umma_commit(&exp_empty[es]);                                 // stage reusable once these MMAs have read it
         if (fl & kLast) {
           acc_meta[ab * 2] = u;
-          acc_meta[ab * 2 + 1] = 0;
+          acc_meta[ab * 2 + 1] = fl & kPair;
           umma_commit(&acc_full[ab]);                                // accumulator complete ...
           mbar_arrive(&acc_full[ab]);                                // ... and its meta word published
           aph[ab] ^= 1;
@@ -254,6 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
         // into one 16-byte unit each (chunk q0 of the [4][16][8][16 B] operand); A bytes carry the site weights
         const uint32_t ma = reinterpret_cast<const uint32_t *>(rawS)[r * 2 + (q0 >> 1)] >> (16 * (q0 & 1));
         const uint32_t mb = reinterpret_cast<const uint32_t *>(rawS + kMaskBytes)[r * 2 + (q0 >> 1)] >> (16 * (q0 & 1));
+        const uint32_t mb1 = reinterpret_cast<const uint32_t *>(rawS + 2 * kMaskBytes)[r * 2 + (q0 >> 1)] >> (16 * (q0 & 1));
         const uint4 ww = *reinterpret_cast<const uint4 *>(rawS + kOffW + 16 * q0);
         uint4 va, vb;
         va.x = (lut16[ma & 15u] * 0xFFu) & ww.x;
@@ -265,8 +278,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
         vb.z = lut16[(mb >> 8) & 15u];
         vb.w = lut16[(mb >> 12) & 15u];
         unsigned char *eA = exps + (size_t) es * kExpBytes + unit_off + (uint32_t) q0 * 2048;
+        unsigned char *eB = exps + (size_t) es * kExpBytes + kOp + unit_off + (uint32_t) q0 * kBChunk;
         *reinterpret_cast<uint4 *>(eA) = va;
-        *reinterpret_cast<uint4 *>(eA + kOp) = vb;
+        *reinterpret_cast<uint4 *>(eB) = vb;
+        if (fl & kPair) {
+          vb.x = lut16[mb1 & 15u];
+          vb.y = lut16[(mb1 >> 4) & 15u];
+          vb.z = lut16[(mb1 >> 8) & 15u];
+          vb.w = lut16[(mb1 >> 12) & 15u];
+          *reinterpret_cast<uint4 *>(eB + 2048) = vb;
+        }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (te == 0) { exp_meta[es * 2] = u; exp_meta[es * 2 + 1] = fl; }
         __syncwarp();
@@ -276,8 +297,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
         continue;
       }
       const uint32_t *cA = reinterpret_cast<const uint32_t *>(rawS) + r, *cB = reinterpret_cast<const uint32_t *>(rawS + kCodeBytes) + r;
-      const uint32_t *W32 = reinterpret_cast<const uint32_t *>(rawS + 2 * kCodeBytes) + q0;
+      const uint32_t *cB1 = reinterpret_cast<const uint32_t *>(rawS + 2 * kCodeBytes) + r;
+      const uint32_t *W32 = reinterpret_cast<const uint32_t *>(rawS + kOffW) + q0;
       unsigned char *eA = exps + (size_t) es * kExpBytes + unit_off, *eB = eA + kOpBytes;
+      const bool paired = (fl & kPair) != 0;
       // The K order inside a 16-byte unit is free as long as both operands use it: PLANE-major here (word k = plane k of the
       // unit's 4 sites), because then one byte-permute builds a whole word.  With sel = the 4 codes spread to the 4 selector
       // nibbles, PRMT(T_k, sel) picks byte c_j of T_k for site j:  T_k = 0xFF << 8k gives the one-hot plane k of A (AND the
@@ -298,9 +321,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
         vb.y = __byte_perm(rowk[1], 0u, sy);
         vb.z = __byte_perm(rowk[2], 0u, sy);
         vb.w = __byte_perm(rowk[3], 0u, sy);
-        const uint32_t off = (uint32_t) (4 * i + q0) * 2048;
-        *reinterpret_cast<uint4 *>(eA + off) = va;
-        *reinterpret_cast<uint4 *>(eB + off) = vb;
+        const uint32_t sq = (uint32_t) (4 * i + q0);
+        *reinterpret_cast<uint4 *>(eA + sq * 2048) = va;
+        *reinterpret_cast<uint4 *>(eB + sq * kBChunk) = vb;
+        if (paired) {                                               // second tile's rows: row groups 16..31 of B
+          const uint32_t z = (cB1[i * 128] >> (8 * q0)) & 0xFFu;
+          uint32_t sz = (z | (z << 4)) & 0x0F0Fu;
+          sz = (sz | (sz << 2)) & 0x3333u;
+          vb.x = __byte_perm(rowk[0], 0u, sz);
+          vb.y = __byte_perm(rowk[1], 0u, sz);
+          vb.z = __byte_perm(rowk[2], 0u, sz);
+          vb.w = __byte_perm(rowk[3], 0u, sz);
+          *reinterpret_cast<uint4 *>(eB + sq * kBChunk + 2048) = vb;
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the UMMA (async) proxy
       if (te == 0) { exp_meta[es * 2] = u; exp_meta[es * 2 + 1] = fl; }
@@ -319,11 +352,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
       const uint32_t u = acc_meta[ab * 2], fl = acc_meta[ab * 2 + 1];
       if (fl & kExit) break;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      int4 *dst = reinterpret_cast<int4 *>(a.partials + (uint64_t) u * a.pstride + (COUNT ? NGSD_TILE_ELEMS : 0) + (uint64_t) (qd * 32 + lane) * 128);
+      const uint32_t q = u / a.n_pairs, p = u - q * a.n_pairs;
+      const int ncol = (fl & kPair) ? 256 : 128;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = 0; c0 < ncol; c0 += 32) {
+        const uint32_t t = a.pairs[2 * p + (c0 >> 7)];
+        int4 *dst = reinterpret_cast<int4 *>(a.partials + ((uint64_t) q * a.n_tiles + t) * a.pstride + (COUNT ? NGSD_TILE_ELEMS : 0) +
+                                             (uint64_t) (qd * 32 + lane) * 128);
         uint32_t v[32];
-        const uint32_t taddr = tmem + ((uint32_t) (qd * 32) << 16) + (uint32_t) (ab * 128 + c0);
+        const uint32_t taddr = tmem + ((uint32_t) (qd * 32) << 16) + (uint32_t) (ab * 256 + c0);
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
@@ -333,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
             : "r"(taddr));
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-        for (int k = 0; k < 8; k++) dst[c0 / 4 + k] = make_int4((int) v[4 * k], (int) v[4 * k + 1], (int) v[4 * k + 2], (int) v[4 * k + 3]);
+        for (int k = 0; k < 8; k++) dst[(c0 & 127) / 4 + k] = make_int4((int) v[4 * k], (int) v[4 * k + 1], (int) v[4 * k + 2], (int) v[4 * k + 3]);
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
@@ -344,7 +381,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(256u) : "memory");
+  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512u) : "memory");
 }
 
 // register / smem-resident UMMA loop: the int8 tensor issue-rate ceiling through tcgen05 (roofline denominator of K2c')
@@ -428,7 +465,9 @@ cudaError_t ngsd_launch_dist_umma(ngsd_ctx *ctx, uint32_t n_units, int grid, uin
   a.partials = reinterpret_cast<int32_t *>(ctx->cur_partials);
   a.NW = ctx->NW;
   a.n_tiles = ctx->n_tiles;
-  a.n_units = n_units;
+  a.n_pairs = ctx->n_pairs;
+  a.pairs = ctx->d_pairs;
+  a.n_units = ctx->n_tiles ? n_units / ctx->n_tiles * ctx->n_pairs : 0;     // (split, tile) units -> (split, tile pair) units
   a.pstride = pstride;
   for (int k = 0; k < 4; k++) a.lut[k] = ctx->int_lut[k];
   cudaError_t e = cudaMemsetAsync(ctx->d_sched, 0, sizeof(uint32_t), ctx->stream);

@@ -78,6 +78,7 @@ struct ngsd_ctx {
   // distance workspaces (allocated lazily)
   ngsd_tile *d_tiles = nullptr; uint32_t n_tiles = 0;
   uint32_t *d_tile_index = nullptr;            // [RB][RB] position of tile (ti, tj) in d_tiles (0xFFFFFFFF: not owned)
+  uint32_t *d_pairs = nullptr; uint32_t n_pairs = 0;   // [n_pairs][2] positions of two tiles of one row block (second 0xFFFFFFFF: single); dist_umma.cu
   double *d_partials = nullptr; uint64_t partial_slots = 0;
   // what the contraction launchers write and the epilogues read: d_partials, or the per-block cache below
   double *cur_partials = nullptr;
