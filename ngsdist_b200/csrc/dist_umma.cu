@@ -7,11 +7,15 @@
 // memory, so the 16x expansion of the 2-bit codes has to go through the LSU: a CTA is a four-role pipeline
 //
 //   warp 0      producer   cp.async.bulk of the packed codes (3 x 2 KiB + 64 weight bytes per 64-site stage)
-//   warps 2-17  expanders  codes -> int8 operand tiles (32 + 64 KiB per stage) in the K-major, no-swizzle UMMA layout
-//                          (8-row x 16-byte core matrices; one STS.128 = 4 sites of one row), fence.proxy.async
-//   warp 1      MMA        one lane issues 8 x tcgen05.mma (128 x 256 x 32) per stage, tcgen05.commit frees the stage
-//   warps 18-21 epilogue   tcgen05.ld of a finished unit's 128 x 256 accumulator (two TMEM buffers: the next unit's
-//                          MMAs overlap the read-out), int32 partial tiles written row-major
+//   warps 2-17  expanders  codes -> int8 operands.  B (64 KiB per stage) goes to shared memory in the K-major, no-swizzle
+//                          UMMA layout (8-row x 16-byte core matrices; one STS.128 = 4 sites of one row, fence.proxy.async);
+//                          A (128 rows x 256 bytes per stage) goes to TENSOR MEMORY with tcgen05.st (row = lane, 4 K bytes
+//                          per 32-bit column) -- the MMA reads it from there, which takes a third of the operand traffic
+//                          off the shared-memory pipe
+//   warp 1      MMA        one lane issues 8 x tcgen05.mma (128 x 256 x 32, A from TMEM) per stage, tcgen05.commit frees the stage
+//   warps 18-21 epilogue   tcgen05.ld of a finished unit's 128 x 256 accumulator, int32 partial tiles written row-major
+//                          (TMEM: 256 accumulator columns + 3 x 64 A columns; the expanders run up to 3 stages ahead
+//                          while the accumulator drains)
 //
 // all connected by mbarrier rings.  Shared-memory bandwidth (expansion stores + UMMA operand reads), not the tensor pipe,
 // is the limit; the expansion itself is ~12 integer ops and one 16-byte store per 16 operand bytes.  To spend less of it
@@ -25,14 +29,15 @@
 namespace {
 
 constexpr int kRaw = 4;                           // raw (packed codes) stages
-constexpr int kExp = 2;                           // expanded operand stages
+constexpr int kExp = 3;                           // expanded operand stages
 constexpr int kExpWarps = 16, kEpiWarps = 4;
 constexpr int kThreads = (2 + kExpWarps + kEpiWarps) * 32;
 constexpr int kCodeBytes = 4 * 128 * 4;           // [4 words][128 rows] uint32, one operand of one 64-site stage
 constexpr int kMaskBytes = 128 * 8;               // presence bits of one operand of one stage (count pass)
 constexpr int kRawBytes = 3 * kCodeBytes + 64;    // A codes, B codes of the two tiles, 64 site weights (count pass: 3 masks + weights, smaller)
 constexpr int kOpBytes = 16 * 16 * 128;           // expanded A operand: [16 site quads][16 row groups][8 rows][16 B] = 32 KiB
-constexpr int kExpBytes = 3 * kOpBytes;           // A + B, B = [16 site quads][32 row groups][8 rows][16 B] (count pass: one byte per site, a quarter of it)
+constexpr int kExpBytes = 2 * kOpBytes;           // B = [16 site quads][32 row groups][8 rows][16 B] (count pass: one byte per site, a quarter of it)
+constexpr uint32_t kAccCols = 256, kACols = 64;   // TMEM columns: accumulator, one stage of A
 constexpr int kNBar = 2 * kRaw + 2 * kExp + 4;
 constexpr size_t kSmemBytes = (size_t) kRaw * kRawBytes + (size_t) kExp * kExpBytes + kNBar * 8 + (kRaw + kExp + 2) * 8 + 16 + 16 + 1024;
 
@@ -91,6 +96,22 @@ __device__ __forceinline__ void umma_i8(uint32_t tmem_d, uint64_t da, uint64_t d
       : "memory");
 }
 
+// the same with the A operand in tensor memory (row = lane, K bytes along the columns)
+__device__ __forceinline__ void umma_i8_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(db), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// 4 consecutive 32-bit columns of this thread's TMEM lane (lane quadrant = warp % 4)
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, uint4 v) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+
 struct UmmaArgs {
   const uint32_t *codes;        // [RB][NW][4][128]
   const uint64_t *mask;         // [RB][NW][128] presence bits (count pass)
@@ -115,7 +136,6 @@ template <bool COUNT>
 __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
   constexpr int kIn = COUNT ? kMaskBytes : kCodeBytes;               // packed bytes of one 128-row operand of one stage
   constexpr int kOffW = 3 * kIn;
-  constexpr int kOp = COUNT ? kOpBytes / 4 : kOpBytes;              // expanded bytes of A (B: twice that) per stage
   constexpr int kBChunk = 4096;                       // B: bytes between 16-byte K chunks (32 row groups x 128 B)
   constexpr int kMmas = COUNT ? 2 : 8;
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -143,7 +163,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
     const uint32_t n = threadIdx.x - 32;
     lut16[n] = (n & 1u) | ((n & 2u) << 7) | ((n & 4u) << 14) | ((n & 8u) << 21);
   }
-  if (warp == 1) {                                  // TMEM: two 256-column int32 accumulators (all 512 columns; one CTA per SM)
+  if (warp == 1) {                                  // TMEM: accumulator + kExp stages of A (448 of the 512 columns; one CTA per SM)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -202,46 +222,48 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
       // D = S32 (2 << 4), A = B = INT8 (1 << 7, 1 << 10), both K-major, N (>> 3 at [17,23)), M = 128 (>> 4 at [24,29))
       const uint32_t idesc1 = (2u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t idesc2 = (2u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
-      int es = 0, ab = 0;
-      uint32_t eph = 0, aph[2] = {0, 0};
+      int es = 0;
+      uint32_t eph = 0, aph = 0;
       for (;;) {
         mbar_wait(&exp_full[es], eph);
         const uint32_t u = exp_meta[es * 2], fl = exp_meta[es * 2 + 1];
         if (fl & kExit) {
-          mbar_wait(&acc_empty[ab], aph[ab] ^ 1);
-          acc_meta[ab * 2 + 1] = kExit;
-          mbar_arrive(&acc_full[ab]);
-          mbar_arrive(&acc_full[ab]);
+          mbar_wait(&acc_empty[0], aph ^ 1);
+          acc_meta[1] = kExit;
+          mbar_arrive(&acc_full[0]);
+          mbar_arrive(&acc_full[0]);
           break;
         }
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         if (fl & kFirst) {
-          mbar_wait(&acc_empty[ab], aph[ab] ^ 1);                    // the epilogue has drained this accumulator
+          mbar_wait(&acc_empty[0], aph ^ 1);                         // the epilogue has drained the accumulator
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         }
-        const uint32_t sa = smem_u32(exps + (size_t) es * kExpBytes), sb = sa + kOp;
+        const uint32_t sb = smem_u32(exps + (size_t) es * kExpBytes);
+        const uint32_t ta = tmem + kAccCols + (uint32_t) es * kACols;
         const uint32_t idesc = (fl & kPair) ? idesc2 : idesc1;
 #pragma unroll
-        for (int j = 0; j < kMmas; j++) {                           // K 32 per instruction = two 16-byte chunks (A: 2 KiB apart, B: 4 KiB)
-          const uint64_t da = umma_desc(sa + j * 2 * 2048, 2048, 128);
+        for (int j = 0; j < kMmas; j++) {                           // K 32 per instruction: 8 TMEM columns of A, two 16-byte chunks of B (4 KiB apart)
           const uint64_t db = umma_desc(sb + j * 2 * kBChunk, kBChunk, 128);
-          umma_i8(tmem + (uint32_t) ab * 256u, da, db, idesc, ((fl & kFirst) && j == 0) ? 0u : 1u);
+          umma_i8_ts(tmem, ta + 8u * j, db, idesc, ((fl & kFirst) && j == 0) ? 0u : 1u);
         }
-        umma_commit(&exp_empty[es]);                                 // stage reusable once these MMAs have read it
+        umma_commit(&exp_empty[es]);                                 // stage (B in shared memory, A in TMEM) reusable once these MMAs have read it
         if (fl & kLast) {
-          acc_meta[ab * 2] = u;
-          acc_meta[ab * 2 + 1] = fl & kPair;
-          umma_commit(&acc_full[ab]);                                // accumulator complete ...
-          mbar_arrive(&acc_full[ab]);                                // ... and its meta word published
-          aph[ab] ^= 1;
-          ab ^= 1;
+          acc_meta[0] = u;
+          acc_meta[1] = fl & kPair;
+          umma_commit(&acc_full[0]);                                 // accumulator complete ...
+          mbar_arrive(&acc_full[0]);                                 // ... and its meta word published
+          aph ^= 1;
         }
         if (++es == kExp) { es = 0; eph ^= 1; }
       }
     }
   } else if (warp < 2 + kExpWarps) {
     // ===== expanders: 512 threads, thread -> (row r, byte q0 of each of the 4 code words) of both operands =====
-    const int te = threadIdx.x - 64, r = te & 127, q0 = te >> 7;
+    // (a warp reaches the TMEM lanes of its quadrant warp % 4 only: that fixes which rows it expands)
+    const int r = (warp & 3) * 32 + lane, q0 = (warp - 2) >> 2;
+    const bool lead = warp == 2 && lane == 0;
+    const uint32_t ta_lane = tmem + ((uint32_t) ((warp & 3) * 32) << 16) + kAccCols;
     uint32_t rowk[4];                                               // row k of the S * f table: byte c = S f(k, c)
 #pragma unroll
     for (int k = 0; k < 4; k++)
@@ -254,8 +276,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
       mbar_wait(&raw_full[rs], rph);
       const uint32_t u = raw_meta[rs * 2], fl = raw_meta[rs * 2 + 1];
       mbar_wait(&exp_empty[es], eph ^ 1);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (fl & kExit) {
-        if (te == 0) exp_meta[es * 2 + 1] = kExit;
+        if (lead) exp_meta[es * 2 + 1] = kExit;
         __syncwarp();
         if (lane == 0) mbar_arrive(&exp_full[es]);
         break;
@@ -277,9 +300,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
         vb.y = lut16[(mb >> 4) & 15u];
         vb.z = lut16[(mb >> 8) & 15u];
         vb.w = lut16[(mb >> 12) & 15u];
-        unsigned char *eA = exps + (size_t) es * kExpBytes + unit_off + (uint32_t) q0 * 2048;
-        unsigned char *eB = exps + (size_t) es * kExpBytes + kOp + unit_off + (uint32_t) q0 * kBChunk;
-        *reinterpret_cast<uint4 *>(eA) = va;
+        unsigned char *eB = exps + (size_t) es * kExpBytes + unit_off + (uint32_t) q0 * kBChunk;
+        tmem_st4(ta_lane + (uint32_t) es * kACols + 4u * q0, va);
         *reinterpret_cast<uint4 *>(eB) = vb;
         if (fl & kPair) {
           vb.x = lut16[mb1 & 15u];
@@ -288,8 +310,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
           vb.w = lut16[(mb1 >> 12) & 15u];
           *reinterpret_cast<uint4 *>(eB + 2048) = vb;
         }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        if (te == 0) { exp_meta[es * 2] = u; exp_meta[es * 2 + 1] = fl; }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        if (lead) { exp_meta[es * 2] = u; exp_meta[es * 2 + 1] = fl; }
         __syncwarp();
         if (lane == 0) { mbar_arrive(&exp_full[es]); mbar_arrive(&raw_empty[rs]); }
         if (++rs == kRaw) { rs = 0; rph ^= 1; }
@@ -299,7 +323,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
       const uint32_t *cA = reinterpret_cast<const uint32_t *>(rawS) + r, *cB = reinterpret_cast<const uint32_t *>(rawS + kCodeBytes) + r;
       const uint32_t *cB1 = reinterpret_cast<const uint32_t *>(rawS + 2 * kCodeBytes) + r;
       const uint32_t *W32 = reinterpret_cast<const uint32_t *>(rawS + kOffW) + q0;
-      unsigned char *eA = exps + (size_t) es * kExpBytes + unit_off, *eB = eA + kOpBytes;
+      unsigned char *eB = exps + (size_t) es * kExpBytes + unit_off;
+      const uint32_t ta = ta_lane + (uint32_t) es * kACols + 4u * q0;
       const bool paired = (fl & kPair) != 0;
       // The K order inside a 16-byte unit is free as long as both operands use it: PLANE-major here (word k = plane k of the
       // unit's 4 sites), because then one byte-permute builds a whole word.  With sel = the 4 codes spread to the 4 selector
@@ -322,7 +347,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
         vb.z = __byte_perm(rowk[2], 0u, sy);
         vb.w = __byte_perm(rowk[3], 0u, sy);
         const uint32_t sq = (uint32_t) (4 * i + q0);
-        *reinterpret_cast<uint4 *>(eA + sq * 2048) = va;
+        tmem_st4(ta + 16u * i, va);                                 // K bytes 16 sq .. 16 sq + 15 of this row = columns 4 sq .. 4 sq + 3
         *reinterpret_cast<uint4 *>(eB + sq * kBChunk) = vb;
         if (paired) {                                               // second tile's rows: row groups 16..31 of B
           const uint32_t z = (cB1[i * 128] >> (8 * q0)) & 0xFFu;
@@ -335,8 +360,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
           *reinterpret_cast<uint4 *>(eB + sq * kBChunk + 2048) = vb;
         }
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // A rows are in tensor memory
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the UMMA (async) proxy
-      if (te == 0) { exp_meta[es * 2] = u; exp_meta[es * 2 + 1] = fl; }
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      if (lead) { exp_meta[es * 2] = u; exp_meta[es * 2 + 1] = fl; }
       __syncwarp();
       if (lane == 0) { mbar_arrive(&exp_full[es]); mbar_arrive(&raw_empty[rs]); }
       if (++rs == kRaw) { rs = 0; rph ^= 1; }
@@ -345,11 +372,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
   } else {
     // ===== epilogue: a warp can read the 32 TMEM lanes (= tile rows) of its quadrant warp % 4 =====
     const int qd = warp & 3;
-    int ab = 0;
-    uint32_t aph[2] = {0, 0};
+    uint32_t aph = 0;
     for (;;) {
-      mbar_wait(&acc_full[ab], aph[ab]);
-      const uint32_t u = acc_meta[ab * 2], fl = acc_meta[ab * 2 + 1];
+      mbar_wait(&acc_full[0], aph);
+      const uint32_t u = acc_meta[0], fl = acc_meta[1];
       if (fl & kExit) break;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t q = u / a.n_pairs, p = u - q * a.n_pairs;
@@ -360,7 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
         int4 *dst = reinterpret_cast<int4 *>(a.partials + ((uint64_t) q * a.n_tiles + t) * a.pstride + (COUNT ? NGSD_TILE_ELEMS : 0) +
                                              (uint64_t) (qd * 32 + lane) * 128);
         uint32_t v[32];
-        const uint32_t taddr = tmem + ((uint32_t) (qd * 32) << 16) + (uint32_t) (ab * 256 + c0);
+        const uint32_t taddr = tmem + ((uint32_t) (qd * 32) << 16) + (uint32_t) c0;
         asm volatile(
             "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
             : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
@@ -374,9 +400,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
       }
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       __syncwarp();
-      if (lane == 0) mbar_arrive(&acc_empty[ab]);
-      aph[ab] ^= 1;
-      ab ^= 1;
+      if (lane == 0) mbar_arrive(&acc_empty[0]);
+      aph ^= 1;
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
