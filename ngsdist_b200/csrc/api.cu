@@ -517,12 +517,18 @@ static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n
   uint64_t n_words = 0;
   if (use_cache) {                                             // identity word list over the blocks in use
     n_words = n_blocks * (block_size / 64);
-    for (uint64_t w = 0; w < n_words && build_cache; w++) { h_ids[w] = (uint32_t) w; h_layer[w] = 0; }
+    for (uint64_t w = 0; w < n_words && build_cache; w++) { h_ids[w] = (uint32_t) w; h_layer[w] = 0x80000000u; }   // bit 31: all 64 weights are 1
   }
   for (uint32_t l = 0; l < layers && !use_cache; l++)
     for (uint64_t w = 0; w < NW; w++) {
       const uint64_t *p8 = (const uint64_t *) (h_w + (uint64_t) l * nsp + w * 64);
-      if (p8[0] | p8[1] | p8[2] | p8[3] | p8[4] | p8[5] | p8[6] | p8[7]) { h_ids[n_words] = (uint32_t) w; h_layer[n_words] = l; n_words++; }
+      if (p8[0] | p8[1] | p8[2] | p8[3] | p8[4] | p8[5] | p8[6] | p8[7]) {
+        const uint64_t one = 0x0101010101010101ull;
+        const bool unit = p8[0] == one && p8[1] == one && p8[2] == one && p8[3] == one && p8[4] == one && p8[5] == one && p8[6] == one && p8[7] == one;
+        h_ids[n_words] = (uint32_t) w;
+        h_layer[n_words] = l | (unit ? 0x80000000u : 0u);      // bit 31: the kernels may skip the weight bytes of this word
+        n_words++;
+      }
     }
   (void) h_ew; (void) h_em;
 

@@ -155,7 +155,7 @@ __global__ void __launch_bounds__(kThreads, NGSD_IMMA_CTAS) k_dist_imma(ImmaArgs
         const uint32_t *Bb = a.codes + (uint64_t) tl.tj * a.NW * 512;
         for (uint32_t c = c0; c < c1; c++) {
           const uint64_t word = a.word_ids[c];
-          const uint8_t *wsrc = a.wsite + ((uint64_t) a.word_layer[c] * a.NW + word) * 64;
+          const uint8_t *wsrc = a.wsite + ((uint64_t) (a.word_layer[c] & 0x7FFFFFFFu) * a.NW + word) * 64;
           mbar_wait_sleep(&empty[stage], phase ^ 1);
           meta[stage * 2] = u;
           meta[stage * 2 + 1] = (c == c0 ? kFirst : 0u) | (c + 1 == c1 ? kLast : 0u);

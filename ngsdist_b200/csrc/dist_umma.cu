@@ -127,7 +127,57 @@ struct UmmaArgs {
   uint32_t lut[4];
 };
 
-enum : uint32_t { kFirst = 1u, kLast = 2u, kPair = 4u, kExit = 8u };
+enum : uint32_t { kFirst = 1u, kLast = 2u, kPair = 4u, kExit = 8u, kUnitW = 16u };
+
+// Expansion of one 64-site stage by thread (row r, byte q0 of each of the 4 code words): A row -> tensor memory, B rows ->
+// shared memory.  The K order inside a 16-byte unit is free as long as both operands use it: PLANE-major here (word k =
+// plane k of the unit's 4 sites), because then one byte-permute builds a whole word.  With sel = the 4 codes spread to the
+// 4 selector nibbles, PRMT(T_k, sel) picks byte c_j of T_k for site j:  T_k = 0xFF << 8k gives the one-hot plane k of A
+// (AND the 4 weight bytes; UNITW: all 64 site weights are 1, T_k = 0x01 << 8k and no AND), T_k = row k of the S * f
+// table gives plane k of B.  No table loads.
+__device__ __forceinline__ uint32_t spread_codes(uint32_t word, uint32_t pick) {
+  const uint32_t x = __byte_perm(word, 0u, pick);                   // byte q0 of the code word, zero-extended
+  const uint32_t s = (x | (x << 4)) & 0x0F0Fu;
+  return (s | (s << 2)) & 0x3333u;
+}
+template <bool UNITW>
+__device__ __forceinline__ void expand_codes(const uint32_t *cA, const uint32_t *cB, const uint32_t *cB1, const uint32_t *W32,
+                                             unsigned char *eB, uint32_t ta, int q0, bool paired, const uint32_t (&rowk)[4]) {
+  constexpr int kBChunk = 4096;
+  const uint32_t pick = 0x4440u + (uint32_t) q0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {                                     // code word i: sites 16 i + 4 q0 .. + 3 = site quad 4 i + q0
+    const uint32_t sx = spread_codes(cA[i * 128], pick), sy = spread_codes(cB[i * 128], pick);
+    uint4 va, vb;
+    if (UNITW) {
+      va.x = __byte_perm(0x00000001u, 0u, sx);
+      va.y = __byte_perm(0x00000100u, 0u, sx);
+      va.z = __byte_perm(0x00010000u, 0u, sx);
+      va.w = __byte_perm(0x01000000u, 0u, sx);
+    } else {
+      const uint32_t ww = W32[i * 4];
+      va.x = __byte_perm(0x000000FFu, 0u, sx) & ww;
+      va.y = __byte_perm(0x0000FF00u, 0u, sx) & ww;
+      va.z = __byte_perm(0x00FF0000u, 0u, sx) & ww;
+      va.w = __byte_perm(0xFF000000u, 0u, sx) & ww;
+    }
+    vb.x = __byte_perm(rowk[0], 0u, sy);
+    vb.y = __byte_perm(rowk[1], 0u, sy);
+    vb.z = __byte_perm(rowk[2], 0u, sy);
+    vb.w = __byte_perm(rowk[3], 0u, sy);
+    const uint32_t sq = (uint32_t) (4 * i + q0);
+    tmem_st4(ta + 16u * i, va);                                     // K bytes 16 sq .. 16 sq + 15 of this row = columns 4 sq .. 4 sq + 3
+    *reinterpret_cast<uint4 *>(eB + sq * kBChunk) = vb;
+    if (paired) {                                                   // second tile's rows: row groups 16..31 of B
+      const uint32_t sz = spread_codes(cB1[i * 128], pick);
+      vb.x = __byte_perm(rowk[0], 0u, sz);
+      vb.y = __byte_perm(rowk[1], 0u, sz);
+      vb.z = __byte_perm(rowk[2], 0u, sz);
+      vb.w = __byte_perm(rowk[3], 0u, sz);
+      *reinterpret_cast<uint4 *>(eB + sq * kBChunk + 2048) = vb;
+    }
+  }
+}
 
 // COUNT = true: the same pipeline computes the shared-site counts of --pairwise_del, cnt(i,j) = sum_s w_s m_i(s) m_j(s), as an
 // int8 GEMM with ONE byte per site (A' = w_s m_i(s), B' = m_j(s) from the presence masks; 2 MMAs per 64-site stage) and
@@ -192,11 +242,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
         uint32_t nword = a.word_ids[c0], nlayer = a.word_layer[c0];
         for (uint32_t c = c0; c < c1; c++) {
           const uint64_t word = nword;
-          const uint8_t *wsrc = a.wsite + ((uint64_t) nlayer * a.NW + word) * 64;
+          const uint32_t unitw = nlayer >> 31;                      // api.cu: bit 31 = all 64 site weights of this word are 1
+          const uint8_t *wsrc = a.wsite + ((uint64_t) (nlayer & 0x7FFFFFFFu) * a.NW + word) * 64;
           if (c + 1 < c1) { nword = a.word_ids[c + 1]; nlayer = a.word_layer[c + 1]; }   // next entry's loads fly during the wait below
           mbar_wait(&raw_empty[rs], rph ^ 1);
           raw_meta[rs * 2] = u;
-          raw_meta[rs * 2 + 1] = (c == c0 ? kFirst : 0u) | (c + 1 == c1 ? kLast : 0u) | (paired ? kPair : 0u);
+          raw_meta[rs * 2 + 1] = (c == c0 ? kFirst : 0u) | (c + 1 == c1 ? kLast : 0u) | (paired ? kPair : 0u) | (unitw ? kUnitW : 0u);
           mbar_expect_tx(&raw_full[rs], (paired ? 3 : 2) * kIn + 64);
           unsigned char *dst = raw + (size_t) rs * kRawBytes;
           if (COUNT) {
@@ -292,10 +343,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
         const uint32_t mb1 = reinterpret_cast<const uint32_t *>(rawS + 2 * kMaskBytes)[r * 2 + (q0 >> 1)] >> (16 * (q0 & 1));
         const uint4 ww = *reinterpret_cast<const uint4 *>(rawS + kOffW + 16 * q0);
         uint4 va, vb;
-        va.x = (lut16[ma & 15u] * 0xFFu) & ww.x;
-        va.y = (lut16[(ma >> 4) & 15u] * 0xFFu) & ww.y;
-        va.z = (lut16[(ma >> 8) & 15u] * 0xFFu) & ww.z;
-        va.w = (lut16[(ma >> 12) & 15u] * 0xFFu) & ww.w;
+        va.x = lut16[ma & 15u];
+        va.y = lut16[(ma >> 4) & 15u];
+        va.z = lut16[(ma >> 8) & 15u];
+        va.w = lut16[(ma >> 12) & 15u];
+        if (!(fl & kUnitW)) {
+          va.x = (va.x * 0xFFu) & ww.x;
+          va.y = (va.y * 0xFFu) & ww.y;
+          va.z = (va.z * 0xFFu) & ww.z;
+          va.w = (va.w * 0xFFu) & ww.w;
+        }
         vb.x = lut16[mb & 15u];
         vb.y = lut16[(mb >> 4) & 15u];
         vb.z = lut16[(mb >> 8) & 15u];
@@ -326,40 +383,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
       unsigned char *eB = exps + (size_t) es * kExpBytes + unit_off;
       const uint32_t ta = ta_lane + (uint32_t) es * kACols + 4u * q0;
       const bool paired = (fl & kPair) != 0;
-      // The K order inside a 16-byte unit is free as long as both operands use it: PLANE-major here (word k = plane k of the
-      // unit's 4 sites), because then one byte-permute builds a whole word.  With sel = the 4 codes spread to the 4 selector
-      // nibbles, PRMT(T_k, sel) picks byte c_j of T_k for site j:  T_k = 0xFF << 8k gives the one-hot plane k of A (AND the
-      // 4 weight bytes), T_k = row k of the S * f table gives plane k of B.  No table loads, ~24 integer ops per unit pair.
-#pragma unroll
-      for (int i = 0; i < 4; i++) {                                 // code word i: sites 16 i + 4 q0 .. + 3 = site quad 4 i + q0
-        const uint32_t x = (cA[i * 128] >> (8 * q0)) & 0xFFu, y = (cB[i * 128] >> (8 * q0)) & 0xFFu;
-        const uint32_t ww = W32[i * 4];
-        uint32_t sx = (x | (x << 4)) & 0x0F0Fu, sy = (y | (y << 4)) & 0x0F0Fu;
-        sx = (sx | (sx << 2)) & 0x3333u;
-        sy = (sy | (sy << 2)) & 0x3333u;
-        uint4 va, vb;
-        va.x = __byte_perm(0x000000FFu, 0u, sx) & ww;
-        va.y = __byte_perm(0x0000FF00u, 0u, sx) & ww;
-        va.z = __byte_perm(0x00FF0000u, 0u, sx) & ww;
-        va.w = __byte_perm(0xFF000000u, 0u, sx) & ww;
-        vb.x = __byte_perm(rowk[0], 0u, sy);
-        vb.y = __byte_perm(rowk[1], 0u, sy);
-        vb.z = __byte_perm(rowk[2], 0u, sy);
-        vb.w = __byte_perm(rowk[3], 0u, sy);
-        const uint32_t sq = (uint32_t) (4 * i + q0);
-        tmem_st4(ta + 16u * i, va);                                 // K bytes 16 sq .. 16 sq + 15 of this row = columns 4 sq .. 4 sq + 3
-        *reinterpret_cast<uint4 *>(eB + sq * kBChunk) = vb;
-        if (paired) {                                               // second tile's rows: row groups 16..31 of B
-          const uint32_t z = (cB1[i * 128] >> (8 * q0)) & 0xFFu;
-          uint32_t sz = (z | (z << 4)) & 0x0F0Fu;
-          sz = (sz | (sz << 2)) & 0x3333u;
-          vb.x = __byte_perm(rowk[0], 0u, sz);
-          vb.y = __byte_perm(rowk[1], 0u, sz);
-          vb.z = __byte_perm(rowk[2], 0u, sz);
-          vb.w = __byte_perm(rowk[3], 0u, sz);
-          *reinterpret_cast<uint4 *>(eB + sq * kBChunk + 2048) = vb;
-        }
-      }
+      if (fl & kUnitW)
+        expand_codes<true>(cA, cB, cB1, W32, eB, ta, q0, paired, rowk);
+      else
+        expand_codes<false>(cA, cB, cB1, W32, eB, ta, q0, paired, rowk);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // A rows are in tensor memory
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the UMMA (async) proxy
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
