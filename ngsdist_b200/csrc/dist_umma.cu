@@ -34,7 +34,7 @@ constexpr int kExpWarps = 16, kEpiWarps = 4;
 constexpr int kThreads = (2 + kExpWarps + kEpiWarps) * 32;
 constexpr int kCodeBytes = 4 * 128 * 4;           // [4 words][128 rows] uint32, one operand of one 64-site stage
 constexpr int kMaskBytes = 128 * 8;               // presence bits of one operand of one stage (count pass)
-constexpr int kRawBytes = 3 * kCodeBytes + 64;    // A codes, B codes of the two tiles, 64 site weights (count pass: 3 masks + weights, smaller)
+constexpr int kRawBytes = 3 * kCodeBytes + 128;   // A codes, B codes of the two tiles, 64 site weights; a multiple of 128 so that a warp's 32 code words stay in one bank row
 constexpr int kOpBytes = 16 * 16 * 128;           // expanded A operand: [16 site quads][16 row groups][8 rows][16 B] = 32 KiB
 constexpr int kExpBytes = 2 * kOpBytes;           // B = [16 site quads][32 row groups][8 rows][16 B] (count pass: one byte per site, a quarter of it)
 constexpr uint32_t kAccCols = 256, kACols = 64;   // TMEM columns: accumulator, one stage of A
@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
     const int qd = warp & 3;
     uint32_t aph = 0;
     for (;;) {
-      mbar_wait(&acc_full[0], aph);
+      mbar_wait_sleep(&acc_full[0], aph);                          // (idle for a whole unit: do not compete for issue slots)
       const uint32_t u = acc_meta[0], fl = acc_meta[1];
       if (fl & kExit) break;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
