@@ -287,7 +287,7 @@ def main():
                                "achieved": exe, "peak": imma_peak, "unit": "TMAC/s", "frac": exe / imma_peak,
                                "peak_source": "live back-to-back %s issue-rate probe in this run" % ("tcgen05.mma 128x128x32" if umma else "IMMA.16832"),
                                "note": "4 int8 MAC per pair-site (one-hot code x table column); the operands are expanded on chip from 2-bit codes: "
-                                       "the tcgen05 path is bound by the on-chip expansion (shared-memory pipe 72 %, integer ALU 58 % in ncu), not by the tensor pipe"}}
+                                       "the tcgen05 path is bound by the on-chip expansion (A rows into TMEM, B rows into shared memory; ncu: tensor pipe 66 %, LSU wavefronts 67 %, integer ALU 62 %), not by the tensor pipe"}}
         gc.close()
         del out_c
 
