@@ -111,6 +111,14 @@ NGSD_API int ngsd_push_sites(ngsd_ctx *ctx, const double *raw_host, uint64_t sit
 NGSD_API int ngsd_push_sites_device(ngsd_ctx *ctx, const double *raw_dev, uint64_t site0, uint64_t n);
 /* Genotype input (no --probs): codes [site][ind] in {-1,0,1,2}; NGSD_ERR_GENO for anything > 2. */
 NGSD_API int ngsd_push_genotypes(ngsd_ctx *ctx, const int8_t *codes_host, uint64_t site0, uint64_t n);
+/* The same genotype input, four individuals per byte (the 1 B -- or as text 2-3 B -- per individual-site
+ * of read_data.cpp:88-95 is what makes the 5 000 x 5 000 000 configuration expensive to store and to move).  Site-major:
+ * individual i of site s is the 2-bit field (packed[s * row_stride + i / 4] >> 2 * (i % 4)) & 3, row_stride >= ceil(n_ind / 4);
+ * code_of_field[f] in {-1,0,1,2} is the reference's code for field value f (NULL: {0,1,2,-1}).  A variant-major PLINK .bed
+ * body (after its 3 magic bytes) is exactly this layout with code_of_field = {0,-1,1,2} and row_stride = ceil(n_ind / 4).
+ * Results are bit-identical to ngsd_push_genotypes of the unpacked codes. */
+NGSD_API int ngsd_push_packed_genotypes(ngsd_ctx *ctx, const uint8_t *packed_host, uint64_t row_stride, const int8_t *code_of_field,
+                                        uint64_t site0, uint64_t n);
 /* Completes the front end: checks that every site was pushed and raises the deferred NGSD_ERR_NAN. */
 NGSD_API int ngsd_frontend(ngsd_ctx *ctx);
 

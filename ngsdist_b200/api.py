@@ -17,7 +17,7 @@ _LIB = os.path.join(_HERE, "libngsdist_b200.so")
 
 ABI_SYMBOLS = [
     "ngsd_abi_version", "ngsd_default_cfg", "ngsd_create", "ngsd_destroy", "ngsd_last_error", "ngsd_push_sites",
-    "ngsd_push_sites_device", "ngsd_push_genotypes", "ngsd_frontend", "ngsd_distances", "ngsd_taus_seed", "ngsd_taus_get",
+    "ngsd_push_sites_device", "ngsd_push_genotypes", "ngsd_push_packed_genotypes", "ngsd_frontend", "ngsd_distances", "ngsd_taus_seed", "ngsd_taus_get",
     "ngsd_boot_block_counts", "ngsd_get_posteriors", "ngsd_synth_raw_device", "ngsd_get_timing", "ngsd_stream",
     "ngsd_probe_fp64_tflops", "ngsd_probe_int8_tmacs", "ngsd_probe_umma_tmacs", "ngsd_host_alloc", "ngsd_host_free", "ngsd_set_tile_shard", "ngsd_device_results", "ngsd_finish",
 ]
@@ -82,6 +82,7 @@ def lib():
     L.ngsd_push_sites.argtypes = [vp, vp, u64, u64]
     L.ngsd_push_sites_device.argtypes = [vp, vp, u64, u64]
     L.ngsd_push_genotypes.argtypes = [vp, vp, u64, u64]
+    L.ngsd_push_packed_genotypes.argtypes = [vp, vp, u64, vp, u64, u64]
     L.ngsd_frontend.argtypes = [vp]
     L.ngsd_distances.argtypes = [vp, vp, u64, u64, vp, vp, vp]
     L.ngsd_taus_seed.argtypes = [vp, C.c_uint32]
@@ -105,7 +106,7 @@ def lib():
     L.ngsd_set_tile_shard.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.ngsd_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.ngsd_finish.argtypes = [vp, vp]
-    for name in ("ngsd_create", "ngsd_destroy", "ngsd_push_sites", "ngsd_push_sites_device", "ngsd_push_genotypes", "ngsd_frontend",
+    for name in ("ngsd_create", "ngsd_destroy", "ngsd_push_sites", "ngsd_push_sites_device", "ngsd_push_genotypes", "ngsd_push_packed_genotypes", "ngsd_frontend",
                  "ngsd_distances", "ngsd_get_posteriors", "ngsd_synth_raw_device", "ngsd_get_timing", "ngsd_probe_fp64_tflops", "ngsd_probe_int8_tmacs", "ngsd_probe_umma_tmacs",
                  "ngsd_set_tile_shard", "ngsd_device_results", "ngsd_finish"):
         getattr(L, name).restype = i32
@@ -191,6 +192,22 @@ def probe_int8_tmacs(device=0):
     return v.value
 
 
+PLINK_BED_CODES = (0, -1, 1, 2)     # .bed 2-bit fields: 0 = homozygous A1, 1 = missing, 2 = heterozygous, 3 = homozygous A2
+
+
+def pack_genotypes(geno, field_of_code=None):
+    """[site][ind] codes {-1,0,1,2} -> [site][ceil(n_ind / 4)] bytes, individual i in bits 2 (i % 4) of byte i / 4.
+    field_of_code maps code c (index c + 1, i.e. [-1, 0, 1, 2]) to its 2-bit field; default: the inverse of {0,1,2,-1}."""
+    geno = np.asarray(geno, dtype=np.int8)
+    f = np.array([3, 0, 1, 2] if field_of_code is None else field_of_code, dtype=np.uint8)[geno.astype(np.int64) + 1]
+    n_sites, n_ind = geno.shape
+    pad = (-n_ind) % 4
+    if pad:
+        f = np.concatenate([f, np.zeros((n_sites, pad), dtype=np.uint8)], axis=1)
+    f = f.reshape(n_sites, -1, 4)
+    return (f[:, :, 0] | (f[:, :, 1] << 2) | (f[:, :, 2] << 4) | (f[:, :, 3] << 6)).astype(np.uint8)
+
+
 class NgsDistB200:
     """One context = one GPU = the hot path of one ngsDist run."""
 
@@ -259,6 +276,15 @@ class NgsDistB200:
         codes = np.ascontiguousarray(codes, dtype=np.int8)
         assert codes.shape[1] == self.p.n_ind
         self._check(lib().ngsd_push_genotypes(self._h, _ptr(codes), site0, codes.shape[0]))
+
+    def push_packed_genotypes(self, packed, code_of_field=None, site0=0, n=None):
+        """2-bit genotypes, four individuals per byte, site-major rows (see ngsd_push_packed_genotypes / pack_genotypes)."""
+        packed = np.ascontiguousarray(packed, dtype=np.uint8)
+        assert packed.ndim == 2
+        cof = None if code_of_field is None else np.ascontiguousarray(code_of_field, dtype=np.int8)
+        assert cof is None or cof.shape == (4,)
+        self._check(lib().ngsd_push_packed_genotypes(self._h, _ptr(packed), packed.shape[1], _ptr(cof), site0,
+                                                     packed.shape[0] if n is None else n))
 
     def frontend(self):
         self._check(lib().ngsd_frontend(self._h))

@@ -378,6 +378,57 @@ int ngsd_push_genotypes(ngsd_ctx *ctx, const int8_t *codes_host, uint64_t site0,
   return NGSD_OK;
 }
 
+int ngsd_push_packed_genotypes(ngsd_ctx *ctx, const uint8_t *packed_host, uint64_t row_stride, const int8_t *code_of_field, uint64_t site0,
+                               uint64_t n) {
+  int rc = check_push(ctx, site0, n);
+  if (rc) return rc;
+  if (!packed_host) { ngsd_set_error(ctx, "null packed pointer"); return NGSD_ERR_ARG; }
+  if (ctx->cfg.input_kind != NGSD_INPUT_GENOTYPES) { ngsd_set_error(ctx, "context expects genotype likelihoods"); return NGSD_ERR_ARG; }
+  if (row_stride < (ctx->n_ind + 3) / 4) { ngsd_set_error(ctx, "row_stride is smaller than ceil(n_ind / 4)"); return NGSD_ERR_ARG; }
+  static const int8_t identity[4] = {0, 1, 2, -1};
+  const int8_t *map = code_of_field ? code_of_field : identity;
+  uint32_t map32 = 0;
+  for (int f = 0; f < 4; f++) {
+    if (map[f] < -1 || map[f] > 2) { ngsd_set_error(ctx, "code_of_field entries must be in {-1,0,1,2}"); return NGSD_ERR_ARG; }
+    map32 |= (uint32_t) (uint8_t) map[f] << (8 * f);
+  }
+  NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
+  // one staging slot = the chunk's packed rows followed by its unpacked int8 codes
+  const uint64_t bps = row_stride + ctx->n_ind;
+  if (ctx->stage_dev[0] && ctx->stage_bps != bps) {          // a different row_stride than the last push: re-size
+    NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < 2; b++) { cudaFree(ctx->stage_dev[b]); ctx->stage_dev[b] = nullptr; }
+  }
+  rc = ensure_staging(ctx, bps);
+  if (rc) return rc;
+  ctx->stage_bps = bps;
+  ctx->timing = ngsd_timing();
+  tick(ctx, 0);
+  int launches = 0;
+  for (uint64_t off = 0; off < n; off += ctx->stage_sites) {
+    const uint64_t m = std::min(ctx->stage_sites, n - off);
+    const int b = ctx->stage_next;
+    ctx->stage_next ^= 1;
+    uint8_t *d_packed = reinterpret_cast<uint8_t *>(ctx->stage_dev[b]);
+    int8_t *d_codes = reinterpret_cast<int8_t *>(d_packed + ctx->stage_sites * row_stride);
+    NGSD_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[b], 0));
+    NGSD_CUDA(ctx, cudaMemcpyAsync(d_packed, packed_host + off * row_stride, m * row_stride, cudaMemcpyHostToDevice, ctx->copy_stream));
+    NGSD_CUDA(ctx, cudaEventRecord(ctx->stage_ready[b], ctx->copy_stream));
+    NGSD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->stage_ready[b], 0));
+    NGSD_CUDA(ctx, ngsd_launch_unpack_2bit(ctx, d_packed, row_stride, map32, m, d_codes));
+    ngsd_frontend_args a{nullptr, d_codes, site0 + off, m};
+    NGSD_CUDA(ctx, ngsd_launch_frontend(ctx, a));
+    NGSD_CUDA(ctx, cudaEventRecord(ctx->stage_free[b], ctx->stream));
+    launches += 2;
+  }
+  tick(ctx, 1);
+  ctx->timing.launches = launches;
+  ctx->timing.total_ms = -1.f;
+  NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the caller may now reuse packed_host
+  mark_pushed(ctx, site0, n);
+  return NGSD_OK;
+}
+
 int ngsd_frontend(ngsd_ctx *ctx) {
   if (!ctx) return NGSD_ERR_ARG;
   if (ctx->words_pushed != ctx->NW) {

@@ -438,6 +438,17 @@ __global__ void k_unpack(const double *__restrict__ Apack, const uint32_t *__res
   if (miss) miss[idx] = !((mask[(rb * NW + (s >> 6)) * 128 + r] >> (s & 63)) & 1);
 }
 
+// ngsd_push_packed_genotypes: 2-bit fields, four individuals per byte -> the int8 codes of read_data.cpp:88-95 that
+// k_frontend / k_frontend_codes take (byte f of code_of_field = the code of field value f)
+__global__ void k_unpack_2bit(const uint8_t *__restrict__ packed, uint64_t row_stride, uint32_t code_of_field, uint64_t n_ind, uint64_t n,
+                              int8_t *__restrict__ codes) {
+  const uint64_t idx = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n * n_ind) return;
+  const uint64_t s = idx / n_ind, i = idx - s * n_ind;
+  const unsigned f = (packed[s * row_stride + (i >> 2)] >> (2 * (i & 3))) & 3u;
+  codes[idx] = (int8_t) (code_of_field >> (8 * f));
+}
+
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
   x += 0x9E3779B97F4A7C15ull;
   x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -487,6 +498,13 @@ cudaError_t ngsd_launch_frontend(ngsd_ctx *ctx, const ngsd_frontend_args &a) {
   else
     k_frontend<false><<<grid, block, 0, ctx->stream>>>(c, a.raw, a.codes, ctx->n_ind, a.site0, a.n, ctx->NC, ctx->NW, ctx->Apack,
                                                        ctx->Bpack, ctx->Cplane, ctx->ldc, ctx->mask, ctx->d_err);
+  return cudaGetLastError();
+}
+
+cudaError_t ngsd_launch_unpack_2bit(ngsd_ctx *ctx, const uint8_t *packed_dev, uint64_t row_stride, uint32_t code_of_field, uint64_t n,
+                                    int8_t *codes_dev) {
+  const uint64_t tot = n * ctx->n_ind;
+  k_unpack_2bit<<<(unsigned) ((tot + 255) / 256), 256, 0, ctx->stream>>>(packed_dev, row_stride, code_of_field, ctx->n_ind, n, codes_dev);
   return cudaGetLastError();
 }
 

@@ -74,6 +74,7 @@ struct ngsd_ctx {
   cudaEvent_t stage_free[2] = {nullptr, nullptr};
   cudaEvent_t stage_ready[2] = {nullptr, nullptr};
   uint64_t stage_sites = 0;
+  uint64_t stage_bps = 0;                      // bytes per site the staging slots were sized for (packed genotype pushes)
   int stage_next = 0;
   // distance workspaces (allocated lazily)
   ngsd_tile *d_tiles = nullptr; uint32_t n_tiles = 0;
@@ -125,6 +126,8 @@ struct ngsd_frontend_args {
 };
 cudaError_t ngsd_launch_frontend(ngsd_ctx *ctx, const ngsd_frontend_args &a);
 cudaError_t ngsd_launch_unpack(ngsd_ctx *ctx, double *P_dev /*[ind][site][3]*/, uint8_t *miss_dev /*[ind][site]*/);
+cudaError_t ngsd_launch_unpack_2bit(ngsd_ctx *ctx, const uint8_t *packed_dev, uint64_t row_stride, uint32_t code_of_field, uint64_t n,
+                                    int8_t *codes_dev);   // packed fields -> [site][ind] int8 codes
 cudaError_t ngsd_launch_synth(ngsd_ctx *ctx, double *raw_dev, uint64_t seed, double miss_rate, uint64_t site0, uint64_t n);
 
 struct ngsd_dist_plan {

@@ -137,3 +137,38 @@ def test_call_decisions_at_the_fast_test_boundaries():
         Pg, mg = g.posteriors()
     assert np.array_equal(Pg, P)
     assert np.array_equal(mg, 1 - oracle.miss_mask(P))
+
+
+@pytest.mark.parametrize("n_ind", [203, 128, 5])
+def test_packed_genotype_input_is_the_same_input(n_ind):
+    """ngsd_push_packed_genotypes (2-bit fields, four individuals per byte) against ngsd_push_genotypes of the
+    same codes: bit-identical matrices, with the default field coding, the PLINK .bed coding, a padded row stride and
+    pushes split at 64-site words."""
+    rng = np.random.RandomState(n_ind)
+    n_sites = 1000
+    geno = rng.randint(-1, 3, size=(n_sites, n_ind)).astype(np.int8)
+    kw = dict(in_probs=False, indep_geno=True, pairwise_del=True, evol_model=2)
+    ref = run(None, genotypes=geno, **kw)[0]
+
+    def packed_run(packed, cof, split):
+        p = nb().Params(n_ind=n_ind, n_sites=n_sites, **kw)
+        with nb().NgsDistB200(p) as g:
+            if split:
+                g.push_packed_genotypes(packed[:640], cof, 0)
+                g.push_packed_genotypes(packed[640:], cof, 640)
+            else:
+                g.push_packed_genotypes(packed, cof)
+            return g.run(want_num=True, want_cnt=True)[0]
+
+    bed = nb().pack_genotypes(geno, field_of_code=[1, 0, 2, 3])            # -1 -> 01, 0 -> 00, 1 -> 10, 2 -> 11
+    wide = np.concatenate([nb().pack_genotypes(geno), np.full((n_sites, 3), 0xA5, np.uint8)], axis=1)   # row_stride > ceil(n/4)
+    for packed, cof, split in [(nb().pack_genotypes(geno), None, False), (bed, nb().PLINK_BED_CODES, True), (wide, None, True)]:
+        r = packed_run(packed, cof, split)
+        for k in ("dist", "num", "cnt"):
+            assert np.array_equal(r[k], ref[k], equal_nan=True), k
+    p = nb().Params(n_ind=n_ind, n_sites=n_sites, **kw)
+    with nb().NgsDistB200(p) as g:
+        with pytest.raises(nb().NgsDistError):
+            g.push_packed_genotypes(bed, [0, 3, 1, 2])                      # 3 is not a genotype code
+        with pytest.raises(nb().NgsDistError):
+            g.push_packed_genotypes(np.zeros((n_sites, (n_ind + 3) // 4 - 1 or 1), np.uint8) if n_ind > 4 else bed, None if n_ind > 4 else [0, -2, 1, 2])
