@@ -330,6 +330,7 @@ int main(int argc, char **argv) {
     fprintf(stderr, "==> Using faster algorithm (assuming independence of genotypes)!\n");
   }
   // input kind (ngsDist.cpp:73-95)
+  bool in_bed = false;
   if (strcmp(p.in_geno, "-") == 0) {
     if (p.verbose >= 1) fprintf(stderr, "==> Reading from STDIN (BINARY)\n");
     p.in_bin = true;
@@ -337,7 +338,15 @@ int main(int argc, char **argv) {
     struct stat st;
     if (stat(p.in_geno, &st) != 0) die("main", "cannot check GENO file size!");
     const char *dot = strrchr(p.in_geno, '.');
-    if (dot && strcmp(dot, ".gz") == 0) {
+    if (dot && strcmp(dot, ".bed") == 0) {
+      // Extension: a variant-major PLINK .bed holds the called genotypes at 2 bits per individual-site
+      // and goes to the device as it is (ngsd_push_packed_genotypes); the reference would take it for a binary
+      // likelihood file and stop at the size check below.
+      if (p.verbose >= 1) fprintf(stderr, "==> PLINK .bed input file (2-bit genotypes)\n");
+      if (p.in_probs) die("main", "a .bed file holds genotypes, not probabilities (--probs)!");
+      in_bed = true;
+      if ((uint64_t) st.st_size != 3 + p.n_sites * ((p.n_ind + 3) / 4)) die("main", "invalid/corrupt genotype input file!");
+    } else if (dot && strcmp(dot, ".gz") == 0) {
       if (p.verbose >= 1) fprintf(stderr, "==> GZIP input file (never BINARY)\n");
       p.in_bin = false;
     } else {
@@ -371,6 +380,31 @@ int main(int argc, char **argv) {
   // A reader thread fills one of two pinned chunk buffers (file read / inflate, text parsing on --n_threads threads)
   // while the main thread pushes the other one through the front end: disk, parser, PCIe and GPU overlap.
   if (p.verbose >= 1) fprintf(stderr, "==> Reading genotype data\n");
+  if (in_bed) {
+    const int fd = open(p.in_geno, O_RDONLY);
+    unsigned char magic[3] = {0, 0, 0};
+    if (fd < 0 || read(fd, magic, 3) != 3) die("read_geno", "cannot open GENO file!");
+    if (magic[0] != 0x6c || magic[1] != 0x1b) die("read_geno", "wrong GENO file format. Not a PLINK .bed file!");
+    if (magic[2] != 0x01) die("read_geno", "wrong GENO file format. Only variant-major .bed files are supported!");
+    const uint64_t stride = (p.n_ind + 3) / 4;
+    uint64_t bchunk = std::max<uint64_t>(64, ((uint64_t) 64 << 20) / stride / 64 * 64);
+    if (const char *e = getenv("NGSD_CLI_CHUNK")) bchunk = std::max<uint64_t>(64, (uint64_t) atol(e) / 64 * 64);
+    unsigned char *buf = (unsigned char *) ngsd_host_alloc(std::min(bchunk, (p.n_sites + 63) / 64 * 64) * stride);
+    if (!buf) die("main", "cannot allocate pinned host buffer");
+    static const int8_t bed_codes[4] = {0, -1, 1, 2};   // fields: 00 homozygous A1, 01 missing, 10 heterozygous, 11 homozygous A2
+    for (uint64_t s0 = 0; s0 < p.n_sites; s0 += bchunk) {
+      const uint64_t n = std::min(bchunk, p.n_sites - s0);
+      for (uint64_t got = 0; got < n * stride;) {
+        const ssize_t r = read(fd, buf + got, n * stride - got);
+        if (r <= 0) die("read_geno", "GENO file at premature EOF. Check GENO file and number of sites!");
+        got += (uint64_t) r;
+      }
+      if (ngsd_push_packed_genotypes(ctx, buf, stride, bed_codes, s0, n)) die("read_geno", ngsd_last_error(ctx));
+    }
+    close(fd);
+    ngsd_host_free(buf);
+  }
+  if (!in_bed) {
   gzFile fh = open_gz(p.in_geno, p.in_bin ? "rb" : "r");
   if (!fh) die("read_geno", "cannot open GENO file!");
   const uint64_t per_site = p.n_ind * 3;
@@ -526,6 +560,7 @@ int main(int argc, char **argv) {
   gzclose(fh);
   for (auto &sl : slots)
     if (sl.raw) ngsd_host_free(sl.raw);
+  }   // !in_bed
   if (ngsd_frontend(ctx)) die("read_geno", ngsd_last_error(ctx));
   stamp("input read + front end");
 

@@ -218,3 +218,43 @@ def test_cli_c1_reference_test_script_matrix(tmp_path):
             worst = max(worst, float(d))
             assert d <= 1e-9 * max(1.0, float(np.nanmax(np.abs(y)))) + 1.01e-10, (name, d)   # + one unit of the 10th printed decimal
     print("C1 test.sh matrix: 18 runs, worst |difference| of printed values %.3g" % worst)
+
+
+@pytest.mark.gpu
+def test_cli_plink_bed_input_matches_genotype_text(tmp_path):
+    """Extension: a variant-major PLINK .bed (2-bit genotypes) gives byte for byte the .dist of the same
+    genotypes as {-1,0,1,2} text -- which the reference binary reads too, so the chain bed -> text -> reference is pinned."""
+    import gzip
+    from ngsdist_b200 import pack_genotypes
+    rng = np.random.RandomState(8)
+    n_ind, n_sites = 23, 300
+    geno = rng.randint(-1, 3, size=(n_sites, n_ind)).astype(np.int8)
+    txt = str(tmp_path / "g.geno.gz")
+    with gzip.open(txt, "wt") as fh:
+        for s in range(n_sites):
+            fh.write("\t".join(str(g) for g in geno[s]) + "\n")
+    bed = str(tmp_path / "g.bed")
+    with open(bed, "wb") as fh:
+        fh.write(bytes([0x6c, 0x1b, 0x01]))
+        fh.write(pack_genotypes(geno, field_of_code=[1, 0, 2, 3]).tobytes())   # -1 -> 01, 0 -> 00, 1 -> 10, 2 -> 11
+    flags = ["--n_ind", str(n_ind), "--n_sites", str(n_sites), "--verbose", "0", "--pairwise_del", "--evol_model", "0",
+             "--n_boot_rep", "3", "--boot_block_size", "20", "--seed", "4"]
+    texts = []
+    for path, env in ((txt, None), (bed, None), (bed, dict(os.environ, NGSD_CLI_CHUNK="64"))):
+        out = str(tmp_path / ("o%d.dist" % len(texts)))
+        r = run_cli(["--geno", path, "--out", out] + flags, env=env)
+        assert r.returncode == 0, r.stderr
+        texts.append(open(out).read())
+    assert texts[0] == texts[1] == texts[2]
+    if oracle.have_ref():
+        _, ref_text = oracle.run_reference(None, flags[6:], geno_path=txt, n_ind=n_ind, n_sites=n_sites)
+        assert texts[0] == ref_text
+    # a truncated file and sample-major files are refused
+    bad = str(tmp_path / "bad.bed")
+    with open(bad, "wb") as fh:
+        fh.write(bytes([0x6c, 0x1b, 0x00]))
+        fh.write(pack_genotypes(geno, field_of_code=[1, 0, 2, 3]).tobytes())
+    r = run_cli(["--geno", bad, "--out", str(tmp_path / "x")] + flags)
+    assert r.returncode != 0 and "variant-major" in r.stderr
+    r = run_cli(["--geno", bed, "--out", str(tmp_path / "x"), "--n_ind", str(n_ind), "--n_sites", str(n_sites + 1), "--verbose", "0"])
+    assert r.returncode != 0 and "invalid/corrupt genotype input file!" in r.stderr

@@ -3,3 +3,4 @@
 mkdir -p gpurun_out
 N_SITES=5000000 PDEL=0 python tools/bench_c4.py 2>&1 | tee gpurun_out/c4_full.log
 N_SITES=5000000 PDEL=1 python tools/bench_c4.py 2>&1 | tee -a gpurun_out/c4_full.log
+PACKED=1 N_SITES=5000000 PDEL=0 python tools/bench_c4.py 2>&1 | tail -1 | tee -a gpurun_out/c4_full.log
