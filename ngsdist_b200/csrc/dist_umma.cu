@@ -1,10 +1,10 @@
 // K2c' dist_umma: the called-genotype contraction of dist_imma.cu on the 5th-generation tensor cores:
-// tcgen05.mma kind::i8 (SASS UTCIMMA), operands in shared memory, int32 accumulators in TMEM.
+// tcgen05.mma kind::i8 (SASS UTCIMMA), A operand and int32 accumulators in tensor memory, B operand in shared memory.
 //
 // Same arithmetic as dist_imma.cu (A_i[s][k] = w_s [c_i(s) == k], B_j[s][k] = S f(k, c_j(s)), K = 4 bytes per site,
-// exact int32 accumulation) and the same (K-split, tile) units, partial buffers and epilogue.  UMMA runs the int8 GEMM
-// 3.7x faster than mma.sync (tools/probe_utcimma.cu: 2.1e15 vs 5.7e14 MAC/s) but reads its operands from shared
-// memory, so the 16x expansion of the 2-bit codes has to go through the LSU: a CTA is a four-role pipeline
+// exact int32 accumulation), the same K splits, partial buffers and epilogue.  UMMA runs the int8 GEMM 3.7x faster than
+// mma.sync (tools/probe_utcimma.cu: 2.1e15 vs 5.7e14 MAC/s) but cannot take operands from registers, so the 16x
+// expansion of the 2-bit codes is written out every stage.  A CTA is a four-role pipeline connected by mbarrier rings:
 //
 //   warp 0      producer   cp.async.bulk of the packed codes (3 x 2 KiB + 64 weight bytes per 64-site stage)
 //   warps 2-17  expanders  codes -> int8 operands.  B (64 KiB per stage) goes to shared memory in the K-major, no-swizzle
@@ -17,10 +17,10 @@
 //                          (TMEM: 256 accumulator columns + 3 x 64 A columns; the expanders run up to 3 stages ahead
 //                          while the accumulator drains)
 //
-// all connected by mbarrier rings.  Shared-memory bandwidth (expansion stores + UMMA operand reads), not the tensor pipe,
-// is the limit; the expansion itself is ~12 integer ops and one 16-byte store per 16 operand bytes.  To spend less of it
-// per MAC a unit is a PAIR of output tiles of one row block (api.cu: d_pairs): they share the A operand, so one stage
-// expands 3 x 128 rows for 128 x 256 pairs instead of 2 x 128 rows for 128 x 128 (the odd tile of a row runs alone, N = 128).
+// A unit is a PAIR of output tiles of one row block (api.cu: d_pairs): they share the A operand, so one stage expands
+// 3 x 128 rows for 128 x 256 pairs instead of 2 x 128 rows for 128 x 128 (the odd tile of a row runs alone, N = 128).
+// The expanders' instruction stream is the limit (ncu: 85 % of their samples in arithmetic; tensor pipe 66 %, LSU
+// wavefronts 67 %, integer ALU 62 %); the expansion is ~9 integer ops and one 16-byte store per 16 operand bytes.
 #include <math.h>
 #include <stdlib.h>
 
@@ -196,7 +196,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
   uint64_t *acc_full = exp_empty + kExp, *acc_empty = acc_full + 2;
   uint32_t *raw_meta = reinterpret_cast<uint32_t *>(bars + kNBar);    // [kRaw][2] = {unit, flags}
   uint32_t *exp_meta = raw_meta + 2 * kRaw;                           // [kExp][2]
-  uint32_t *acc_meta = exp_meta + 2 * kExp;                           // [2][2]
+  uint32_t *acc_meta = exp_meta + 2 * kExp;                           // {unit, flags} of the finished accumulator (+ 2 spare words)
   uint32_t *lut = acc_meta + 4;                                       // [4]
   uint32_t *tmem_slot = lut + 4;
   uint32_t *lut16 = tmem_slot + 4;                                    // [16] presence nibble -> 0x01 bytes (count pass)
