@@ -1070,9 +1070,16 @@ int ngsd_set_tile_shard(ngsd_ctx *ctx, uint32_t rank, uint32_t world) {
   if (world == 0 || rank >= world) { ngsd_set_error(ctx, "invalid tile shard %u of %u", rank, world); return NGSD_ERR_ARG; }
   if (!ctx->cfg.indep_geno && world > 1) { ngsd_set_error(ctx, "tile sharding is not available on the per pair-site EM path"); return NGSD_ERR_ARG; }
   NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
+  // the unit of ownership is a PAIR of neighbouring tiles of one row block (the odd tile of a row alone): dist_umma.cu
+  // contracts such pairs with one shared A operand, so a shard keeps them together
   std::vector<ngsd_tile> all = make_tiles((uint32_t) ctx->RB), mine;
-  for (size_t t = 0; t < all.size(); t++)
-    if (t % world == rank) mine.push_back(all[t]);
+  uint32_t unit = 0;
+  for (size_t t = 0; t < all.size(); unit++) {
+    const size_t len = (t + 1 < all.size() && all[t + 1].ti == all[t].ti) ? 2 : 1;
+    if (unit % world == rank)
+      for (size_t k = 0; k < len; k++) mine.push_back(all[t + k]);
+    t += len;
+  }
   NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->n_tiles = (uint32_t) mine.size();
   ctx->n_diag_tiles = 0;

@@ -64,8 +64,15 @@ def tile_list(n_ind, band=12):
 def tile_owner_mask(n_ind, rank, world):
     """Boolean n x n mask (upper and lower triangle, no diagonal) of the entries `rank` owns under ngsd_set_tile_shard."""
     m = np.zeros((n_ind, n_ind), dtype=bool)
-    for k, (ti, tj) in enumerate(tile_list(n_ind)):
-        if k % world != rank:
+    tiles = tile_list(n_ind)
+    owner, unit, t = [], 0, 0
+    while t < len(tiles):                       # ownership goes by pairs of neighbouring tiles of one row block
+        ln = 2 if t + 1 < len(tiles) and tiles[t + 1][0] == tiles[t][0] else 1
+        owner += [unit % world] * ln
+        unit += 1
+        t += ln
+    for k, (ti, tj) in enumerate(tiles):
+        if owner[k] != rank:
             continue
         i0, i1, j0, j1 = ti * 128, min((ti + 1) * 128, n_ind), tj * 128, min((tj + 1) * 128, n_ind)
         blk = np.zeros((i1 - i0, j1 - j0), dtype=bool)
