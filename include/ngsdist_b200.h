@@ -138,7 +138,7 @@ NGSD_API int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_
  * Bootstrap replicates shard by simply calling ngsd_distances for different replicates on different contexts.
  *
  * Output-triangle tiles: after ngsd_set_tile_shard(rank, world) the context computes only the 128 x 128 upper-triangle
- * tiles dealt to `rank` (round-robin over pairs of neighbouring tiles of one row block); every entry it does not own is written as 0 in out / num /
+ * tiles dealt to `rank` (pairs of neighbouring tiles of one row block, each to the rank holding the fewest so far); every entry it does not own is written as 0 in out / num /
  * cnt, so an element-wise SUM over the ranks assembles the full matrices exactly (x + 0 == x).  Not available for the
  * per pair-site EM path.
  *

@@ -1072,11 +1072,14 @@ int ngsd_set_tile_shard(ngsd_ctx *ctx, uint32_t rank, uint32_t world) {
   NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
   // the unit of ownership is a PAIR of neighbouring tiles of one row block (the odd tile of a row alone): dist_umma.cu
   // contracts such pairs with one shared A operand, so a shard keeps them together
+  // (dealt in list order, each unit to the rank holding the fewest tiles so far, lowest rank first: tile counts differ by <= 2)
   std::vector<ngsd_tile> all = make_tiles((uint32_t) ctx->RB), mine;
-  uint32_t unit = 0;
-  for (size_t t = 0; t < all.size(); unit++) {
+  std::vector<uint32_t> held(world, 0);
+  for (size_t t = 0; t < all.size();) {
     const size_t len = (t + 1 < all.size() && all[t + 1].ti == all[t].ti) ? 2 : 1;
-    if (unit % world == rank)
+    const uint32_t to = (uint32_t) (std::min_element(held.begin(), held.end()) - held.begin());
+    held[to] += (uint32_t) len;
+    if (to == rank)
       for (size_t k = 0; k < len; k++) mine.push_back(all[t + k]);
     t += len;
   }

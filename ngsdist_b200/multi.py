@@ -65,11 +65,12 @@ def tile_owner_mask(n_ind, rank, world):
     """Boolean n x n mask (upper and lower triangle, no diagonal) of the entries `rank` owns under ngsd_set_tile_shard."""
     m = np.zeros((n_ind, n_ind), dtype=bool)
     tiles = tile_list(n_ind)
-    owner, unit, t = [], 0, 0
-    while t < len(tiles):                       # ownership goes by pairs of neighbouring tiles of one row block
+    owner, held, t = [], [0] * world, 0
+    while t < len(tiles):                       # ownership goes by pairs of neighbouring tiles of one row block,
         ln = 2 if t + 1 < len(tiles) and tiles[t + 1][0] == tiles[t][0] else 1
-        owner += [unit % world] * ln
-        unit += 1
+        to = held.index(min(held))              # each to the rank holding the fewest tiles so far (ngsd_set_tile_shard)
+        held[to] += ln
+        owner += [to] * ln
         t += ln
     for k, (ti, tj) in enumerate(tiles):
         if owner[k] != rank:

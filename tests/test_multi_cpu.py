@@ -126,3 +126,39 @@ def test_bootstream_matches_oracle_taus():
         sm = t.boot_map(10, 10)
         want = np.bincount((sm[::10] // 10).astype(int), minlength=10)
         assert np.array_equal(c, want)
+
+
+def test_tile_shards_keep_row_block_pairs_together_and_balanced():
+    """Ownership goes by pairs of neighbouring tiles of one row block (what dist_umma.cu contracts with one shared A):
+    a rank's tiles split into such pairs again, and the ranks' tile counts differ by at most 2 x ceil-rounding."""
+    for n, world in [(5000, 8), (1300, 3), (700, 2), (128, 4)]:
+        tiles = multi.tile_list(n)
+        owner = np.full(len(tiles), -1)
+        for r in range(world):
+            m = multi.tile_owner_mask(n, r, world)
+            for k, (ti, tj) in enumerate(tiles):
+                i, j = ti * 128, tj * 128 + (1 if ti == tj else 0)
+                if j < n and m[i, j]:
+                    owner[k] = r
+        known = owner >= 0                                  # a 1-individual diagonal tile owns no off-diagonal entry
+        k = 0
+        while k < len(tiles):
+            ln = 2 if k + 1 < len(tiles) and tiles[k + 1][0] == tiles[k][0] else 1
+            if ln == 2 and known[k] and known[k + 1]:
+                assert owner[k] == owner[k + 1]
+            k += ln
+        cnt = np.bincount(owner[known], minlength=world)
+        assert cnt.max() - cnt.min() <= 2 + (len(tiles) % 2), (n, world, cnt)
+
+
+def test_pack_genotypes_layout():
+    """pack_genotypes: individual i of a site in bits 2 (i % 4) of byte i / 4; default fields {0,1,2,-1} -> {0,1,2,3}."""
+    from ngsdist_b200 import pack_genotypes, PLINK_BED_CODES
+    g = np.array([[0, 1, 2, -1, 2], [-1, -1, 0, 0, 1]], dtype=np.int8)
+    p = pack_genotypes(g)
+    assert p.shape == (2, 2) and p.dtype == np.uint8
+    assert p[0, 0] == (0 | 1 << 2 | 2 << 4 | 3 << 6) and p[0, 1] == 2
+    assert p[1, 0] == (3 | 3 << 2) and p[1, 1] == 1
+    bed = pack_genotypes(g, field_of_code=[1, 0, 2, 3])     # PLINK: 00 hom A1, 01 missing, 10 het, 11 hom A2
+    fields = [(bed[0, i // 4] >> (2 * (i % 4))) & 3 for i in range(5)]
+    assert [PLINK_BED_CODES[f] for f in fields] == list(g[0])
