@@ -38,6 +38,11 @@ constexpr int kRawBytes = 3 * kCodeBytes + 128;   // A codes, B codes of the two
 constexpr int kOpBytes = 16 * 16 * 128;           // expanded A operand: [16 site quads][16 row groups][8 rows][16 B] = 32 KiB
 constexpr int kExpBytes = 2 * kOpBytes;           // B = [16 site quads][32 row groups][8 rows][16 B] (count pass: one byte per site, a quarter of it)
 constexpr uint32_t kAccCols = 256, kACols = 64;   // TMEM columns: accumulator, one stage of A
+constexpr int kCntGroup = 4;                      // count pass: word-list entries (64 sites, one byte each) per stage
+constexpr int kCntEntry = 3 * kMaskBytes;         // count pass raw stage: kCntGroup x {A, B, B' masks} then kCntGroup x 64 weights
+constexpr int kCntRawBytes = kCntGroup * (kCntEntry + 64);
+constexpr int kCntRaw = 2;                        // ... and two of those stages fill the same ring bytes
+static_assert(kCntRaw * kCntRawBytes <= kRaw * kRawBytes && kCntRawBytes % 128 == 0, "count-pass raw ring must fit the code ring");
 constexpr int kNBar = 2 * kRaw + 2 * kExp + 4;
 constexpr size_t kSmemBytes = (size_t) kRaw * kRawBytes + (size_t) kExp * kExpBytes + kNBar * 8 + (kRaw + kExp + 2) * 8 + 16 + 16 + 1024;
 
@@ -127,7 +132,7 @@ struct UmmaArgs {
   uint32_t lut[4];
 };
 
-enum : uint32_t { kFirst = 1u, kLast = 2u, kPair = 4u, kExit = 8u, kUnitW = 16u };
+enum : uint32_t { kFirst = 1u, kLast = 2u, kPair = 4u, kExit = 8u, kUnitW = 16u, kEntriesShift = 8u };   // count pass: entries of the stage in bits 8..10
 
 // Expansion of one 64-site stage by thread (row r, byte q0 of each of the 4 code words): A row -> tensor memory, B rows ->
 // shared memory.  The K order inside a 16-byte unit is free as long as both operands use it: PLANE-major here (word k =
@@ -180,14 +185,16 @@ __device__ __forceinline__ void expand_codes(const uint32_t *cA, const uint32_t 
 }
 
 // COUNT = true: the same pipeline computes the shared-site counts of --pairwise_del, cnt(i,j) = sum_s w_s m_i(s) m_j(s), as an
-// int8 GEMM with ONE byte per site (A' = w_s m_i(s), B' = m_j(s) from the presence masks; 2 MMAs per 64-site stage) and
-// writes them as the second tile of the unit's slot.
+// int8 GEMM with ONE byte per site (A' = w_s m_i(s), B' = m_j(s) from the presence masks) and writes them as the second
+// tile of the unit's slot.  A stage then holds up to kCntGroup = 4 word-list entries (256 sites), so that it is the same
+// 256 K bytes, 8 MMAs and operand layout as a stage of the sum pass instead of a quarter-size stage with full-size overheads.
 template <bool COUNT>
 __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
-  constexpr int kIn = COUNT ? kMaskBytes : kCodeBytes;               // packed bytes of one 128-row operand of one stage
-  constexpr int kOffW = 3 * kIn;
+  constexpr int kOffW = 3 * kCodeBytes;                              // sum pass: weights behind the three code tiles
+  constexpr int kRawN = COUNT ? kCntRaw : kRaw;                      // raw ring: stages and bytes per stage
+  constexpr int kRawStage = COUNT ? kCntRawBytes : kRawBytes;
   constexpr int kBChunk = 4096;                       // B: bytes between 16-byte K chunks (32 row groups x 128 B)
-  constexpr int kMmas = COUNT ? 2 : 8;
+  constexpr int kMmas = 8;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char *raw = smem;                                         // kRaw x kRawBytes
   unsigned char *exps = smem + (size_t) kRaw * kRawBytes;            // kExp x kExpBytes (16-byte aligned: kRawBytes % 16 == 0)
@@ -239,6 +246,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
         const uint32_t *Ab = a.codes + (uint64_t) tl.ti * a.NW * 512;
         const uint32_t *Bb = a.codes + (uint64_t) tl.tj * a.NW * 512;
         const uint32_t *B1b = a.codes + (uint64_t) tj1 * a.NW * 512;
+        if (COUNT) {
+          for (uint32_t c = c0; c < c1; c += kCntGroup) {
+            const uint32_t ne = min((uint32_t) kCntGroup, c1 - c);
+            uint32_t words[kCntGroup], layers[kCntGroup], unitw = 1u;
+            for (uint32_t e = 0; e < ne; e++) { words[e] = a.word_ids[c + e]; layers[e] = a.word_layer[c + e]; unitw &= layers[e] >> 31; }
+            mbar_wait(&raw_empty[rs], rph ^ 1);
+            raw_meta[rs * 2] = u;
+            raw_meta[rs * 2 + 1] = (c == c0 ? kFirst : 0u) | (c + kCntGroup >= c1 ? kLast : 0u) | (paired ? kPair : 0u) | (unitw ? kUnitW : 0u) | (ne << kEntriesShift);
+            mbar_expect_tx(&raw_full[rs], ne * ((paired ? 3 : 2) * kMaskBytes + 64));
+            unsigned char *dst = raw + (size_t) rs * kRawStage;
+            for (uint32_t e = 0; e < ne; e++) {
+              const uint64_t word = words[e];
+              unsigned char *de = dst + e * kCntEntry;
+              bulk_g2s(de, a.mask + ((uint64_t) tl.ti * a.NW + word) * 128, kMaskBytes, &raw_full[rs]);
+              bulk_g2s(de + kMaskBytes, a.mask + ((uint64_t) tl.tj * a.NW + word) * 128, kMaskBytes, &raw_full[rs]);
+              if (paired) bulk_g2s(de + 2 * kMaskBytes, a.mask + ((uint64_t) tj1 * a.NW + word) * 128, kMaskBytes, &raw_full[rs]);
+              bulk_g2s(dst + kCntGroup * kCntEntry + e * 64, a.wsite + ((uint64_t) (layers[e] & 0x7FFFFFFFu) * a.NW + word) * 64, 64, &raw_full[rs]);
+            }
+            if (++rs == kRawN) { rs = 0; rph ^= 1; }
+          }
+          continue;
+        }
         uint32_t nword = a.word_ids[c0], nlayer = a.word_layer[c0];
         for (uint32_t c = c0; c < c1; c++) {
           const uint64_t word = nword;
@@ -248,19 +277,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
           mbar_wait(&raw_empty[rs], rph ^ 1);
           raw_meta[rs * 2] = u;
           raw_meta[rs * 2 + 1] = (c == c0 ? kFirst : 0u) | (c + 1 == c1 ? kLast : 0u) | (paired ? kPair : 0u) | (unitw ? kUnitW : 0u);
-          mbar_expect_tx(&raw_full[rs], (paired ? 3 : 2) * kIn + 64);
-          unsigned char *dst = raw + (size_t) rs * kRawBytes;
-          if (COUNT) {
-            bulk_g2s(dst, a.mask + ((uint64_t) tl.ti * a.NW + word) * 128, kMaskBytes, &raw_full[rs]);
-            bulk_g2s(dst + kMaskBytes, a.mask + ((uint64_t) tl.tj * a.NW + word) * 128, kMaskBytes, &raw_full[rs]);
-            if (paired) bulk_g2s(dst + 2 * kMaskBytes, a.mask + ((uint64_t) tj1 * a.NW + word) * 128, kMaskBytes, &raw_full[rs]);
-          } else {
-            bulk_g2s(dst, Ab + word * 512, kCodeBytes, &raw_full[rs]);
-            bulk_g2s(dst + kCodeBytes, Bb + word * 512, kCodeBytes, &raw_full[rs]);
-            if (paired) bulk_g2s(dst + 2 * kCodeBytes, B1b + word * 512, kCodeBytes, &raw_full[rs]);
-          }
+          mbar_expect_tx(&raw_full[rs], (paired ? 3 : 2) * kCodeBytes + 64);
+          unsigned char *dst = raw + (size_t) rs * kRawStage;
+          bulk_g2s(dst, Ab + word * 512, kCodeBytes, &raw_full[rs]);
+          bulk_g2s(dst + kCodeBytes, Bb + word * 512, kCodeBytes, &raw_full[rs]);
+          if (paired) bulk_g2s(dst + 2 * kCodeBytes, B1b + word * 512, kCodeBytes, &raw_full[rs]);
           bulk_g2s(dst + kOffW, wsrc, 64, &raw_full[rs]);
-          if (++rs == kRaw) { rs = 0; rph ^= 1; }
+          if (++rs == kRawN) { rs = 0; rph ^= 1; }
         }
       }
       mbar_wait_sleep(&raw_empty[rs], rph ^ 1);
@@ -293,10 +316,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
         const uint32_t sb = smem_u32(exps + (size_t) es * kExpBytes);
         const uint32_t ta = tmem + kAccCols + (uint32_t) es * kACols;
         const uint32_t idesc = (fl & kPair) ? idesc2 : idesc1;
+        const int n_mma = COUNT ? 2 * (int) ((fl >> kEntriesShift) & 7u) : kMmas;   // count pass: 2 per word-list entry of the stage
 #pragma unroll
         for (int j = 0; j < kMmas; j++) {                           // K 32 per instruction: 8 TMEM columns of A, two 16-byte chunks of B (4 KiB apart)
-          const uint64_t db = umma_desc(sb + j * 2 * kBChunk, kBChunk, 128);
-          umma_i8_ts(tmem, ta + 8u * j, db, idesc, ((fl & kFirst) && j == 0) ? 0u : 1u);
+          if (j < n_mma) {
+            const uint64_t db = umma_desc(sb + j * 2 * kBChunk, kBChunk, 128);
+            umma_i8_ts(tmem, ta + 8u * j, db, idesc, ((fl & kFirst) && j == 0) ? 0u : 1u);
+          }
         }
         umma_commit(&exp_empty[es]);                                 // stage (B in shared memory, A in TMEM) reusable once these MMAs have read it
         if (fl & kLast) {
@@ -334,38 +360,42 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
         if (lane == 0) mbar_arrive(&exp_full[es]);
         break;
       }
-      const unsigned char *rawS = raw + (size_t) rs * kRawBytes;
+      const unsigned char *rawS = raw + (size_t) rs * kRawStage;
       if (COUNT) {
-        // one byte per site: thread (r, q0) expands the 16 presence bits 16 q0 .. 16 q0 + 15 of its row of both operands
-        // into one 16-byte unit each (chunk q0 of the [4][16][8][16 B] operand); A bytes carry the site weights
-        const uint32_t ma = reinterpret_cast<const uint32_t *>(rawS)[r * 2 + (q0 >> 1)] >> (16 * (q0 & 1));
-        const uint32_t mb = reinterpret_cast<const uint32_t *>(rawS + kMaskBytes)[r * 2 + (q0 >> 1)] >> (16 * (q0 & 1));
-        const uint32_t mb1 = reinterpret_cast<const uint32_t *>(rawS + 2 * kMaskBytes)[r * 2 + (q0 >> 1)] >> (16 * (q0 & 1));
-        const uint4 ww = *reinterpret_cast<const uint4 *>(rawS + kOffW + 16 * q0);
-        uint4 va, vb;
-        va.x = lut16[ma & 15u];
-        va.y = lut16[(ma >> 4) & 15u];
-        va.z = lut16[(ma >> 8) & 15u];
-        va.w = lut16[(ma >> 12) & 15u];
-        if (!(fl & kUnitW)) {
-          va.x = (va.x * 0xFFu) & ww.x;
-          va.y = (va.y * 0xFFu) & ww.y;
-          va.z = (va.z * 0xFFu) & ww.z;
-          va.w = (va.w * 0xFFu) & ww.w;
-        }
-        vb.x = lut16[mb & 15u];
-        vb.y = lut16[(mb >> 4) & 15u];
-        vb.z = lut16[(mb >> 8) & 15u];
-        vb.w = lut16[(mb >> 12) & 15u];
-        unsigned char *eB = exps + (size_t) es * kExpBytes + unit_off + (uint32_t) q0 * kBChunk;
-        tmem_st4(ta_lane + (uint32_t) es * kACols + 4u * q0, va);
-        *reinterpret_cast<uint4 *>(eB) = vb;
-        if (fl & kPair) {
-          vb.x = lut16[mb1 & 15u];
-          vb.y = lut16[(mb1 >> 4) & 15u];
-          vb.z = lut16[(mb1 >> 8) & 15u];
-          vb.w = lut16[(mb1 >> 12) & 15u];
-          *reinterpret_cast<uint4 *>(eB + 2048) = vb;
+        // one byte per site: for each word-list entry e of the stage, thread (r, q0) expands the 16 presence bits
+        // 16 q0 .. 16 q0 + 15 of its row of each operand into one 16-byte unit (K chunk 4 e + q0); A bytes carry the site weights
+        const uint32_t ne = (fl >> kEntriesShift) & 7u;
+        for (uint32_t e = 0; e < ne; e++) {
+          const unsigned char *re = rawS + e * kCntEntry;
+          const uint32_t ma = reinterpret_cast<const uint32_t *>(re)[r * 2 + (q0 >> 1)] >> (16 * (q0 & 1));
+          const uint32_t mb = reinterpret_cast<const uint32_t *>(re + kMaskBytes)[r * 2 + (q0 >> 1)] >> (16 * (q0 & 1));
+          uint4 va, vb;
+          va.x = lut16[ma & 15u];
+          va.y = lut16[(ma >> 4) & 15u];
+          va.z = lut16[(ma >> 8) & 15u];
+          va.w = lut16[(ma >> 12) & 15u];
+          if (!(fl & kUnitW)) {
+            const uint4 ww = *reinterpret_cast<const uint4 *>(rawS + kCntGroup * kCntEntry + e * 64 + 16 * q0);
+            va.x = (va.x * 0xFFu) & ww.x;
+            va.y = (va.y * 0xFFu) & ww.y;
+            va.z = (va.z * 0xFFu) & ww.z;
+            va.w = (va.w * 0xFFu) & ww.w;
+          }
+          vb.x = lut16[mb & 15u];
+          vb.y = lut16[(mb >> 4) & 15u];
+          vb.z = lut16[(mb >> 8) & 15u];
+          vb.w = lut16[(mb >> 12) & 15u];
+          unsigned char *eB = exps + (size_t) es * kExpBytes + unit_off + (4u * e + (uint32_t) q0) * kBChunk;
+          tmem_st4(ta_lane + (uint32_t) es * kACols + 16u * e + 4u * q0, va);
+          *reinterpret_cast<uint4 *>(eB) = vb;
+          if (fl & kPair) {
+            const uint32_t mb1 = reinterpret_cast<const uint32_t *>(re + 2 * kMaskBytes)[r * 2 + (q0 >> 1)] >> (16 * (q0 & 1));
+            vb.x = lut16[mb1 & 15u];
+            vb.y = lut16[(mb1 >> 4) & 15u];
+            vb.z = lut16[(mb1 >> 8) & 15u];
+            vb.w = lut16[(mb1 >> 12) & 15u];
+            *reinterpret_cast<uint4 *>(eB + 2048) = vb;
+          }
         }
         asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -373,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
         if (lead) { exp_meta[es * 2] = u; exp_meta[es * 2 + 1] = fl; }
         __syncwarp();
         if (lane == 0) { mbar_arrive(&exp_full[es]); mbar_arrive(&raw_empty[rs]); }
-        if (++rs == kRaw) { rs = 0; rph ^= 1; }
+        if (++rs == kRawN) { rs = 0; rph ^= 1; }
         if (++es == kExp) { es = 0; eph ^= 1; }
         continue;
       }
@@ -393,7 +423,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
       if (lead) { exp_meta[es * 2] = u; exp_meta[es * 2 + 1] = fl; }
       __syncwarp();
       if (lane == 0) { mbar_arrive(&exp_full[es]); mbar_arrive(&raw_empty[rs]); }
-      if (++rs == kRaw) { rs = 0; rph ^= 1; }
+      if (++rs == kRawN) { rs = 0; rph ^= 1; }
       if (++es == kExp) { es = 0; eph ^= 1; }
     }
   } else {
