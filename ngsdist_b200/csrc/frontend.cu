@@ -412,6 +412,50 @@ __global__ void __launch_bounds__(512, 2) k_frontend_codes(FrontCfg c, const dou
   }
 }
 
+// Genotype-code input on the integer path (read_data.cpp:88-95: codes {-1,0,1,2}, anything above 2 is an error): the same
+// block shape and output as k_frontend_codes without any of its floating-point state, so that it is a ~20-register
+// kernel that can share an SM with a persistent contraction CTA (a packed push overlapping another context's contraction).
+__global__ void __launch_bounds__(512, 4) k_codes_from_int8(const int8_t *__restrict__ codes, uint64_t n_ind, uint64_t site0, uint64_t n, uint64_t NW,
+                                                            uint32_t *__restrict__ codes_out, uint64_t *__restrict__ mask, int *__restrict__ err) {
+  __shared__ unsigned cod[16][32];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const uint64_t i = (uint64_t) blockIdx.x * 32 + tx;
+  const uint64_t word = site0 / 64 + blockIdx.y;
+  const uint64_t s_local0 = (uint64_t) blockIdx.y * 64 + ty * 4;
+  unsigned cbits = 0xFF;                  // 2 bits per site; 3 = missing / padding
+  int bad = 0;
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint64_t sl = s_local0 + q;
+    if (i < n_ind && sl < n) {
+      const int g = (int) codes[sl * n_ind + i];
+      unsigned cg = g < 0 ? 3u : (unsigned) g;                       // -1 = missing
+      if (g > 2) { bad = 2; cg = 3u; }
+      cbits = (cbits & ~(3u << (2 * q))) | (cg << (2 * q));
+    }
+  }
+  if (bad) atomicOr(err, bad);
+  unsigned pres = ~(cbits & (cbits >> 1)) & 0x55u;                   // presence nibble of this thread's 4 sites
+  pres = (pres | (pres >> 1)) & 0x33u;
+  pres = (pres | (pres >> 2)) & 0x0Fu;
+  cod[ty][tx] = cbits | (pres << 8);
+  __syncthreads();
+  const uint64_t rb = i >> 7, r = i & 127;
+  if (ty < 4) {
+    const unsigned w = (cod[4 * ty][tx] & 0xFFu) | ((cod[4 * ty + 1][tx] & 0xFFu) << 8) | ((cod[4 * ty + 2][tx] & 0xFFu) << 16) |
+                       (cod[4 * ty + 3][tx] << 24);
+    codes_out[((rb * NW + word) * 4 + ty) * 128 + r] = w;
+  } else if (ty == 4) {
+    unsigned mlo = 0, mhi = 0;
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      mlo |= ((cod[k][tx] >> 8) & 0xFu) << (4 * k);
+      mhi |= ((cod[k + 8][tx] >> 8) & 0xFu) << (4 * k);
+    }
+    mask[(rb * NW + word) * 128 + r] = ((uint64_t) mhi << 32) | mlo;
+  }
+}
+
 // Inspection: packed A planes + mask -> [ind][site][3] / [ind][site]
 __global__ void k_unpack(const double *__restrict__ Apack, const uint32_t *__restrict__ codes, const uint64_t *__restrict__ mask,
                          uint64_t n_ind, uint64_t n_sites, uint64_t NC, uint64_t NW, int planes, double *__restrict__ P,
@@ -489,7 +533,9 @@ cudaError_t ngsd_launch_frontend(ngsd_ctx *ctx, const ngsd_frontend_args &a) {
   c.call_thresh = ctx->cfg.call_thresh;
   for (int k = 0; k < 9; k++) c.score[k] = ctx->cfg.score[k];
   dim3 grid((unsigned) (ctx->n_pad / 32), (unsigned) ((a.n + 63) / 64)), block(32, 16);
-  if (ctx->int_path)
+  if (ctx->int_path && a.codes)
+    k_codes_from_int8<<<grid, block, 0, ctx->stream>>>(a.codes, ctx->n_ind, a.site0, a.n, ctx->NW, ctx->codes, ctx->mask, ctx->d_err);
+  else if (ctx->int_path)
     k_frontend_codes<<<grid, block, 0, ctx->stream>>>(c, a.raw, a.codes, ctx->n_ind, a.site0, a.n, ctx->NW, ctx->codes, ctx->mask,
                                                       ctx->d_err);
   else if (c.call_geno)
