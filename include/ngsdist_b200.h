@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define NGSD_ABI_VERSION 1
+#define NGSD_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define NGSD_API __attribute__((visibility("default")))
@@ -41,8 +41,19 @@ typedef enum {
                               threshold!"                                (gen_func.cpp:887-888)   */
   NGSD_ERR_MODEL = -5,     /* evol_model 3..6 "not yet supported" / invalid (ngsDist.cpp:387-401) */
   NGSD_ERR_STATE = -6,     /* call order violated (e.g. distances before all sites were pushed)   */
-  NGSD_ERR_GENO = -7       /* "Genotypes must be coded as {-1,0,1,2} !"  (read_data.cpp:91-92)    */
+  NGSD_ERR_GENO = -7,      /* "Genotypes must be coded as {-1,0,1,2} !"  (read_data.cpp:91-92)    */
+  NGSD_ERR_COMM = -8       /* NCCL failure / communicator misuse (multi-GPU entry points)         */
 } ngsd_status;
+
+/* How a multi-GPU context (ngsd_cfg.n_gpus > 1) places the data set on its GPUs. */
+typedef enum {
+  NGSD_SHARD_AUTO = 0,        /* REPLICATED when the packed operands of all sites fit one GPU, else SITES            */
+  NGSD_SHARD_REPLICATED = 1,  /* every GPU ends up with all sites (site-sharded front end + NCCL all-gather of the packed
+                                 operands): bootstrap replicates (ngsd_distances_batch) and output-triangle tiles
+                                 (ngsd_distances) are dealt to the GPUs, no reduction on the data path                */
+  NGSD_SHARD_SITES = 2        /* GPU g holds a contiguous site range: partial sums, ONE ncclReduce of the upper triangle
+                                 of num (+ cnt under --pairwise_del), epilogue after the reduction                    */
+} ngsd_shard_mode;
 
 /* How raw values were read; selects the reader-side half of the front end (H2 in SURVEY §8a). */
 typedef enum {
@@ -72,6 +83,12 @@ typedef struct {
                                 them through the FP64 contraction like soft posteriors (A/B testing);
                                 bit 2 = contract every bootstrap replicate directly (weighted contraction) instead of
                                 reusing per-block partial sums (the bootstrap block cache)                          */
+  int32_t n_gpus;            /* 0 / 1: one GPU (`device`).  N > 1: the context drives devices device .. device+N-1 from one
+                                host thread per GPU inside the library (replaces the pthread pool of ngsDist.cpp:197-269
+                                at box level); every entry point below takes such a context unchanged                 */
+  int32_t shard;             /* ngsd_shard_mode (n_gpus > 1 only)                                                     */
+  uint64_t boot_block_size;  /* params.boot_block_size when bootstrap replicates will follow (0 / 1: none): site shards
+                                are aligned to whole blocks (ngsDist.cpp:416-437)                                     */
 } ngsd_cfg;
 
 typedef struct ngsd_ctx ngsd_ctx;
@@ -134,6 +151,15 @@ NGSD_API int ngsd_frontend(ngsd_ctx *ctx);
 NGSD_API int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_blocks, uint64_t block_size,
                    double *out, double *num_opt, uint64_t *cnt_opt);
 
+/* The bootstrap loop of main() in one call (ngsDist.cpp:217-238 for rep = 1 .. n_rep): block_counts[r][b] as for
+ * ngsd_distances, out[r] = the n_ind x n_ind matrix of replicate r (host).  With one GPU the replicates run back to back;
+ * a multi-GPU context (REPLICATED) or a communicator (ngsd_comm_attach) deals replicate r to GPU / rank r % N -- no
+ * data-path collective, every GPU writes its matrices to the host through its own PCIe link; with a communicator the
+ * matrices are gathered on rank 0 (NCCL send/recv) and `out` may be NULL on the other ranks.  SITES contexts run the
+ * replicates one after the other, each on all GPUs. */
+NGSD_API int ngsd_distances_batch(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_rep, uint64_t n_blocks, uint64_t block_size,
+                                  double *out);
+
 /* ---- multi-GPU support (one context per GPU / process) -------------------------------------------------
  * Bootstrap replicates shard by simply calling ngsd_distances for different replicates on different contexts.
  *
@@ -150,6 +176,34 @@ NGSD_API int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_
 NGSD_API int ngsd_set_tile_shard(ngsd_ctx *ctx, uint32_t rank, uint32_t world);
 NGSD_API int ngsd_device_results(ngsd_ctx *ctx, double **out_dev, double **num_dev, uint64_t **cnt_dev);   /* n_ind x n_ind each */
 NGSD_API int ngsd_finish(ngsd_ctx *ctx, double *out_host);
+
+/* ---- one process per GPU: NCCL communicator over the contexts of all ranks (SURVEY §5 "distributed communication
+ * backend", §2.1 rows C1 / C2).  The library links NCCL itself; the host only has to carry 128 bytes from rank 0 to
+ * the other ranks (a file, MPI, torch.distributed -- anything).  All calls below are collective: every rank makes
+ * them in the same order.  The reference has no counterpart (ngsDist.cpp:197-269 is one shared-memory pool). */
+#define NGSD_COMM_ID_BYTES 128
+NGSD_API int ngsd_comm_unique_id(uint8_t id[NGSD_COMM_ID_BYTES]);                           /* ncclGetUniqueId, on rank 0 */
+NGSD_API int ngsd_comm_attach(ngsd_ctx *ctx, const uint8_t id[NGSD_COMM_ID_BYTES], uint32_t rank, uint32_t world);
+/* REPLICATED data from a site-sharded front end: rank g pushed only sites [site_begin[g], site_begin[g+1]) (multiples
+ * of 64; 192 when the context contracts two planes) of a context created for ALL sites; one grouped NCCL all-gather of
+ * the packed operands, masks and codes makes every rank hold every site (row C2). */
+NGSD_API int ngsd_comm_allgather_operands(ngsd_ctx *ctx, const uint64_t *site_begin /* [world + 1] */);
+/* Site shards (row C1): after ngsd_distances(out == NULL) on every rank, ONE ncclReduce of the packed upper triangle of
+ * num (FP64) -- and of cnt (uint64) only under --pairwise_del, otherwise cnt is the constant n_eff_total -- onto `root`,
+ * which then runs the tail of gen_dist (ngsDist.cpp:372-401) and returns the matrix in out_host (NULL elsewhere). */
+NGSD_API int ngsd_comm_reduce_sites(ngsd_ctx *ctx, uint32_t root, uint64_t n_eff_total, double *out_host);
+/* Tile shards (ngsd_set_tile_shard(rank, world) on every rank): after ngsd_distances(out == NULL), the matrices are
+ * assembled on `root` by an NCCL sum (entries a rank does not own are exact zeros).  with_num_cnt (the same value on
+ * every rank) also assembles the raw sums and counts; the host pointers are only read on `root`. */
+NGSD_API int ngsd_comm_reduce_tiles(ngsd_ctx *ctx, uint32_t root, int32_t with_num_cnt, double *out_host, double *num_host, uint64_t *cnt_host);
+NGSD_API int ngsd_comm_barrier(ngsd_ctx *ctx);
+/* bytes moved over NVLink by the last collective of this rank (sent + received) and its device time in ms */
+NGSD_API int ngsd_comm_stats(const ngsd_ctx *ctx, uint64_t *bytes, float *ms);
+
+/* Host placement (8 ranks pushing from pinned buffers that all sit on one NUMA node): binds the calling
+ * thread to the CPUs local to `device` (sysfs local_cpulist of its PCI function) and prefers that node for the pages
+ * it touches afterwards -- call before ngsd_host_alloc.  Returns the NUMA node, -1 when the platform exposes none. */
+NGSD_API int ngsd_bind_host_to_device(int device);
 
 /* Host-side helper with the reference's RNG semantics (gsl_rng_taus; ngsDist.cpp:179-180, gen_func.cpp:117-119):
  * state[3] is seeded by ngsd_taus_seed and advanced by n_blocks draws per call of ngsd_boot_block_counts, which

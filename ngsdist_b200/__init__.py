@@ -5,7 +5,10 @@ this package is a thin ctypes mirror of it for tests and bench.py.  There is no 
 works without a GPU, but every compute entry point fails loudly when the library or a CUDA device is missing.
 """
 from .api import (NgsDistError, Params, NgsDistB200, Timing, lib, lib_path, build_library, taus_block_counts, probe_fp64_tflops, probe_int8_tmacs, probe_umma_tmacs,
-                  ABI_SYMBOLS, pack_genotypes, PLINK_BED_CODES)
+                  ABI_SYMBOLS, pack_genotypes, PLINK_BED_CODES, comm_unique_id, bind_host_to_device, SHARD_AUTO, SHARD_REPLICATED,
+                  SHARD_SITES)
+from . import api
 
 __all__ = ["NgsDistError", "Params", "NgsDistB200", "Timing", "lib", "lib_path", "build_library", "taus_block_counts",
-           "probe_fp64_tflops", "probe_int8_tmacs", "probe_umma_tmacs", "ABI_SYMBOLS", "pack_genotypes", "PLINK_BED_CODES"]
+           "probe_fp64_tflops", "probe_int8_tmacs", "probe_umma_tmacs", "ABI_SYMBOLS", "pack_genotypes", "PLINK_BED_CODES", "comm_unique_id", "bind_host_to_device",
+           "SHARD_AUTO", "SHARD_REPLICATED", "SHARD_SITES", "api"]

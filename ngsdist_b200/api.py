@@ -20,7 +20,12 @@ ABI_SYMBOLS = [
     "ngsd_push_sites_device", "ngsd_push_genotypes", "ngsd_push_packed_genotypes", "ngsd_frontend", "ngsd_distances", "ngsd_taus_seed", "ngsd_taus_get",
     "ngsd_boot_block_counts", "ngsd_get_posteriors", "ngsd_synth_raw_device", "ngsd_get_timing", "ngsd_stream",
     "ngsd_probe_fp64_tflops", "ngsd_probe_int8_tmacs", "ngsd_probe_umma_tmacs", "ngsd_host_alloc", "ngsd_host_free", "ngsd_set_tile_shard", "ngsd_device_results", "ngsd_finish",
+    "ngsd_distances_batch", "ngsd_comm_unique_id", "ngsd_comm_attach", "ngsd_comm_allgather_operands", "ngsd_comm_reduce_sites", "ngsd_comm_reduce_tiles",
+    "ngsd_comm_barrier", "ngsd_comm_stats", "ngsd_bind_host_to_device",
 ]
+ABI_VERSION = 2
+COMM_ID_BYTES = 128
+SHARD_AUTO, SHARD_REPLICATED, SHARD_SITES = 0, 1, 2
 
 
 class NgsDistError(RuntimeError):
@@ -36,7 +41,8 @@ class _Cfg(C.Structure):
     _fields_ = [("n_ind", C.c_uint64), ("n_sites", C.c_uint64), ("tot_sites", C.c_uint64), ("score", C.c_double * 9),
                 ("evol_model", C.c_int32), ("pairwise_del", C.c_int32), ("indep_geno", C.c_int32), ("call_geno", C.c_int32),
                 ("N_thresh", C.c_double), ("call_thresh", C.c_double), ("input_is_log", C.c_int32), ("input_kind", C.c_int32),
-                ("device", C.c_int32), ("reserved", C.c_int32)]
+                ("device", C.c_int32), ("reserved", C.c_int32), ("n_gpus", C.c_int32), ("shard", C.c_int32),
+                ("boot_block_size", C.c_uint64)]
 
 
 class Timing(C.Structure):
@@ -106,9 +112,20 @@ def lib():
     L.ngsd_set_tile_shard.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.ngsd_device_results.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp)]
     L.ngsd_finish.argtypes = [vp, vp]
+    L.ngsd_distances_batch.argtypes = [vp, vp, u64, u64, u64, vp]
+    L.ngsd_comm_unique_id.argtypes = [vp]
+    L.ngsd_comm_attach.argtypes = [vp, vp, C.c_uint32, C.c_uint32]
+    L.ngsd_comm_allgather_operands.argtypes = [vp, vp]
+    L.ngsd_comm_reduce_sites.argtypes = [vp, C.c_uint32, u64, vp]
+    L.ngsd_comm_reduce_tiles.argtypes = [vp, C.c_uint32, C.c_int32, vp, vp, vp]
+    L.ngsd_comm_barrier.argtypes = [vp]
+    L.ngsd_comm_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(C.c_float)]
+    L.ngsd_bind_host_to_device.argtypes = [i32]
     for name in ("ngsd_create", "ngsd_destroy", "ngsd_push_sites", "ngsd_push_sites_device", "ngsd_push_genotypes", "ngsd_push_packed_genotypes", "ngsd_frontend",
                  "ngsd_distances", "ngsd_get_posteriors", "ngsd_synth_raw_device", "ngsd_get_timing", "ngsd_probe_fp64_tflops", "ngsd_probe_int8_tmacs", "ngsd_probe_umma_tmacs",
-                 "ngsd_set_tile_shard", "ngsd_device_results", "ngsd_finish"):
+                 "ngsd_set_tile_shard", "ngsd_device_results", "ngsd_finish", "ngsd_distances_batch", "ngsd_comm_unique_id", "ngsd_comm_attach",
+                 "ngsd_comm_allgather_operands", "ngsd_comm_reduce_sites", "ngsd_comm_reduce_tiles", "ngsd_comm_barrier", "ngsd_comm_stats",
+                 "ngsd_bind_host_to_device"):
         getattr(L, name).restype = i32
     _lib = L
     return L
@@ -192,6 +209,19 @@ def probe_int8_tmacs(device=0):
     return v.value
 
 
+def comm_unique_id():
+    """ncclGetUniqueId through the library (rank 0); hand the bytes to every rank for NgsDistB200.comm_attach."""
+    buf = (C.c_uint8 * COMM_ID_BYTES)()
+    rc = lib().ngsd_comm_unique_id(buf)
+    if rc:
+        raise NgsDistError(rc, lib().ngsd_last_error(None).decode())
+    return bytes(buf)
+
+
+def bind_host_to_device(device):
+    return lib().ngsd_bind_host_to_device(device)
+
+
 PLINK_BED_CODES = (0, -1, 1, 2)     # .bed 2-bit fields: 0 = homozygous A1, 1 = missing, 2 = heterozygous, 3 = homozygous A2
 
 
@@ -211,7 +241,8 @@ def pack_genotypes(geno, field_of_code=None):
 class NgsDistB200:
     """One context = one GPU = the hot path of one ngsDist run."""
 
-    def __init__(self, params: Params, device=0):
+    def __init__(self, params: Params, device=0, n_gpus=1, shard=SHARD_AUTO):
+        """n_gpus > 1: one context driving devices device .. device + n_gpus - 1 (ngsd_cfg.n_gpus / shard)."""
         self.p = params.resolved()
         L = lib()
         cfg = _Cfg()
@@ -229,6 +260,10 @@ class NgsDistB200:
         cfg.input_kind = 2 if not p.in_probs else (1 if p.in_text else 0)
         cfg.device = device
         cfg.reserved = (1 if p.keep_planes else 0) | (2 if p.force_fp64 else 0) | (4 if p.no_block_cache else 0)
+        cfg.n_gpus = n_gpus if n_gpus > 1 else 0
+        cfg.shard = shard
+        cfg.boot_block_size = p.boot_block_size if p.n_boot_rep > 0 else 0
+        self.n_gpus = max(1, n_gpus)
         self._h = C.c_void_p()
         rc = L.ngsd_create(C.byref(cfg), C.byref(self._h))
         if rc:
@@ -327,6 +362,31 @@ class NgsDistB200:
         n_blocks = self._n_sites_boot // bs
         return taus_block_counts(self._taus, n_blocks), bs
 
+    def distances_batch(self, counts, block_size, out=None):
+        """counts: [n_rep][n_blocks] uint32 -> [n_rep][n][n] matrices (ngsd_distances_batch).  With a communicator attached
+        only rank 0 receives them (the other ranks return None)."""
+        counts = np.ascontiguousarray(counts, dtype=np.uint32)
+        n_rep, n_blocks = counts.shape
+        n = self.p.n_ind
+        root = getattr(self, "_comm_rank", 0) == 0
+        if out is None and root:
+            out = np.empty((n_rep, n, n), dtype=np.float64)
+        self._check(lib().ngsd_distances_batch(self._h, _ptr(counts), n_rep, n_blocks, block_size, _ptr(out) if root else None))
+        return out if root else None
+
+    def run_batched(self):
+        """main()'s replicate loop with the bootstrap replicates in ONE ngsd_distances_batch call: list of matrices."""
+        self.frontend()
+        res = [self.distances()["dist"]]
+        if self.p.n_boot_rep > 0:
+            rows = []
+            for _ in range(self.p.n_boot_rep):
+                c, bs = self.next_boot_counts()
+                rows.append(c)
+            nb_ = min(len(r) for r in rows)          # the truncation is persistent, so every replicate has the same count
+            res += list(self.distances_batch(np.stack([r[:nb_] for r in rows]), self.p.boot_block_size))
+        return res
+
     def run(self, want_num=False, want_cnt=False):
         """The replicate loop of main() (ngsDist.cpp:217-289): list of 1 + n_boot_rep result dicts."""
         self.frontend()
@@ -364,6 +424,47 @@ class NgsDistB200:
             out = np.empty((n, n), dtype=np.float64)
         self._check(lib().ngsd_finish(self._h, _ptr(out)))
         return out
+
+    # -- one process per GPU: NCCL below the C ABI (ngsd_comm_*) --
+    def comm_attach(self, comm_id, rank, world):
+        """comm_id: the 128 bytes rank 0 got from comm_unique_id(), carried to every rank by the host."""
+        buf = (C.c_uint8 * COMM_ID_BYTES).from_buffer_copy(bytes(comm_id))
+        self._check(lib().ngsd_comm_attach(self._h, buf, rank, world))
+        self._comm_rank, self._comm_world = rank, world
+
+    def comm_allgather_operands(self, site_begin):
+        sb = np.ascontiguousarray(site_begin, dtype=np.uint64)
+        self._check(lib().ngsd_comm_allgather_operands(self._h, _ptr(sb)))
+
+    def comm_reduce_sites(self, root, n_eff_total, out=None):
+        n = self.p.n_ind
+        if out is None and self._comm_rank == root:
+            out = np.empty((n, n), dtype=np.float64)
+        self._check(lib().ngsd_comm_reduce_sites(self._h, root, n_eff_total, _ptr(out) if self._comm_rank == root else None))
+        return out if self._comm_rank == root else None
+
+    def comm_reduce_tiles(self, root, want_num_cnt=False, out=None):
+        n = self.p.n_ind
+        is_root = self._comm_rank == root
+        if out is None and is_root:
+            out = np.empty((n, n), dtype=np.float64)
+        num = np.empty((n, n), dtype=np.float64) if (want_num_cnt and is_root) else None
+        cnt = np.empty((n, n), dtype=np.uint64) if (want_num_cnt and is_root) else None
+        self._check(lib().ngsd_comm_reduce_tiles(self._h, root, int(want_num_cnt), _ptr(out) if is_root else None, _ptr(num), _ptr(cnt)))
+        if not is_root:
+            return None
+        res = dict(dist=out)
+        if want_num_cnt:
+            res.update(num=num, cnt=cnt)
+        return res
+
+    def comm_barrier(self):
+        self._check(lib().ngsd_comm_barrier(self._h))
+
+    def comm_stats(self):
+        b, ms = C.c_uint64(0), C.c_float(0)
+        self._check(lib().ngsd_comm_stats(self._h, C.byref(b), C.byref(ms)))
+        return b.value, ms.value
 
     # -- measurement --
     def timing(self):

@@ -157,6 +157,9 @@ int ngsd_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
     return NGSD_ERR_THRESH;
   }
   if (cfg->input_kind < 0 || cfg->input_kind > 2 || (cfg->reserved & ~7)) { ngsd_set_error(nullptr, "invalid input_kind / flags"); return NGSD_ERR_ARG; }
+  // internal index types: 64-site word and chunk ids are uint32, per-split shared-site counts are uint32
+  if (cfg->n_sites > ((uint64_t) 1 << 32) - 64) { ngsd_set_error(nullptr, "n_sites too large for one context (limit 2^32 - 64 sites per GPU): shard the sites (ngsd_cfg.n_gpus with NGSD_SHARD_SITES)"); return NGSD_ERR_ARG; }
+  if (cfg->n_gpus < 0 || cfg->n_gpus > 64 || cfg->shard < 0 || cfg->shard > 2) { ngsd_set_error(nullptr, "invalid n_gpus / shard"); return NGSD_ERR_ARG; }
   if ((cfg->input_kind == NGSD_INPUT_GENOTYPES || cfg->call_geno) && !cfg->indep_geno) {
     ngsd_set_error(nullptr, "indep_geno must be set for genotype input / call_geno (ngsDist.cpp:55-62)");
     return NGSD_ERR_ARG;
@@ -169,6 +172,10 @@ int ngsd_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
     return NGSD_ERR_CUDA;
   }
   if (cfg->device < 0 || cfg->device >= ndev) { ngsd_set_error(nullptr, "invalid device ordinal %d", cfg->device); return NGSD_ERR_ARG; }
+  if (cfg->n_gpus > 1) {
+    if (cfg->device + cfg->n_gpus > ndev) { ngsd_set_error(nullptr, "n_gpus %d from device %d: only %d devices visible", cfg->n_gpus, cfg->device, ndev); return NGSD_ERR_ARG; }
+    return ngsd_group_create(cfg, out);
+  }
 
   ngsd_ctx *ctx = new (std::nothrow) ngsd_ctx();
   if (!ctx) { ngsd_set_error(nullptr, "out of host memory"); return NGSD_ERR_ARG; }
@@ -229,8 +236,8 @@ int ngsd_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
   CREATE_CUDA(dev_alloc(&ctx->Bpack, plane));
   CREATE_CUDA(dev_alloc(&ctx->mask, ctx->RB * ctx->NW * 128));
   if (ctx->planes == 2) {
-    ctx->ldc = ctx->NW * 64;
-    CREATE_CUDA(dev_alloc(&ctx->Cplane, ctx->n_pad * ctx->ldc));
+    ctx->ldc = ctx->n_pad;   // Cplane is [NW][n_pad][64]: the sites of a 64-site word are contiguous per individual
+    CREATE_CUDA(dev_alloc(&ctx->Cplane, ctx->NW * ctx->n_pad * 64));
     CREATE_CUDA(dev_alloc(&ctx->d_cvec, ctx->n_pad));
   }
   CREATE_CUDA(dev_alloc(&ctx->d_err, 1));
@@ -249,8 +256,10 @@ int ngsd_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
 
 int ngsd_destroy(ngsd_ctx *ctx) {
   if (!ctx) return NGSD_OK;
+  if (!ctx->kids.empty()) return ngsd_group_destroy(ctx);
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  ngsd_comm_release(ctx);
   if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
   if (ctx->aux_stream) cudaStreamSynchronize(ctx->aux_stream);
   cudaFree(ctx->Apack); cudaFree(ctx->Bpack); cudaFree(ctx->mask); cudaFree(ctx->d_err); cudaFree(ctx->Cplane); cudaFree(ctx->d_cvec);
@@ -294,6 +303,7 @@ static void mark_pushed(ngsd_ctx *ctx, uint64_t site0, uint64_t n) {
 }
 
 int ngsd_push_sites_device(ngsd_ctx *ctx, const double *raw_dev, uint64_t site0, uint64_t n) {
+  if (ctx && !ctx->kids.empty()) return ngsd_group_push(ctx, 3, raw_dev, ctx->n_ind * 3 * sizeof(double), 0, nullptr, site0, n);
   int rc = check_push(ctx, site0, n);
   if (rc) return rc;
   if (ctx->cfg.input_kind == NGSD_INPUT_GENOTYPES) { ngsd_set_error(ctx, "context expects genotype codes"); return NGSD_ERR_ARG; }
@@ -323,6 +333,7 @@ static int ensure_staging(ngsd_ctx *ctx, uint64_t bytes_per_site) {
 }
 
 int ngsd_push_sites(ngsd_ctx *ctx, const double *raw_host, uint64_t site0, uint64_t n) {
+  if (ctx && !ctx->kids.empty()) return ngsd_group_push(ctx, 0, raw_host, ctx->n_ind * 3 * sizeof(double), 0, nullptr, site0, n);
   int rc = check_push(ctx, site0, n);
   if (rc) return rc;
   if (!raw_host) { ngsd_set_error(ctx, "null raw pointer"); return NGSD_ERR_ARG; }
@@ -356,6 +367,7 @@ int ngsd_push_sites(ngsd_ctx *ctx, const double *raw_host, uint64_t site0, uint6
 }
 
 int ngsd_push_genotypes(ngsd_ctx *ctx, const int8_t *codes_host, uint64_t site0, uint64_t n) {
+  if (ctx && !ctx->kids.empty()) return ngsd_group_push(ctx, 1, codes_host, ctx->n_ind, 0, nullptr, site0, n);
   int rc = check_push(ctx, site0, n);
   if (rc) return rc;
   if (!codes_host) { ngsd_set_error(ctx, "null codes pointer"); return NGSD_ERR_ARG; }
@@ -380,6 +392,7 @@ int ngsd_push_genotypes(ngsd_ctx *ctx, const int8_t *codes_host, uint64_t site0,
 
 int ngsd_push_packed_genotypes(ngsd_ctx *ctx, const uint8_t *packed_host, uint64_t row_stride, const int8_t *code_of_field, uint64_t site0,
                                uint64_t n) {
+  if (ctx && !ctx->kids.empty()) return ngsd_group_push(ctx, 2, packed_host, row_stride, row_stride, code_of_field, site0, n);
   int rc = check_push(ctx, site0, n);
   if (rc) return rc;
   if (!packed_host) { ngsd_set_error(ctx, "null packed pointer"); return NGSD_ERR_ARG; }
@@ -429,24 +442,40 @@ int ngsd_push_packed_genotypes(ngsd_ctx *ctx, const uint8_t *packed_host, uint64
   return NGSD_OK;
 }
 
+void ngsd_mark_all_pushed(ngsd_ctx *ctx) {
+  std::fill(ctx->pushed.begin(), ctx->pushed.end(), (uint8_t) 1);
+  ctx->words_pushed = ctx->NW;
+  ctx->frontend_done = true;
+  ctx->cache_valid = false;
+}
+
 int ngsd_frontend(ngsd_ctx *ctx) {
   if (!ctx) return NGSD_ERR_ARG;
+  if (!ctx->kids.empty()) return ngsd_group_frontend(ctx);
   if (ctx->words_pushed != ctx->NW) {
     ngsd_set_error(ctx, "front end incomplete: %llu of %llu 64-site words pushed", (unsigned long long) ctx->words_pushed, (unsigned long long) ctx->NW);
     return NGSD_ERR_STATE;
   }
+  int rc = ngsd_frontend_flags(ctx);
+  if (rc) return rc;
+  ctx->frontend_done = true;
+  return NGSD_OK;
+}
+
+// The deferred error flags of the pushes so far (NaN on the binary path, genotype codes above 2).
+int ngsd_frontend_flags(ngsd_ctx *ctx) {
   NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
   int flags = 0;
   NGSD_CUDA(ctx, cudaMemcpyAsync(&flags, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (flags & 1) { ngsd_set_error(ctx, "NaN found! Is the file format correct?"); return NGSD_ERR_NAN; }
   if (flags & 2) { ngsd_set_error(ctx, "wrong GENO file format. Genotypes must be coded as {-1,0,1,2} !"); return NGSD_ERR_GENO; }
-  ctx->frontend_done = true;
   return NGSD_OK;
 }
 
 int ngsd_get_posteriors(ngsd_ctx *ctx, double *P_host, uint8_t *miss_host) {
   if (!ctx) return NGSD_ERR_ARG;
+  if (!ctx->kids.empty()) return ngsd_group_get_posteriors(ctx, P_host, miss_host);
   NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
   const uint64_t tot = ctx->n_ind * ctx->n_sites;
   double *dP = nullptr;
@@ -744,6 +773,7 @@ static int ensure_entries(ngsd_ctx *ctx, uint64_t n) {
 int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_blocks, uint64_t block_size, double *out,
                    double *num_opt, uint64_t *cnt_opt) {
   if (!ctx) return NGSD_ERR_ARG;
+  if (!ctx->kids.empty()) return ngsd_group_distances(ctx, block_counts, n_blocks, block_size, out, num_opt, cnt_opt);
   NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
   if (!ctx->frontend_done) {
     int rc = ngsd_frontend(ctx);
@@ -753,11 +783,29 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   const bool weighted = block_counts != nullptr;
   uint64_t n_eff = ctx->n_sites;
   if (weighted) {
-    if (block_size == 0 || n_blocks == 0 || n_blocks * block_size > ctx->n_sites) {
+    if (block_size == 0 || n_blocks * block_size > ctx->n_sites) {
       ngsd_set_error(ctx, "invalid bootstrap geometry: %llu blocks of %llu sites", (unsigned long long) n_blocks, (unsigned long long) block_size);
       return NGSD_ERR_ARG;
     }
     n_eff = n_blocks * block_size;
+    if (n_blocks == 0) {
+      // --boot_block_size > n_sites: the reference truncates n_sites to 0 (ngsDist.cpp:236) and still writes a matrix --
+      // every pair has dist = 0 over cnt = 0 sites, i.e. 0/0 (or 0/tot_sites) through ngsDist.cpp:372-401.  The same
+      // degenerate replicate is what a site shard without any block contributes: all-zero sums.
+      int rc0 = ensure_dist_buffers(ctx, 1);
+      if (rc0) return rc0;
+      const uint64_t n2z = ctx->n_ind * ctx->n_ind;
+      NGSD_CUDA(ctx, cudaMemsetAsync(ctx->d_num, 0, n2z * sizeof(double), ctx->stream));
+      NGSD_CUDA(ctx, cudaMemsetAsync(ctx->d_cntout, 0, n2z * sizeof(uint64_t), ctx->stream));
+      NGSD_CUDA(ctx, ngsd_launch_finish(ctx));
+      if (out) NGSD_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, n2z * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      if (num_opt) NGSD_CUDA(ctx, cudaMemcpyAsync(num_opt, ctx->d_num, n2z * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      if (cnt_opt) NGSD_CUDA(ctx, cudaMemcpyAsync(cnt_opt, ctx->d_cntout, n2z * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+      NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      ctx->timing = ngsd_timing();
+      ctx->timing.launches = 1;
+      return NGSD_OK;
+    }
   }
   if (ctx->int_path) return distances_int(ctx, block_counts, n_blocks, block_size, out, num_opt, cnt_opt);
   const uint64_t SC = (uint64_t) ctx->sc;
@@ -1063,10 +1111,32 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   return NGSD_OK;
 }
 
+// The bootstrap loop of main() (ngsDist.cpp:217-238) in one call.  One GPU: replicates back to back on the context's
+// stream; groups and communicators deal them out (comm.cu).
+int ngsd_distances_batch(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_rep, uint64_t n_blocks, uint64_t block_size, double *out) {
+  if (!ctx) return NGSD_ERR_ARG;
+  if (!block_counts && n_rep) { ngsd_set_error(ctx, "null block_counts"); return NGSD_ERR_ARG; }
+  if (!ctx->kids.empty() || ctx->comm) return ngsd_group_distances_batch(ctx, block_counts, n_rep, n_blocks, block_size, out);
+  if (!out && n_rep) { ngsd_set_error(ctx, "null output"); return NGSD_ERR_ARG; }
+  const uint64_t n2 = ctx->n_ind * ctx->n_ind;
+  ngsd_timing sum = ngsd_timing();
+  for (uint64_t r = 0; r < n_rep; r++) {
+    int rc = ngsd_distances(ctx, block_counts + r * n_blocks, n_blocks, block_size, out + r * n2, nullptr, nullptr);
+    if (rc) return rc;
+    sum.count_ms += ctx->timing.count_ms; sum.dist_ms += ctx->timing.dist_ms; sum.epilogue_ms += ctx->timing.epilogue_ms;
+    sum.total_ms += ctx->timing.total_ms; sum.launches += ctx->timing.launches; sum.dist_dmma += ctx->timing.dist_dmma;
+    sum.dist_imma += ctx->timing.dist_imma; sum.active_sites += ctx->timing.active_sites;
+    sum.dist_ctas = ctx->timing.dist_ctas; sum.block_cache = ctx->timing.block_cache;
+  }
+  ctx->timing = sum;
+  return NGSD_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- multi-GPU ----
 
 int ngsd_set_tile_shard(ngsd_ctx *ctx, uint32_t rank, uint32_t world) {
   if (!ctx) return NGSD_ERR_ARG;
+  if (!ctx->kids.empty()) { ngsd_set_error(ctx, "a multi-GPU context deals the tiles to its GPUs itself"); return NGSD_ERR_ARG; }
   if (world == 0 || rank >= world) { ngsd_set_error(ctx, "invalid tile shard %u of %u", rank, world); return NGSD_ERR_ARG; }
   if (!ctx->cfg.indep_geno && world > 1) { ngsd_set_error(ctx, "tile sharding is not available on the per pair-site EM path"); return NGSD_ERR_ARG; }
   NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1097,6 +1167,7 @@ int ngsd_set_tile_shard(ngsd_ctx *ctx, uint32_t rank, uint32_t world) {
 
 int ngsd_device_results(ngsd_ctx *ctx, double **out_dev, double **num_dev, uint64_t **cnt_dev) {
   if (!ctx) return NGSD_ERR_ARG;
+  if (!ctx->kids.empty()) ctx = ctx->kids[0];   // the root GPU of a group holds the assembled / reduced matrices
   if (!ctx->d_out) { ngsd_set_error(ctx, "no results yet: call ngsd_distances first"); return NGSD_ERR_STATE; }
   if (out_dev) *out_dev = ctx->d_out;
   if (num_dev) *num_dev = ctx->d_num;
@@ -1106,6 +1177,7 @@ int ngsd_device_results(ngsd_ctx *ctx, double **out_dev, double **num_dev, uint6
 
 int ngsd_finish(ngsd_ctx *ctx, double *out_host) {
   if (!ctx) return NGSD_ERR_ARG;
+  if (!ctx->kids.empty()) ctx = ctx->kids[0];
   if (!ctx->d_out) { ngsd_set_error(ctx, "no results yet: call ngsd_distances first"); return NGSD_ERR_STATE; }
   NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
   NGSD_CUDA(ctx, ngsd_launch_finish(ctx));
@@ -1150,6 +1222,7 @@ void ngsd_boot_block_counts(uint32_t state[3], uint64_t n_blocks, uint32_t *coun
 
 int ngsd_synth_raw_device(ngsd_ctx *ctx, double *raw_dev, uint64_t seed, double miss_rate, uint64_t site0, uint64_t n) {
   if (!ctx || !raw_dev) return NGSD_ERR_ARG;
+  if (!ctx->kids.empty()) { ngsd_set_error(ctx, "synthetic device input needs a single-GPU context"); return NGSD_ERR_ARG; }
   NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
   NGSD_CUDA(ctx, ngsd_launch_synth(ctx, raw_dev, seed, miss_rate, site0, n));
   NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1159,6 +1232,7 @@ int ngsd_synth_raw_device(ngsd_ctx *ctx, double *raw_dev, uint64_t seed, double 
 int ngsd_get_timing(const ngsd_ctx *ctx, ngsd_timing *t) {
   if (!ctx || !t) return NGSD_ERR_ARG;
   ngsd_ctx *c = const_cast<ngsd_ctx *>(ctx);
+  if (!c->kids.empty()) return ngsd_group_get_timing(c, t);
   if (c->timing.total_ms < 0) {   // a push: events 0..1
     if (cudaEventSynchronize(c->ev[1]) != cudaSuccess) return NGSD_ERR_CUDA;
     float ms = 0;
@@ -1170,7 +1244,7 @@ int ngsd_get_timing(const ngsd_ctx *ctx, ngsd_timing *t) {
   return NGSD_OK;
 }
 
-void *ngsd_stream(ngsd_ctx *ctx) { return ctx ? (void *) ctx->stream : nullptr; }
+void *ngsd_stream(ngsd_ctx *ctx) { return ctx ? (void *) (ctx->kids.empty() ? ctx->stream : ctx->kids[0]->stream) : nullptr; }
 
 void *ngsd_host_alloc(uint64_t bytes) {
   void *p = nullptr;

@@ -103,12 +103,13 @@ __global__ void k_zero_diag(double *out, double *num, uint64_t *cnt, uint64_t n)
 }
 
 // ngsd_finish: the tail of gen_dist on already reduced raw sums (site-sharded runs): out = model(num / cnt)
-__global__ void k_finish(const double *__restrict__ num, const uint64_t *__restrict__ cnt, double *__restrict__ out, uint64_t n,
-                         uint64_t tot_sites, int evol_model) {
+__global__ void k_finish(const double *__restrict__ num, uint64_t *__restrict__ cnt, double *__restrict__ out, uint64_t n,
+                         uint64_t tot_sites, int evol_model, uint64_t const_cnt) {
   const uint64_t idx = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n * n) return;
   const uint64_t i = idx / n, j = idx % n;
   if (i == j) { out[idx] = 0.0; return; }
+  if (const_cnt) cnt[idx] = const_cnt;      // no --pairwise_del: every pair counted every site (ngsDist.cpp:362)
   uint64_t c = cnt[idx];
   if (tot_sites > 0) c = tot_sites;
   double d = num[idx] / (double) c;
@@ -117,13 +118,17 @@ __global__ void k_finish(const double *__restrict__ num, const uint64_t *__restr
   out[idx] = d;
 }
 
-// 2-plane mode: c_j = sum_s w_s * C[j][s] (C = B_2 plane); one block per individual, fixed-order tree reduction
-__global__ void __launch_bounds__(256) k_cvec(const double *__restrict__ C, uint64_t ldc, const double *__restrict__ w, uint64_t n_eff,
+// 2-plane mode: c_j = sum_s w_s * C[j][s] (C = B_2 plane, stored [64-site word][n_pad][64]); one block per individual,
+// fixed-order tree reduction
+__global__ void __launch_bounds__(256) k_cvec(const double *__restrict__ C, uint64_t n_pad, const double *__restrict__ w, uint64_t n_eff,
                                              double *__restrict__ cvec) {
   __shared__ double red[256];
-  const double *row = C + (uint64_t) blockIdx.x * ldc;
+  const double *row = C + (uint64_t) blockIdx.x * 64;
   double s = 0;
-  for (uint64_t k = threadIdx.x; k < n_eff; k += 256) s += w ? w[k] * row[k] : row[k];
+  for (uint64_t k = threadIdx.x; k < n_eff; k += 256) {
+    const double v = row[(k >> 6) * n_pad * 64 + (k & 63)];
+    s += w ? w[k] * v : v;
+  }
   red[threadIdx.x] = s;
   __syncthreads();
   for (int o = 128; o > 0; o >>= 1) {
@@ -140,10 +145,10 @@ cudaError_t ngsd_launch_cvec(ngsd_ctx *ctx, bool weighted, uint64_t n_eff) {
   return cudaGetLastError();
 }
 
-cudaError_t ngsd_launch_finish(ngsd_ctx *ctx) {
+cudaError_t ngsd_launch_finish(ngsd_ctx *ctx, uint64_t const_cnt) {
   const uint64_t n2 = ctx->n_ind * ctx->n_ind;
   k_finish<<<(unsigned) ((n2 + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_num, ctx->d_cntout, ctx->d_out, ctx->n_ind, ctx->cfg.tot_sites,
-                                                                 ctx->cfg.evol_model);
+                                                                 ctx->cfg.evol_model, const_cnt);
   return cudaGetLastError();
 }
 

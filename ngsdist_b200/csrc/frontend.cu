@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(512, EXACT ? 1 : 2) k_frontend(FrontCfg c, con
       st256(Apack + o, A[0][g], A[1][g], A[2][g], A[3][g]);
       st256(Bpack + o, Bv[g][0] - Bv[2][0], Bv[g][1] - Bv[2][1], Bv[g][2] - Bv[2][2], Bv[g][3] - Bv[2][3]);
     }
-    st256(Cplane + i * ldc + sgrp * 4, Bv[2][0], Bv[2][1], Bv[2][2], Bv[2][3]);
+    st256(Cplane + (word * ldc + i) * 64 + ty * 4, Bv[2][0], Bv[2][1], Bv[2][2], Bv[2][3]);   // [word][n_pad][64]: a site range is contiguous (all-gather)
   }
 
   nib[ty][tx] = bits;

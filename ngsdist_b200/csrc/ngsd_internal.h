@@ -51,7 +51,7 @@ struct ngsd_ctx {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   uint64_t n_ind = 0, n_pad = 0, RB = 0, n_sites = 0, NC = 0, NW = 0;
   int planes = 3, sc = NGSD_SC;                // operand planes per site (3, or 2 with the sum-to-one reduction) / sites per chunk
-  double *Cplane = nullptr;                    // [n_pad][ldc] B_2 plane (2-plane mode)
+  double *Cplane = nullptr;                    // [NW][n_pad][64] B_2 plane (2-plane mode); ldc = n_pad
   uint64_t ldc = 0;
   double *d_cvec = nullptr;                    // [n_pad] weighted row sums of Cplane for the current matrix
   double *Apack = nullptr, *Bpack = nullptr;   // [RB][NC][3072]
@@ -101,6 +101,19 @@ struct ngsd_ctx {
   uint32_t *d_cnt = nullptr;                   // [n_pad][n_pad] shared-site counts
   double *d_out = nullptr, *d_num = nullptr; uint64_t *d_cntout = nullptr;   // [n_ind][n_ind]
   void *h_pin = nullptr; uint64_t h_pin_bytes = 0;    // pinned scratch for weights / lists / results
+  // ---- multi-GPU (comm.cu) ----
+  void *comm = nullptr;                        // ncclComm_t of this context's rank (ngsd_comm_attach, or the group's ncclCommInitAll)
+  uint32_t comm_rank = 0, comm_world = 1;
+  double *d_tri = nullptr; uint64_t tri_cap = 0;        // packed upper triangle of num / cnt for the site-shard reduce
+  double *d_gather = nullptr; uint64_t gather_cap = 0;  // root side: matrices received from the other ranks (batched replicates)
+  uint64_t comm_bytes = 0; float comm_ms = 0.f;         // last collective: bytes over NVLink (sent + received), device time
+  cudaEvent_t ev_comm[2] = {nullptr, nullptr};
+  // in-process group (ngsd_cfg.n_gpus > 1): the parent owns no device memory, only its per-GPU contexts
+  std::vector<ngsd_ctx *> kids;
+  ngsd_ctx *parent = nullptr;
+  int shard_mode = 0;                          // ngsd_shard_mode the group resolved to
+  std::vector<uint64_t> site_begin;            // [n_gpus + 1] first site of every kid
+  bool kids_tile_sharded = false;
   // timing
   cudaEvent_t ev[10] = {};
   ngsd_timing timing = {};
@@ -151,7 +164,7 @@ size_t ngsd_dist_smem_bytes();
 uint32_t ngsd_em_splits(const ngsd_ctx *ctx, uint32_t n_chunks);
 uint64_t ngsd_em_ld(const ngsd_ctx *ctx);     // leading dimension of the EM partials (64-row tiles)
 cudaError_t ngsd_launch_dist_em(ngsd_ctx *ctx, uint32_t n_chunks, uint32_t n_splits, bool weighted);
-cudaError_t ngsd_launch_finish(ngsd_ctx *ctx);
+cudaError_t ngsd_launch_finish(ngsd_ctx *ctx, uint64_t const_cnt = 0);   // const_cnt > 0: cnt is that constant (no --pairwise_del)
 cudaError_t ngsd_launch_cvec(ngsd_ctx *ctx, bool weighted, uint64_t n_eff);
 cudaError_t ngsd_launch_epilogue_em(ngsd_ctx *ctx, uint32_t n_splits, uint64_t const_cnt, bool use_cnt);
 // K2c: called genotypes on the int8 tensor cores (dist_imma.cu)
@@ -161,3 +174,18 @@ int ngsd_imma_ctas_per_sm();
 bool ngsd_use_umma();
 cudaError_t ngsd_launch_dist_umma(ngsd_ctx *ctx, uint32_t n_units, int grid, uint32_t pstride, bool count);   // dist_umma.cu (tcgen05)
 cudaError_t ngsd_launch_epilogue_int(ngsd_ctx *ctx, uint32_t n_splits, uint64_t const_cnt, bool use_cnt, bool in_kernel_cnt);
+
+// ---- multi-GPU (comm.cu) ----
+extern "C" int ngsd_frontend_flags(ngsd_ctx *ctx);        // api.cu: the deferred error flags of the front end, without the completeness check
+extern "C" void ngsd_mark_all_pushed(ngsd_ctx *ctx);      // api.cu: after an all-gather every site is resident
+void ngsd_comm_release(ngsd_ctx *ctx);         // comm.cu: communicator + staging buffers of one context
+int ngsd_group_create(const ngsd_cfg *cfg, ngsd_ctx **out);
+int ngsd_group_destroy(ngsd_ctx *ctx);
+int ngsd_group_push(ngsd_ctx *ctx, int what /*0 sites host, 1 genotypes, 2 packed genotypes, 3 sites device*/, const void *ptr,
+                    uint64_t bytes_per_site, uint64_t row_stride, const int8_t *code_of_field, uint64_t site0, uint64_t n);
+int ngsd_group_frontend(ngsd_ctx *ctx);
+int ngsd_group_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_blocks, uint64_t block_size, double *out, double *num_opt,
+                         uint64_t *cnt_opt);
+int ngsd_group_distances_batch(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_rep, uint64_t n_blocks, uint64_t block_size, double *out);
+int ngsd_group_get_posteriors(ngsd_ctx *ctx, double *P_host, uint8_t *miss_host);
+int ngsd_group_get_timing(ngsd_ctx *ctx, ngsd_timing *t);

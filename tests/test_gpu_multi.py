@@ -1,4 +1,5 @@
-"""Multi-GPU sharding modes on real GPUs (needs >= 2 devices; the driver's 1-GPU run skips it)."""
+"""Multi-GPU sharding modes on real GPUs, through the C ABI only (needs >= 2 devices; a 1-GPU box skips them).
+The tools print what they verified; logs of the 2- and 8-GPU runs are under profiles/."""
 import os
 import subprocess
 import sys
@@ -9,11 +10,32 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_three_sharding_modes_on_two_gpus():
+def _n_gpus():
     import torch
-    if torch.cuda.device_count() < 2:
+    return torch.cuda.device_count()
+
+
+def test_one_process_per_gpu_nccl_below_the_abi():
+    """torchrun, one rank per GPU: ngsd_comm_attach + ngsd_distances_batch / reduce_tiles / reduce_sites / allgather."""
+    if _n_gpus() < 2:
         pytest.skip("needs 2 GPUs")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
            "--master-port", "29611", os.path.join(ROOT, "tools", "multi_gpu_check.py")]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=900)
     assert r.returncode == 0 and "MULTI_GPU_CHECK_OK" in r.stdout, r.stdout[-3000:]
+
+
+def test_one_process_many_gpus_group_context():
+    """ngsd_cfg.n_gpus = 2 in ONE process (REPLICATED and SITES) against a single-GPU context."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "group_check.py"), "2"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                       text=True, timeout=900)
+    assert r.returncode == 0 and "GROUP_CHECK_OK" in r.stdout, r.stdout[-3000:]
+
+
+def test_group_context_rejects_more_gpus_than_visible():
+    import ngsdist_b200 as nb
+    p = nb.Params(n_ind=10, n_sites=640, indep_geno=True)
+    with pytest.raises(nb.NgsDistError):
+        nb.NgsDistB200(p, n_gpus=_n_gpus() + 1)
