@@ -91,6 +91,13 @@ typedef struct {
                                 are aligned to whole blocks (ngsDist.cpp:416-437)                                     */
 } ngsd_cfg;
 
+/* An empty text line consumes a site and leaves the reference's values at their -1e15 fill without normalisation
+ * (read_data.cpp:58-59): after exp() every individual has (0,0,0) there -- or plain missing data under --call_geno.
+ * A host reader reproduces that by filling the site, for every individual, with this quiet-NaN bit pattern (all three
+ * doubles) or, for genotype input, with the code NGSD_BLANK_SITE_CODE. */
+#define NGSD_BLANK_SITE_BITS 0x7FF84E4753444231ull
+#define NGSD_BLANK_SITE_CODE (-128)
+
 typedef struct ngsd_ctx ngsd_ctx;
 
 /* Per-call device timings of the last ngsd_distances()/ngsd_push_* call, milliseconds, measured with CUDA
@@ -216,6 +223,10 @@ NGSD_API void ngsd_boot_block_counts(uint32_t state[3], uint64_t n_blocks, uint3
  *   P    : [ind][site][3] normal-space posteriors as gen_dist would read them (params.geno_lkl).
  *   miss : [ind][site] 1 where miss_data() is true (gen_func.cpp:862-868). */
 NGSD_API int ngsd_get_posteriors(ngsd_ctx *ctx, double *P_host, uint8_t *miss_host);
+/* How many individual-sites sat within 1e-11 of one of the reference's comparisons (miss_data's EPSILON, N_thresh,
+ * call_thresh, a tie of the two largest values) and were therefore evaluated by the HOST's libm -- the reference's own
+ * log / exp -- instead of the device's (front end). */
+NGSD_API int ngsd_deferred_stats(const ngsd_ctx *ctx, uint64_t *host_evaluated);
 
 /* Measurement support (bench.py): device-side synthetic raw GLs (SURVEY §8(d) generator, bit-identical to the CPU
  * restatement), timings of the last call, the context's stream, and an FP64 DMMA issue-rate probe used as the

@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "ngsd_boot_block_counts", "ngsd_get_posteriors", "ngsd_synth_raw_device", "ngsd_get_timing", "ngsd_stream",
     "ngsd_probe_fp64_tflops", "ngsd_probe_int8_tmacs", "ngsd_probe_umma_tmacs", "ngsd_host_alloc", "ngsd_host_free", "ngsd_set_tile_shard", "ngsd_device_results", "ngsd_finish",
     "ngsd_distances_batch", "ngsd_comm_unique_id", "ngsd_comm_attach", "ngsd_comm_allgather_operands", "ngsd_comm_reduce_sites", "ngsd_comm_reduce_tiles",
-    "ngsd_comm_barrier", "ngsd_comm_stats", "ngsd_bind_host_to_device",
+    "ngsd_comm_barrier", "ngsd_comm_stats", "ngsd_bind_host_to_device", "ngsd_deferred_stats",
 ]
 ABI_VERSION = 2
 COMM_ID_BYTES = 128
@@ -121,11 +121,12 @@ def lib():
     L.ngsd_comm_barrier.argtypes = [vp]
     L.ngsd_comm_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(C.c_float)]
     L.ngsd_bind_host_to_device.argtypes = [i32]
+    L.ngsd_deferred_stats.argtypes = [vp, C.POINTER(u64)]
     for name in ("ngsd_create", "ngsd_destroy", "ngsd_push_sites", "ngsd_push_sites_device", "ngsd_push_genotypes", "ngsd_push_packed_genotypes", "ngsd_frontend",
                  "ngsd_distances", "ngsd_get_posteriors", "ngsd_synth_raw_device", "ngsd_get_timing", "ngsd_probe_fp64_tflops", "ngsd_probe_int8_tmacs", "ngsd_probe_umma_tmacs",
                  "ngsd_set_tile_shard", "ngsd_device_results", "ngsd_finish", "ngsd_distances_batch", "ngsd_comm_unique_id", "ngsd_comm_attach",
                  "ngsd_comm_allgather_operands", "ngsd_comm_reduce_sites", "ngsd_comm_reduce_tiles", "ngsd_comm_barrier", "ngsd_comm_stats",
-                 "ngsd_bind_host_to_device"):
+                 "ngsd_bind_host_to_device", "ngsd_deferred_stats"):
         getattr(L, name).restype = i32
     _lib = L
     return L
@@ -221,6 +222,9 @@ def comm_unique_id():
 def bind_host_to_device(device):
     return lib().ngsd_bind_host_to_device(device)
 
+
+BLANK_SITE = np.array([0x7FF84E4753444231], dtype=np.uint64).view(np.float64)[0]   # NGSD_BLANK_SITE_BITS: an empty text line
+BLANK_SITE_CODE = -128
 
 PLINK_BED_CODES = (0, -1, 1, 2)     # .bed 2-bit fields: 0 = homozygous A1, 1 = missing, 2 = heterozygous, 3 = homozygous A2
 
@@ -341,6 +345,8 @@ class NgsDistB200:
         if block_counts is not None:
             block_counts = np.ascontiguousarray(block_counts, dtype=np.uint32)
             nb = len(block_counts)
+            if nb == 0:                          # --boot_block_size > n_sites: a replicate of zero blocks (not replicate 0)
+                block_counts = np.zeros(1, dtype=np.uint32)
         else:
             nb = 0
         self._check(lib().ngsd_distances(self._h, _ptr(block_counts), nb, block_size, _ptr(out), _ptr(num), _ptr(cnt)))
@@ -477,3 +483,9 @@ class NgsDistB200:
 
     def stream(self):
         return lib().ngsd_stream(self._h)
+
+    def deferred_stats(self):
+        """Individual-sites the host's libm decided (knife edges of the reference's comparisons)."""
+        n = C.c_uint64(0)
+        self._check(lib().ngsd_deferred_stats(self._h, C.byref(n)))
+        return n.value

@@ -241,6 +241,12 @@ int ngsd_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
     CREATE_CUDA(dev_alloc(&ctx->d_cvec, ctx->n_pad));
   }
   CREATE_CUDA(dev_alloc(&ctx->d_err, 1));
+  ctx->defer_cap = 1u << 18;
+  CREATE_CUDA(dev_alloc(&ctx->d_defer, ctx->defer_cap));
+  CREATE_CUDA(dev_alloc(&ctx->d_defer_n, 1));
+  CREATE_CUDA(cudaMemsetAsync(ctx->d_defer_n, 0, sizeof(unsigned), ctx->stream));
+  CREATE_CUDA(dev_alloc(&ctx->d_blank, ctx->NW));
+  CREATE_CUDA(cudaMemsetAsync(ctx->d_blank, 0, ctx->NW * sizeof(uint64_t), ctx->stream));
   CREATE_CUDA(dev_alloc(&ctx->d_sched, 1));
   CREATE_CUDA(cudaMemsetAsync(ctx->d_err, 0, sizeof(int), ctx->stream));
   std::vector<ngsd_tile> tiles = make_tiles((uint32_t) ctx->RB);
@@ -269,7 +275,11 @@ int ngsd_destroy(ngsd_ctx *ctx) {
   cudaFree(ctx->d_out); cudaFree(ctx->d_num); cudaFree(ctx->d_cntout);
   cudaFree(ctx->d_cache); cudaFree(ctx->d_cnt_cache); cudaFree(ctx->d_ent_begin); cudaFree(ctx->d_tile_index); cudaFree(ctx->d_pairs);
   cudaFree(ctx->codes); cudaFree(ctx->d_wsite); cudaFree(ctx->d_word_layer); cudaFree(ctx->d_word_ids);
+  cudaFree(ctx->d_defer); cudaFree(ctx->d_defer_n); cudaFree(ctx->d_blank);
+  cudaFree(ctx->d_def_rowptr); cudaFree(ctx->d_def_rowind); cudaFree(ctx->d_def_site); cudaFree(ctx->d_def_delta); cudaFree(ctx->d_fix);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);
+  if (ctx->h_pin2) cudaFreeHost(ctx->h_pin2);
+  cudaFree(ctx->d_cs_begin); cudaFree(ctx->d_cnt_part);
   for (auto &e : ctx->ev) if (e) cudaEventDestroy(e);
   for (int b = 0; b < 2; b++) {
     if (ctx->stage_free[b]) cudaEventDestroy(ctx->stage_free[b]);
@@ -296,6 +306,12 @@ static int check_push(ngsd_ctx *ctx, uint64_t site0, uint64_t n) {
 }
 
 static void mark_pushed(ngsd_ctx *ctx, uint64_t site0, uint64_t n) {
+  if (!ctx->deficit.empty()) {   // sites pushed again: what the earlier push recorded for them is void
+    auto &v = ctx->deficit;
+    v.erase(std::remove_if(v.begin(), v.end(), [&](const ngsd_ctx::deficit_entry &e) { return e.site >= site0 && e.site < site0 + n; }), v.end());
+    ctx->deficit_dirty = true;
+    if (v.empty()) ctx->def_rows = 0;
+  }
   for (uint64_t w = site0 / 64; w < (site0 + n + 63) / 64; w++)
     if (!ctx->pushed[w]) { ctx->pushed[w] = 1; ctx->words_pushed++; }
   ctx->frontend_done = false;
@@ -342,6 +358,7 @@ int ngsd_push_sites(ngsd_ctx *ctx, const double *raw_host, uint64_t site0, uint6
   const uint64_t bps = ctx->n_ind * 3 * sizeof(double);
   rc = ensure_staging(ctx, bps);
   if (rc) return rc;
+  ctx->stage_bps = bps;
   ctx->timing = ngsd_timing();
   tick(ctx, 0);
   int launches = 0;
@@ -373,19 +390,36 @@ int ngsd_push_genotypes(ngsd_ctx *ctx, const int8_t *codes_host, uint64_t site0,
   if (!codes_host) { ngsd_set_error(ctx, "null codes pointer"); return NGSD_ERR_ARG; }
   if (ctx->cfg.input_kind != NGSD_INPUT_GENOTYPES) { ngsd_set_error(ctx, "context expects genotype likelihoods"); return NGSD_ERR_ARG; }
   NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
-  int8_t *d = nullptr;
-  NGSD_CUDA(ctx, cudaMalloc((void **) &d, n * ctx->n_ind));
-  cudaError_t e = cudaMemcpyAsync(d, codes_host, n * ctx->n_ind, cudaMemcpyHostToDevice, ctx->stream);
+  // same double-buffered device staging as ngsd_push_sites: the copy of chunk k + 1 overlaps the front end of chunk k
+  const uint64_t bps = ctx->n_ind;
+  if (ctx->stage_dev[0] && ctx->stage_bps != bps) {
+    NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < 2; b++) { cudaFree(ctx->stage_dev[b]); ctx->stage_dev[b] = nullptr; }
+  }
+  rc = ensure_staging(ctx, bps);
+  if (rc) return rc;
+  ctx->stage_bps = bps;
   ctx->timing = ngsd_timing();
   tick(ctx, 0);
-  ngsd_frontend_args a{nullptr, d, site0, n};
-  if (e == cudaSuccess) e = ngsd_launch_frontend(ctx, a);
+  int launches = 0;
+  for (uint64_t off = 0; off < n; off += ctx->stage_sites) {
+    const uint64_t m = std::min(ctx->stage_sites, n - off);
+    const int b = ctx->stage_next;
+    ctx->stage_next ^= 1;
+    int8_t *d = reinterpret_cast<int8_t *>(ctx->stage_dev[b]);
+    NGSD_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[b], 0));
+    NGSD_CUDA(ctx, cudaMemcpyAsync(d, codes_host + off * ctx->n_ind, m * bps, cudaMemcpyHostToDevice, ctx->copy_stream));
+    NGSD_CUDA(ctx, cudaEventRecord(ctx->stage_ready[b], ctx->copy_stream));
+    NGSD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->stage_ready[b], 0));
+    ngsd_frontend_args a{nullptr, d, site0 + off, m};
+    NGSD_CUDA(ctx, ngsd_launch_frontend(ctx, a));
+    NGSD_CUDA(ctx, cudaEventRecord(ctx->stage_free[b], ctx->stream));
+    launches++;
+  }
   tick(ctx, 1);
-  ctx->timing.launches = 1;
+  ctx->timing.launches = launches;
   ctx->timing.total_ms = -1.f;
-  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-  cudaFree(d);
-  NGSD_CUDA(ctx, e);
+  NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the caller may now reuse codes_host
   mark_pushed(ctx, site0, n);
   return NGSD_OK;
 }
@@ -462,14 +496,101 @@ int ngsd_frontend(ngsd_ctx *ctx) {
   return NGSD_OK;
 }
 
+// One triple through the reader-side normalisation and the front-end loop of main() exactly as the reference runs them
+// on the host, with the host's libm: read_data.cpp:37-45 / :83-99 (log, -inf clamp on the binary path, post_prob),
+// gen_func.cpp:135-151 (logsum), :73-98,886-914 (call_geno on log-scale values), ngsDist.cpp:172-173 (exp).
+static bool host_posterior(const ngsd_cfg &c, const double x[3], double p[3]) {
+  double L[3] = {x[0], x[1], x[2]};
+  const bool binary = c.input_kind == NGSD_INPUT_BINARY_GL;
+  if (!c.input_is_log)
+    for (int g = 0; g < 3; g++) {
+      L[g] = log(L[g]);
+      if (binary && L[g] == -INFINITY) L[g] = -1e15;
+    }
+  double M = L[0];
+  for (int g = 1; g < 3; g++) M = std::max(L[g], M);
+  double norm;
+  if (M == -INFINITY) {
+    norm = -INFINITY;
+  } else {
+    double sum = 0;
+    for (int g = 0; g < 3; g++) sum += exp(L[g] - M);
+    norm = log(sum) + M;
+  }
+  for (int g = 0; g < 3; g++) L[g] -= norm;
+  const bool ok = !(binary && (std::isnan(L[0]) || std::isnan(L[1]) || std::isnan(L[2])));
+  if (c.call_geno) {
+    int max_pos = 0, min_pos = 0;
+    double mx = -INFINITY, mn = INFINITY;
+    for (int g = 0; g < 3; g++) {
+      if (L[g] > mx) { max_pos = g; mx = L[g]; }
+      if (L[g] < mn) { min_pos = g; mn = L[g]; }
+    }
+    double max_pp = exp(L[max_pos]);
+    if (L[min_pos] == L[max_pos]) max_pp = -1;
+    if (max_pp < c.N_thresh)
+      for (int g = 0; g < 3; g++) L[g] = log((double) 1 / 3);
+    if (max_pp >= c.call_thresh) {
+      for (int g = 0; g < 3; g++) L[g] = -1e15;
+      L[max_pos] = log(1);
+    }
+  }
+  for (int g = 0; g < 3; g++) p[g] = exp(L[g]);
+  return ok;
+}
+
+// Knife-edge triples (ngsd_deferred): decided here with the host's libm, written back by k_patch.
+extern "C" int ngsd_frontend_resolve(ngsd_ctx *ctx) {
+  NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
+  unsigned n = 0;
+  NGSD_CUDA(ctx, cudaMemcpyAsync(&n, ctx->d_defer_n, sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+  NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (n == 0) return NGSD_OK;
+  n = std::min(n, ctx->defer_cap);
+  std::vector<ngsd_deferred> list(n);
+  NGSD_CUDA(ctx, cudaMemcpy(list.data(), ctx->d_defer, (size_t) n * sizeof(ngsd_deferred), cudaMemcpyDeviceToHost));
+  bool nan_found = false;
+  for (ngsd_deferred &d : list) {
+    double p[3];
+    if (!host_posterior(ctx->cfg, d.x, p)) nan_found = true;
+    const bool miss = fabs(p[0] - p[1]) < 1e-5 && fabs(p[1] - p[2]) < 1e-5;          // gen_func.cpp:862-868
+    const unsigned code = p[0] == 1.0 ? 0u : p[1] == 1.0 ? 1u : p[2] == 1.0 ? 2u : 3u;   // one-hot, or the uniform "missing" triple
+    d.flags = (miss ? 1u : 0u) | (code << 8);
+    d.x[0] = p[0]; d.x[1] = p[1]; d.x[2] = p[2];
+    if (ctx->planes == 2 && !ctx->int_path) {
+      const double delta = ((p[0] + p[1]) + p[2]) - 1.0;
+      if (fabs(delta) > 1e-9) { ctx->deficit.push_back({d.ind, d.site, delta}); ctx->deficit_dirty = true; }
+    }
+  }
+  NGSD_CUDA(ctx, cudaMemcpy(ctx->d_defer, list.data(), (size_t) n * sizeof(ngsd_deferred), cudaMemcpyHostToDevice));
+  NGSD_CUDA(ctx, ngsd_launch_patch(ctx, ctx->d_defer, n));
+  NGSD_CUDA(ctx, cudaMemsetAsync(ctx->d_defer_n, 0, sizeof(unsigned), ctx->stream));
+  if (nan_found) ctx->deferred_nan = true;
+  NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->deferred_total += n;
+  return NGSD_OK;
+}
+
 // The deferred error flags of the pushes so far (NaN on the binary path, genotype codes above 2).
 int ngsd_frontend_flags(ngsd_ctx *ctx) {
+  int rc0 = ngsd_frontend_resolve(ctx);
+  if (rc0) return rc0;
   NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
   int flags = 0;
   NGSD_CUDA(ctx, cudaMemcpyAsync(&flags, ctx->d_err, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->deferred_nan) flags |= 1;
   if (flags & 1) { ngsd_set_error(ctx, "NaN found! Is the file format correct?"); return NGSD_ERR_NAN; }
   if (flags & 2) { ngsd_set_error(ctx, "wrong GENO file format. Genotypes must be coded as {-1,0,1,2} !"); return NGSD_ERR_GENO; }
+  if (flags & 16) {
+    ngsd_set_error(ctx, "all-zero likelihood triples with a site-sharded front end over several processes: create the contexts with ngsd_cfg.reserved bit 0 (three operand planes)");
+    return NGSD_ERR_ARG;
+  }
+  ctx->any_blank = (flags & 4) != 0;
+  if (ctx->any_blank) {        // sites that were empty text lines: the integer path gives them weight 0 (distances_int)
+    ctx->h_blank.resize(ctx->NW);
+    NGSD_CUDA(ctx, cudaMemcpy(ctx->h_blank.data(), ctx->d_blank, ctx->NW * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+  }
   return NGSD_OK;
 }
 
@@ -525,6 +646,49 @@ static uint64_t build_count_entries(const ngsd_ctx *ctx, const uint32_t *block_c
 
 static int ensure_dist_buffers(ngsd_ctx *ctx, uint64_t slots);
 static int ensure_entries(ngsd_ctx *ctx, uint64_t n);
+
+// Row triples that do not sum to one (2-plane mode, see ngsd_ctx::deficit): CSR by individual, last push of a site wins.
+static int upload_deficit(ngsd_ctx *ctx) {
+  if (!ctx->deficit_dirty && ctx->d_fix) return NGSD_OK;
+  auto &v = ctx->deficit;
+  std::stable_sort(v.begin(), v.end(), [](const ngsd_ctx::deficit_entry &a, const ngsd_ctx::deficit_entry &b) {
+    return a.ind != b.ind ? a.ind < b.ind : a.site < b.site;
+  });
+  std::vector<ngsd_ctx::deficit_entry> u;
+  for (size_t k = 0; k < v.size(); k++) {
+    if (!u.empty() && u.back().ind == v[k].ind && u.back().site == v[k].site) u.back() = v[k];
+    else u.push_back(v[k]);
+  }
+  v.swap(u);
+  std::vector<uint32_t> rowptr, rowind;
+  std::vector<uint64_t> site(v.size());
+  std::vector<double> delta(v.size());
+  for (size_t k = 0; k < v.size(); k++) {
+    if (rowind.empty() || rowind.back() != v[k].ind) { rowind.push_back(v[k].ind); rowptr.push_back((uint32_t) k); }
+    site[k] = v[k].site;
+    delta[k] = v[k].delta;
+  }
+  rowptr.push_back((uint32_t) v.size());
+  if (v.size() > ctx->def_cap) {
+    cudaFree(ctx->d_def_rowptr); cudaFree(ctx->d_def_rowind); cudaFree(ctx->d_def_site); cudaFree(ctx->d_def_delta);
+    ctx->d_def_rowptr = ctx->d_def_rowind = nullptr; ctx->d_def_site = nullptr; ctx->d_def_delta = nullptr;
+    ctx->def_cap = 0;
+    const uint64_t cap = v.size() * 2 + 16;
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_def_rowptr, cap + 1));
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_def_rowind, cap));
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_def_site, cap));
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_def_delta, cap));
+    ctx->def_cap = cap;
+  }
+  if (!ctx->d_fix) NGSD_CUDA(ctx, dev_alloc(&ctx->d_fix, ctx->n_ind * ctx->n_ind));
+  NGSD_CUDA(ctx, cudaMemcpy(ctx->d_def_rowptr, rowptr.data(), rowptr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  NGSD_CUDA(ctx, cudaMemcpy(ctx->d_def_rowind, rowind.data(), rowind.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  NGSD_CUDA(ctx, cudaMemcpy(ctx->d_def_site, site.data(), site.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  NGSD_CUDA(ctx, cudaMemcpy(ctx->d_def_delta, delta.data(), delta.size() * sizeof(double), cudaMemcpyHostToDevice));
+  ctx->def_rows = (uint32_t) rowind.size();
+  ctx->deficit_dirty = false;
+  return NGSD_OK;
+}
 
 // One matrix on the called-genotype integer path (K2c dist_imma.cu): same contract as ngsd_distances.
 static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_blocks, uint64_t block_size, double *out,
@@ -594,10 +758,20 @@ static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n
       }
     }
   }
+  // Sites that were empty text lines hold (0,0,0) in the reference (read_data.cpp:58-59): nothing to add for any pair,
+  // but still counted without --pairwise_del.  A 2-bit code cannot say that, a site weight of 0 can.
+  const bool blanks = ctx->any_blank && !ctx->cfg.pairwise_del;
+  if (blanks)
+    for (uint64_t w = 0; w < NW; w++)
+      for (uint64_t m = ctx->h_blank[w]; m; m &= m - 1)
+        for (uint32_t l = 0; l < layers; l++) h_w[(uint64_t) l * nsp + w * 64 + (uint64_t) __builtin_ctzll(m)] = 0;
   uint64_t n_words = 0;
   if (use_cache) {                                             // identity word list over the blocks in use
     n_words = n_blocks * (block_size / 64);
-    for (uint64_t w = 0; w < n_words && build_cache; w++) { h_ids[w] = (uint32_t) w; h_layer[w] = 0x80000000u; }   // bit 31: all 64 weights are 1
+    for (uint64_t w = 0; w < n_words && build_cache; w++) {   // bit 31: all 64 weights are 1
+      h_ids[w] = (uint32_t) w;
+      h_layer[w] = (blanks && ctx->h_blank[w]) ? 0u : 0x80000000u;
+    }
   }
   for (uint32_t l = 0; l < layers && !use_cache; l++)
     for (uint64_t w = 0; w < NW; w++) {
@@ -770,6 +944,107 @@ static int ensure_entries(ngsd_ctx *ctx, uint64_t n) {
   return NGSD_OK;
 }
 
+// --pairwise_del counts of the FP64 path as an int8 GEMM on the tensor cores (north_star (3): "integer mask GEMM"):
+// per-site weight bytes (bootstrap multiplicities, layers of <= 127), the list of 64-site words with a non-zero weight,
+// K splits for load balance, then k_dist_umma<true> + k_cnt_reduce into ctx->d_cnt.  Queued on ctx->stream.
+static int count_on_tensor_cores(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_blocks, uint64_t block_size, uint32_t maxw, int *launches) {
+  const bool weighted = block_counts != nullptr;
+  const uint64_t NW = ctx->NW, nsp = NW * 64;
+  const uint32_t layers = (maxw + 126) / 127;
+  const uint64_t bytes_w = (uint64_t) layers * nsp, n_list = (uint64_t) layers * NW;
+  const uint64_t need = ((bytes_w + 63) / 64) * 64 + 2 * n_list * sizeof(uint32_t) + 64;
+  if (ctx->h_pin2_bytes < need) {
+    if (ctx->h_pin2) cudaFreeHost(ctx->h_pin2);
+    ctx->h_pin2 = nullptr;
+    ctx->h_pin2_bytes = 0;
+    NGSD_CUDA(ctx, cudaHostAlloc(&ctx->h_pin2, need, cudaHostAllocDefault));
+    ctx->h_pin2_bytes = need;
+  }
+  uint8_t *h_w = (uint8_t *) ctx->h_pin2;
+  uint32_t *h_ids = (uint32_t *) (h_w + ((bytes_w + 63) / 64) * 64), *h_layer = h_ids + n_list;
+  memset(h_w, 0, bytes_w);
+  if (!weighted) {
+    memset(h_w, 1, ctx->n_sites);
+  } else {
+    for (uint64_t b = 0; b < n_blocks; b++) {
+      uint32_t left = block_counts[b];
+      for (uint32_t l = 0; l < layers && left; l++) {
+        const uint32_t w = std::min<uint32_t>(left, 127);
+        memset(h_w + (uint64_t) l * nsp + b * block_size, (int) w, block_size);
+        left -= w;
+      }
+    }
+  }
+  uint64_t n_words = 0;
+  for (uint32_t l = 0; l < layers; l++)
+    for (uint64_t w = 0; w < NW; w++) {
+      const uint64_t *p8 = (const uint64_t *) (h_w + (uint64_t) l * nsp + w * 64);
+      if (p8[0] | p8[1] | p8[2] | p8[3] | p8[4] | p8[5] | p8[6] | p8[7]) {
+        const uint64_t one = 0x0101010101010101ull;
+        const bool unit = (p8[0] & p8[1] & p8[2] & p8[3] & p8[4] & p8[5] & p8[6] & p8[7]) == one && (p8[0] | p8[1] | p8[2] | p8[3] | p8[4] | p8[5] | p8[6] | p8[7]) == one;
+        h_ids[n_words] = (uint32_t) w;
+        h_layer[n_words] = l | (unit ? 0x80000000u : 0u);
+        n_words++;
+      }
+    }
+  if (n_words == 0) {
+    NGSD_CUDA(ctx, cudaMemsetAsync(ctx->d_cnt, 0, ctx->n_pad * ctx->n_pad * sizeof(uint32_t), ctx->stream));
+    return NGSD_OK;
+  }
+  std::vector<uint32_t> splits = plan_splits((uint32_t) n_words, ctx->n_tiles, (double) ctx->n_tiles, ctx->n_sm);
+  {   // an int32 accumulator holds 127 * 64 per word
+    const uint32_t cap = 2147483647u / (127u * 64u);
+    std::vector<uint32_t> cut;
+    cut.push_back(0);
+    for (size_t k = 1; k < splits.size(); k++) {
+      while (splits[k] - cut.back() > cap) cut.push_back(cut.back() + cap);
+      if (splits[k] > cut.back()) cut.push_back(splits[k]);
+    }
+    splits.swap(cut);
+  }
+  const uint32_t n_splits = (uint32_t) splits.size() - 1;
+  if (bytes_w > ctx->wsite_cap) {
+    cudaFree(ctx->d_wsite);
+    ctx->d_wsite = nullptr;
+    ctx->wsite_cap = 0;
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_wsite, bytes_w));
+    ctx->wsite_cap = bytes_w;
+  }
+  if (n_list > ctx->word_cap) {
+    cudaFree(ctx->d_word_ids);
+    cudaFree(ctx->d_word_layer);
+    ctx->d_word_ids = ctx->d_word_layer = nullptr;
+    ctx->word_cap = 0;
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_word_ids, n_list));
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_word_layer, n_list));
+    ctx->word_cap = n_list;
+  }
+  if (splits.size() > ctx->cs_cap) {
+    cudaFree(ctx->d_cs_begin);
+    ctx->d_cs_begin = nullptr;
+    ctx->cs_cap = 0;
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_cs_begin, splits.size() + 64));
+    ctx->cs_cap = (uint32_t) splits.size() + 64;
+  }
+  const uint64_t part = (uint64_t) n_splits * ctx->n_tiles * NGSD_TILE_ELEMS;
+  if (part > ctx->cnt_part_ints) {
+    cudaFree(ctx->d_cnt_part);
+    ctx->d_cnt_part = nullptr;
+    ctx->cnt_part_ints = 0;
+    NGSD_CUDA(ctx, dev_alloc(&ctx->d_cnt_part, part));
+    ctx->cnt_part_ints = part;
+  }
+  NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_cs_begin, splits.data(), splits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));   // pageable: staged before return
+  NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_wsite, h_w, bytes_w, cudaMemcpyHostToDevice, ctx->stream));
+  NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_word_ids, h_ids, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_word_layer, h_layer, n_words * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+  if (ctx->shard_world > 1) NGSD_CUDA(ctx, cudaMemsetAsync(ctx->d_cnt, 0, ctx->n_pad * ctx->n_pad * sizeof(uint32_t), ctx->stream));
+  ngsd_count_umma_args ca{ctx->d_cs_begin, n_splits, ctx->d_cnt_part, ctx->d_wsite, ctx->d_word_ids, ctx->d_word_layer};
+  NGSD_CUDA(ctx, ngsd_launch_count_umma(ctx, ca));
+  *launches += 2;
+  return NGSD_OK;
+}
+
 int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_blocks, uint64_t block_size, double *out,
                    double *num_opt, uint64_t *cnt_opt) {
   if (!ctx) return NGSD_ERR_ARG;
@@ -808,6 +1083,30 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
     }
   }
   if (ctx->int_path) return distances_int(ctx, block_counts, n_blocks, block_size, out, num_opt, cnt_opt);
+  if (em_path && ctx->any_blank && !ctx->cfg.pairwise_del) {
+    // An empty text line is (0,0,0) for every individual (read_data.cpp:58-59); em2 on it divides 0 by 0
+    // (emOptim2.cpp:69-75 normalize), so every pair's sum turns NaN as soon as one such site is in the replicate.
+    bool hit = false;
+    for (uint64_t w = 0; w < ctx->NW && !hit; w++)
+      for (uint64_t m = ctx->h_blank[w]; m && !hit; m &= m - 1) {
+        const uint64_t s_ = w * 64 + (uint64_t) __builtin_ctzll(m);
+        hit = weighted ? (s_ < n_eff && block_counts[s_ / block_size] > 0) : true;
+      }
+    if (hit) {
+      int rc0 = ensure_dist_buffers(ctx, 1);
+      if (rc0) return rc0;
+      const uint64_t n2z = ctx->n_ind * ctx->n_ind;
+      NGSD_CUDA(ctx, cudaMemsetAsync(ctx->d_num, 0xFF, n2z * sizeof(double), ctx->stream));   // all-ones = the negative quiet NaN x86 gives 0/0
+      NGSD_CUDA(ctx, ngsd_launch_finish(ctx, n_eff));
+      if (out) NGSD_CUDA(ctx, cudaMemcpyAsync(out, ctx->d_out, n2z * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      if (num_opt) NGSD_CUDA(ctx, cudaMemcpyAsync(num_opt, ctx->d_num, n2z * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+      if (cnt_opt) NGSD_CUDA(ctx, cudaMemcpyAsync(cnt_opt, ctx->d_cntout, n2z * sizeof(uint64_t), cudaMemcpyDeviceToHost, ctx->stream));
+      NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      ctx->timing = ngsd_timing();
+      ctx->timing.launches = 1;
+      return NGSD_OK;
+    }
+  }
   const uint64_t SC = (uint64_t) ctx->sc;
   const uint64_t NCu = (ctx->n_sites + SC - 1) / SC;   // chunks that hold data
 
@@ -907,7 +1206,8 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
     }
   }
   const bool cnt_cacheable = use_cache && ctx->cfg.pairwise_del && n_blocks <= 65535 && ctx->d_cnt_cache != nullptr;
-  if (ctx->cfg.pairwise_del && !cnt_cacheable) n_entries = build_count_entries(ctx, block_counts, n_blocks, block_size, maxw, h_ew, h_em);
+  const bool tc_count_planned = ctx->cfg.pairwise_del && !cnt_cacheable && ngsd_use_umma() && !getenv("NGSD_COUNT_POPC");
+  if (ctx->cfg.pairwise_del && !cnt_cacheable && !tc_count_planned) n_entries = build_count_entries(ctx, block_counts, n_blocks, block_size, maxw, h_ew, h_em);
 
   if (ctx->n_tiles == 0) {   // a tile shard that owns nothing: all-zero contribution
     int rc0 = ensure_dist_buffers(ctx, 1);
@@ -1037,8 +1337,16 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
     NGSD_CUDA(ctx, cudaMemcpyAsync(ctx->d_ent_begin, ent_begin.data(), ent_begin.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
   int launches = 0;
   const bool do_count = ctx->cfg.pairwise_del != 0;
-  const bool run_count = do_count && !(cnt_cached && !build_cache);   // cached counts of this geometry are resident
+  bool run_count = do_count && !(cnt_cached && !build_cache);   // cached counts of this geometry are resident
   tick(ctx, 2);
+  const bool tc_count = run_count && !cnt_cached && ngsd_use_umma() && !getenv("NGSD_COUNT_POPC");
+  if (tc_count) {   // counts on the int8 tensor cores, ahead of the contraction on the same stream (mask_count.cu stays for the block cache)
+    NGSD_CUDA(ctx, cudaEventRecord(ctx->ev[6], ctx->stream));
+    int rcc = count_on_tensor_cores(ctx, block_counts, n_blocks, block_size, maxw, &launches);
+    if (rcc) return rcc;
+    NGSD_CUDA(ctx, cudaEventRecord(ctx->ev[7], ctx->stream));
+    run_count = false;
+  }
   if (run_count) NGSD_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));   // entry lists are on the device
   tick(ctx, 3);
   // K2 / K2b first, so that its persistent CTAs own every SM; K3 is then launched on the auxiliary stream and its
@@ -1070,6 +1378,12 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   if (!em_path && ctx->planes == 2) {
     NGSD_CUDA(ctx, ngsd_launch_cvec(ctx, weighted, n_eff));
     launches++;
+    if (!ctx->deficit.empty()) {
+      int rcd = upload_deficit(ctx);
+      if (rcd) return rcd;
+      NGSD_CUDA(ctx, ngsd_launch_deficit_fix(ctx, weighted, n_eff));
+      launches++;
+    }
   }
   if (em_path) {
     NGSD_CUDA(ctx, ngsd_launch_epilogue_em(ctx, em_splits, n_eff, do_count));
@@ -1091,7 +1405,7 @@ int ngsd_distances(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n_block
   NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   float ms;
   ctx->timing.count_ms = 0;
-  if (run_count) { cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ctx->timing.count_ms = ms; }   // overlaps dist_ms
+  if (run_count || tc_count) { cudaEventElapsedTime(&ms, ctx->ev[6], ctx->ev[7]); ctx->timing.count_ms = ms; }   // K3 overlaps dist_ms; the tensor-core count precedes it
   cudaEventElapsedTime(&ms, ctx->ev[3], ctx->ev[4]); ctx->timing.dist_ms = ms;
   cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[5]); ctx->timing.epilogue_ms = ms;
   cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[5]); ctx->timing.total_ms = ms;
@@ -1241,6 +1555,14 @@ int ngsd_get_timing(const ngsd_ctx *ctx, ngsd_timing *t) {
     c->timing.total_ms = ms;
   }
   *t = c->timing;
+  return NGSD_OK;
+}
+
+int ngsd_deferred_stats(const ngsd_ctx *ctx, uint64_t *host_evaluated) {
+  if (!ctx || !host_evaluated) return NGSD_ERR_ARG;
+  uint64_t n = ctx->deferred_total;
+  for (const ngsd_ctx *k : ctx->kids) n += k->deferred_total;
+  *host_evaluated = n;
   return NGSD_OK;
 }
 

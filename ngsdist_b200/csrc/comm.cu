@@ -56,6 +56,16 @@ __global__ void k_tri_unpack(const T *__restrict__ tri, uint64_t n, T *__restric
   else full[idx] = tri[i < j ? tri_index(i, j, n) : tri_index(j, i, n)];
 }
 
+// error / information bits of the front end (ngsd_ctx::d_err) as one int per bit, so that a max-reduce is a bitwise OR
+__global__ void k_flags_split(const int *err, int *bits) { if (threadIdx.x < 8) bits[threadIdx.x] = (*err >> threadIdx.x) & 1; }
+__global__ void k_flags_merge(int *err, const int *bits) {
+  if (threadIdx.x == 0) {
+    int v = 0;
+    for (int b = 0; b < 8; b++) v |= (bits[b] ? 1 : 0) << b;
+    *err |= v;
+  }
+}
+
 ncclComm_t comm_of(const ngsd_ctx *c) { return (ncclComm_t) c->comm; }
 
 int ensure_events(ngsd_ctx *c) {
@@ -198,6 +208,7 @@ void site_range_segments(ngsd_ctx *c, uint64_t s0, uint64_t s1, bool last, std::
       out.push_back({(char *) (c->Apack + (rb * c->NC + c0) * NGSD_TILE_DOUBLES), (c1 - c0) * NGSD_TILE_BYTES});
       out.push_back({(char *) (c->Bpack + (rb * c->NC + c0) * NGSD_TILE_DOUBLES), (c1 - c0) * NGSD_TILE_BYTES});
     }
+    if (rb == 0 && w1 > w0) out.push_back({(char *) (c->d_blank + w0), (w1 - w0) * sizeof(uint64_t)});
     if (w1 > w0) {
       out.push_back({(char *) (c->mask + (rb * c->NW + w0) * 128), (w1 - w0) * 128 * sizeof(uint64_t)});
       if (c->int_path) out.push_back({(char *) (c->codes + (rb * c->NW + w0) * 512), (w1 - w0) * 512 * sizeof(uint32_t)});
@@ -219,11 +230,30 @@ int allgather_impl(ngsd_ctx *err_to, const std::vector<ngsd_ctx *> &cs, const ui
     }
   }
   std::vector<Seg> seg;
+  // knife-edge triples are settled by the host (and patched into the resident layout) BEFORE the pieces travel
+  bool any_deficit = false;
   for (ngsd_ctx *c : cs) {
     if (!c->comm) { ngsd_set_error(err_to, "no communicator: call ngsd_comm_attach first"); return NGSD_ERR_COMM; }
+    ngsd_frontend_resolve(c);                 // a failure here shows up again in ngsd_frontend_flags below
+    any_deficit |= !c->deficit.empty();
+  }
+  if (any_deficit && cs.size() == world) {    // one process: every GPU gets every row's deficit list
+    std::vector<ngsd_ctx::deficit_entry> all;
+    for (ngsd_ctx *c : cs) all.insert(all.end(), c->deficit.begin(), c->deficit.end());
+    for (ngsd_ctx *c : cs) { c->deficit = all; c->deficit_dirty = true; }
+    any_deficit = false;
+  }
+  for (ngsd_ctx *c : cs) {
     NGSD_CUDA(err_to, cudaSetDevice(c->device));
     int rc = ensure_events(c);
+    if (!rc) rc = ensure_tri(c, 8);
     if (rc) return rc;
+    if (any_deficit) {                        // one process per GPU: the lists are host state of other processes -> refuse on every rank
+      int f = 0;
+      NGSD_CUDA(err_to, cudaMemcpy(&f, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+      f |= 16;
+      NGSD_CUDA(err_to, cudaMemcpy(c->d_err, &f, sizeof(int), cudaMemcpyHostToDevice));
+    }
     NGSD_CUDA(err_to, cudaEventRecord(c->ev_comm[0], c->stream));
   }
   std::vector<uint64_t> moved(cs.size(), 0);
@@ -240,10 +270,18 @@ int allgather_impl(ngsd_ctx *err_to, const std::vector<ngsd_ctx *> &cs, const ui
     }
   }
   NGSD_NCCL(err_to, ncclGroupEnd());
-  // a front-end error on any rank (NaN, bad genotype code) must stop every rank: max-reduce the flag words
+  // a front-end error on any rank (NaN, bad genotype code) must stop every rank: OR-reduce the flag words
+  for (ngsd_ctx *c : cs) {
+    NGSD_CUDA(err_to, cudaSetDevice(c->device));
+    k_flags_split<<<1, 32, 0, c->stream>>>(c->d_err, reinterpret_cast<int *>(c->d_tri));
+  }
   NGSD_NCCL(err_to, ncclGroupStart());
-  for (ngsd_ctx *c : cs) NGSD_NCCL(err_to, ncclAllReduce(c->d_err, c->d_err, 1, ncclInt32, ncclMax, comm_of(c), c->stream));
+  for (ngsd_ctx *c : cs) NGSD_NCCL(err_to, ncclAllReduce(c->d_tri, c->d_tri, 8, ncclInt32, ncclMax, comm_of(c), c->stream));
   NGSD_NCCL(err_to, ncclGroupEnd());
+  for (ngsd_ctx *c : cs) {
+    NGSD_CUDA(err_to, cudaSetDevice(c->device));
+    k_flags_merge<<<1, 32, 0, c->stream>>>(c->d_err, reinterpret_cast<const int *>(c->d_tri));
+  }
   for (size_t k = 0; k < cs.size(); k++) {
     ngsd_ctx *c = cs[k];
     NGSD_CUDA(err_to, cudaSetDevice(c->device));

@@ -24,6 +24,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <algorithm>
+
 #include "ngsd_internal.h"
 
 namespace {
@@ -129,6 +131,7 @@ struct UmmaArgs {
   int32_t *partials;            // [n_units][pstride], sum tile row-major [128][128]
   uint64_t NW;
   uint32_t n_tiles, n_pairs, n_units, pstride;   // n_units = splits x n_pairs
+  uint32_t cnt_off;             // count pass: offset of the count tile inside a unit's slot (ints)
   uint32_t lut[4];
 };
 
@@ -440,7 +443,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
 #pragma unroll 1
       for (int c0 = 0; c0 < ncol; c0 += 32) {
         const uint32_t t = a.pairs[2 * p + (c0 >> 7)];
-        int4 *dst = reinterpret_cast<int4 *>(a.partials + ((uint64_t) q * a.n_tiles + t) * a.pstride + (COUNT ? NGSD_TILE_ELEMS : 0) +
+        int4 *dst = reinterpret_cast<int4 *>(a.partials + ((uint64_t) q * a.n_tiles + t) * a.pstride + (COUNT ? a.cnt_off : 0u) +
                                              (uint64_t) (qd * 32 + lane) * 128);
         uint32_t v[32];
         const uint32_t taddr = tmem + ((uint32_t) (qd * 32) << 16) + (uint32_t) c0;
@@ -551,6 +554,7 @@ cudaError_t ngsd_launch_dist_umma(ngsd_ctx *ctx, uint32_t n_units, int grid, uin
   a.pairs = ctx->d_pairs;
   a.n_units = ctx->n_tiles ? n_units / ctx->n_tiles * ctx->n_pairs : 0;     // (split, tile) units -> (split, tile pair) units
   a.pstride = pstride;
+  a.cnt_off = NGSD_TILE_ELEMS;
   for (int k = 0; k < 4; k++) a.lut[k] = ctx->int_lut[k];
   cudaError_t e = cudaMemsetAsync(ctx->d_sched, 0, sizeof(uint32_t), ctx->stream);
   if (e != cudaSuccess) return e;
@@ -558,5 +562,65 @@ cudaError_t ngsd_launch_dist_umma(ngsd_ctx *ctx, uint32_t n_units, int grid, uin
     k_dist_umma<true><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a);
   else
     k_dist_umma<false><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a);
+  return cudaGetLastError();
+}
+
+namespace {
+
+// shared-site counts of the FP64 path: K splits of the int8 count GEMM -> cnt [n_pad][n_pad]
+// grid (n_tiles, 16), block 256: one thread per int4 of the 128 x 128 tile
+__global__ void __launch_bounds__(256) k_cnt_reduce(const int32_t *__restrict__ partials, uint32_t n_splits, uint32_t n_tiles,
+                                                    const ngsd_tile *__restrict__ tiles, uint32_t *__restrict__ cnt, uint64_t n_pad) {
+  const uint32_t t = blockIdx.x, e = blockIdx.y * 256 + threadIdx.x;
+  const ngsd_tile tl = tiles[t];
+  const int4 *src = reinterpret_cast<const int4 *>(partials + (uint64_t) t * NGSD_TILE_ELEMS) + e;
+  const uint64_t stride = (uint64_t) n_tiles * (NGSD_TILE_ELEMS / 4);
+  int4 s = make_int4(0, 0, 0, 0);
+  for (uint32_t q = 0; q < n_splits; q++) {
+    const int4 v = src[(uint64_t) q * stride];
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+  }
+  const uint32_t row = e >> 5, col0 = (e & 31u) * 4u;
+  *reinterpret_cast<uint4 *>(cnt + ((uint64_t) tl.ti * NGSD_TILE + row) * n_pad + (uint64_t) tl.tj * NGSD_TILE + col0) =
+      make_uint4((uint32_t) s.x, (uint32_t) s.y, (uint32_t) s.z, (uint32_t) s.w);
+}
+
+}  // namespace
+
+// --pairwise_del counts of the FP64 path on the int8 tensor cores: cnt(i,j) = sum_s w_s m_i(s) m_j(s) from the presence
+// masks (k_dist_umma<true>, one byte per site), K splits reduced into ctx->d_cnt.  Replaces the AND+POPC kernel
+// (mask_count.cu) on the per-replicate path: 7x faster alone, and it does not have to share SMs with the contraction.
+cudaError_t ngsd_launch_count_umma(ngsd_ctx *ctx, const ngsd_count_umma_args &c) {
+  static bool attr_set[64] = {};
+  if (!attr_set[ctx->device & 63]) {
+    cudaError_t e = cudaFuncSetAttribute((const void *) k_dist_umma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) kSmemBytes);
+    if (e != cudaSuccess) return e;
+    attr_set[ctx->device & 63] = true;
+  }
+  UmmaArgs a;
+  a.codes = nullptr;
+  a.mask = ctx->mask;
+  a.wsite = c.wsite;
+  a.word_ids = c.word_ids;
+  a.word_layer = c.word_layer;
+  a.tiles = ctx->d_tiles;
+  a.split_begin = c.split_begin;
+  a.sched = ctx->d_sched;
+  a.partials = c.partials;
+  a.NW = ctx->NW;
+  a.n_tiles = ctx->n_tiles;
+  a.n_pairs = ctx->n_pairs;
+  a.pairs = ctx->d_pairs;
+  a.n_units = c.n_splits * ctx->n_pairs;
+  a.pstride = NGSD_TILE_ELEMS;
+  a.cnt_off = 0;
+  for (int k = 0; k < 4; k++) a.lut[k] = 0;
+  cudaError_t e = cudaMemsetAsync(ctx->d_sched, 0, sizeof(uint32_t), ctx->stream);
+  if (e != cudaSuccess) return e;
+  const int grid = (int) std::min<uint64_t>((uint64_t) ctx->n_sm, std::max<uint32_t>(a.n_units, 1u));
+  k_dist_umma<true><<<grid, kThreads, kSmemBytes, ctx->stream>>>(a);
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  k_cnt_reduce<<<dim3(ctx->n_tiles, 16), 256, 0, ctx->stream>>>(c.partials, c.n_splits, ctx->n_tiles, ctx->d_tiles, ctx->d_cnt, ctx->n_pad);
   return cudaGetLastError();
 }

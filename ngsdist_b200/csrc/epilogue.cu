@@ -14,6 +14,7 @@ struct EpiArgs {
   const uint32_t *cnt;        // [n_pad][n_pad] or nullptr
   const uint32_t *cnt_cache;  // per-block counts [n_splits][n_tiles][4][64][64] (bootstrap block cache) or nullptr
   const double *cvec;         // [n_pad] 2-plane mode: weighted row sums of the B_2 plane, added for column j; or nullptr
+  const double *fix;          // [n_ind][n_ind] 2-plane mode: correction for row triples that do not sum to one; or nullptr
   double *out, *num;          // [n_ind][n_ind]
   uint64_t *cntout;
   uint64_t n_ind, n_pad, const_cnt, tot_sites;
@@ -72,7 +73,8 @@ __global__ void __launch_bounds__(256) k_epilogue(EpiArgs a) {
   for (int c = 0; c < 2; c++) {
     const uint64_t j = j0 + c;
     if (i >= j || j >= a.n_ind) continue;
-    const double num = (c ? s1 : s0) + (a.cvec ? a.cvec[j] : 0.0);
+    double num = (c ? s1 : s0) + (a.cvec ? a.cvec[j] : 0.0);
+    if (a.fix) num += a.fix[i * a.n_ind + j];
     uint64_t cnt = a.cnt ? (uint64_t) a.cnt[i * a.n_pad + j] : a.const_cnt;
     if (a.cnt_cache) {        // sum_b c[b] * cnt_b(i,j): integers, exact
       const int rr = row, cc = col0 + c;
@@ -138,7 +140,35 @@ __global__ void __launch_bounds__(256) k_cvec(const double *__restrict__ C, uint
   if (threadIdx.x == 0) cvec[blockIdx.x] = red[0];
 }
 
+// 2-plane mode, rows holding a triple with p0 + p1 + p2 = 1 + delta: the contraction used p2 = 1 - p0 - p1, so
+// delta * w_s * B_2(j, s) is missing from num(i, j) for every j > i.  One block per such row, entries in (site) order.
+__global__ void __launch_bounds__(256) k_deficit_fix(const uint32_t *__restrict__ row_ptr, const uint32_t *__restrict__ row_ind,
+                                                    const uint64_t *__restrict__ site, const double *__restrict__ delta,
+                                                    const double *__restrict__ w, uint64_t n_eff, const double *__restrict__ C, uint64_t n_pad,
+                                                    uint64_t n_ind, double *__restrict__ fix) {
+  const uint64_t i = row_ind[blockIdx.x];
+  const uint32_t e0 = row_ptr[blockIdx.x], e1 = row_ptr[blockIdx.x + 1];
+  for (uint64_t j = i + 1 + threadIdx.x; j < n_ind; j += blockDim.x) {
+    double acc = 0;
+    for (uint32_t e = e0; e < e1; e++) {
+      const uint64_t s = site[e];
+      if (s >= n_eff) continue;
+      const double ws = w ? w[s] : 1.0;
+      acc += delta[e] * ws * C[((s >> 6) * n_pad + j) * 64 + (s & 63)];
+    }
+    fix[i * n_ind + j] = acc;
+  }
+}
+
 }  // namespace
+
+cudaError_t ngsd_launch_deficit_fix(ngsd_ctx *ctx, bool weighted, uint64_t n_eff) {
+  cudaError_t e = cudaMemsetAsync(ctx->d_fix, 0, ctx->n_ind * ctx->n_ind * sizeof(double), ctx->stream);
+  if (e != cudaSuccess) return e;
+  k_deficit_fix<<<ctx->def_rows, 256, 0, ctx->stream>>>(ctx->d_def_rowptr, ctx->d_def_rowind, ctx->d_def_site, ctx->d_def_delta,
+                                                       weighted ? ctx->d_weights : nullptr, n_eff, ctx->Cplane, ctx->n_pad, ctx->n_ind, ctx->d_fix);
+  return cudaGetLastError();
+}
 
 cudaError_t ngsd_launch_cvec(ngsd_ctx *ctx, bool weighted, uint64_t n_eff) {
   k_cvec<<<(unsigned) ctx->n_pad, 256, 0, ctx->stream>>>(ctx->Cplane, ctx->ldc, weighted ? ctx->d_weights : nullptr, n_eff, ctx->d_cvec);
@@ -160,6 +190,7 @@ cudaError_t ngsd_launch_epilogue(ngsd_ctx *ctx, const ngsd_epilogue_args &e) {
   a.cnt = (e.use_cnt && !ctx->cur_cnt_cache) ? ctx->d_cnt : nullptr;
   a.cnt_cache = e.use_cnt ? ctx->cur_cnt_cache : nullptr;
   a.cvec = ctx->planes == 2 ? ctx->d_cvec : nullptr;
+  a.fix = (ctx->planes == 2 && ctx->def_rows) ? ctx->d_fix : nullptr;
   a.out = ctx->d_out;
   a.num = ctx->d_num;
   a.cntout = ctx->d_cntout;

@@ -9,6 +9,8 @@
 //
 // HBM-bound by design: 24 B read + 48 B written per individual-site; one thread owns 4 consecutive sites of one
 // individual so that every global store is a full 32-byte sector and a warp stores 1 KiB contiguous per plane.
+#include <algorithm>
+
 #include "ngsd_internal.h"
 
 namespace {
@@ -31,13 +33,46 @@ struct FrontCfg {
   int int_path;      // called genotypes: write 2-bit codes for dist_imma.cu instead of FP64 planes
   double N_thresh, call_thresh;
   double score[9];
+  ngsd_deferred *defer;      // knife-edge triples handed to the host's libm (api.cu resolve_deferred)
+  unsigned *defer_n;
+  unsigned defer_cap;
+  uint64_t *blank;           // [NW] bit = site came from an empty text line (read_data.cpp:58-59)
 };
 
+constexpr double kKnife = 1e-11;                     // half-width of the band around a comparison threshold that goes to the host
+
+// An empty text line leaves the reference's geno at its -1e15 fill for every individual and skips post_prob
+// (read_data.cpp:58-59): the host marks such a site with this NaN payload (doubles) or code -128 (genotypes).
+__device__ __forceinline__ bool is_blank(double x0) { return (unsigned long long) __double_as_longlong(x0) == NGSD_BLANK_SITE_BITS; }
+
+__device__ __forceinline__ void defer_triple(const FrontCfg &c, uint64_t site, uint64_t ind, double x0, double x1, double x2, int *err) {
+  const unsigned k = atomicAdd(c.defer_n, 1u);
+  if (k < c.defer_cap) {
+    ngsd_deferred d;
+    d.site = site; d.ind = (uint32_t) ind; d.flags = 0; d.x[0] = x0; d.x[1] = x1; d.x[2] = x2;
+    c.defer[k] = d;
+  } else {
+    atomicOr(err, 8);        // list full: this triple keeps the device's own evaluation
+  }
+}
+
+// |p0-p1| or |p1-p2| within kKnife of EPSILON while the other does not already decide miss_data (gen_func.cpp:862-868)
+__device__ __forceinline__ bool miss_knife(const double p[3]) {
+  const double d01 = fabs(p[0] - p[1]), d12 = fabs(p[1] - p[2]);
+  return (fabs(d01 - kEps) < kKnife && d12 < kEps + kKnife) || (fabs(d12 - kEps) < kKnife && d01 < kEps + kKnife);
+}
+
 // Normal-space posterior triple of one individual-site, following the reference step by step.
-// Returns false when a NaN was produced on the binary path (fatal in the reference).
-__device__ __forceinline__ bool posterior(const FrontCfg &c, double x0, double x1, double x2, double p[3]) {
+// Returns false when a NaN was produced on the binary path (fatal in the reference).  *knife is set when one of the
+// reference's comparisons (first strict maximum, exact tie, N_thresh, call_thresh, EPSILON) is within kKnife of flipping:
+// the device's log / exp are within 1 ulp of glibc's, not identical, so those triples are re-evaluated on the host.
+__device__ __forceinline__ bool posterior(const FrontCfg &c, double x0, double x1, double x2, double p[3], bool *knife) {
   double L[3] = {x0, x1, x2};
-  if (!c.in_log) {
+  *knife = false;
+  const bool blank = is_blank(x0);
+  if (blank) {
+    L[0] = L[1] = L[2] = kNegInfClamp;      // the untouched fill; post_prob never ran
+  } else if (!c.in_log) {
 #pragma unroll
     for (int g = 0; g < 3; g++) {
       L[g] = log(L[g]);
@@ -49,7 +84,9 @@ __device__ __forceinline__ bool posterior(const FrontCfg &c, double x0, double x
   M = (L[1] >= M ? L[1] : M);
   M = (L[2] >= M ? L[2] : M);
   double norm;
-  if (M == -INFINITY) {
+  if (blank) {
+    norm = 0;
+  } else if (M == -INFINITY) {
     norm = -INFINITY;
   } else {
     double sum = 0;
@@ -73,6 +110,12 @@ __device__ __forceinline__ bool posterior(const FrontCfg &c, double x0, double x
     }
     double max_pp = exp(L[max_pos]);
     if (L[min_pos] == L[max_pos]) max_pp = -1;                      // gen_func.cpp:895-897 (miss_data == 0)
+    else {
+      // runner-up within kKnife of the maximum (array_max_pos / the exact-tie test could go the other way), or max_pp
+      // within kKnife of a threshold it is compared with
+      const double second = max_pos == 0 ? fmax(L[1], L[2]) : max_pos == 1 ? fmax(L[0], L[2]) : fmax(L[0], L[1]);
+      if (mx - second < kKnife || fabs(max_pp - c.N_thresh) < kKnife || fabs(max_pp - c.call_thresh) < kKnife) *knife = true;
+    }
     bool to_missing = max_pp < c.N_thresh;                          // :903-905
     bool to_call = max_pp >= c.call_thresh;                         // :908-913
     if (to_call) {
@@ -87,6 +130,7 @@ __device__ __forceinline__ bool posterior(const FrontCfg &c, double x0, double x
   }
 #pragma unroll
   for (int g = 0; g < 3; g++) p[g] = exp(L[g]);                     // ngsDist.cpp:172-173
+  if (!blank && miss_knife(p)) *knife = true;
   return ok;
 }
 
@@ -98,8 +142,13 @@ __device__ __forceinline__ bool posterior(const FrontCfg &c, double x0, double x
 // inside the 1e-9 budget on distances.  Reference corner cases are reproduced explicitly:
 //   x_g == 0 -> p_g = 0 (exp(-1e15 - norm) underflows to 0);  all three 0 on the binary path -> exp(-1.125) each
 //   (SURVEY App. E-11);  negative / NaN input -> NaN -> fatal on the binary path.
-__device__ __forceinline__ bool posterior_fast(const FrontCfg &c, double x0, double x1, double x2, double p[3]) {
+__device__ __forceinline__ bool posterior_fast(const FrontCfg &c, double x0, double x1, double x2, double p[3], bool *knife) {
   double e0 = x0, e1 = x1, e2 = x2;
+  *knife = false;
+  if (is_blank(x0)) {                           // exp(-1e15) three times (ngsDist.cpp:172-173 on the untouched fill)
+    p[0] = p[1] = p[2] = 0.0;
+    return true;
+  }
   if (c.in_log) {
     double M = x0;
     M = (x1 >= M ? x1 : M);
@@ -115,6 +164,7 @@ __device__ __forceinline__ bool posterior_fast(const FrontCfg &c, double x0, dou
     if (x0 < 0 || x1 < 0 || x2 < 0) e0 = NAN;   // log(negative) = NaN in the reference
     if (c.kind == NGSD_INPUT_BINARY_GL && x0 == 0 && x1 == 0 && x2 == 0) {
       p[0] = p[1] = p[2] = 0.32465246735834974;  // exp(-1.125): -1e15 - (-1e15 + log 3) after rounding
+      *knife = c.planes == 2;                    // does not sum to one: the host records its deficit for the 2-plane contraction
       return true;
     }
   }
@@ -124,6 +174,7 @@ __device__ __forceinline__ bool posterior_fast(const FrontCfg &c, double x0, dou
   p[2] = e2 / sum;
   bool ok = true;
   if (c.kind == NGSD_INPUT_BINARY_GL && (isnan(p[0]) || isnan(p[1]) || isnan(p[2]))) ok = false;
+  *knife = miss_knife(p);                       // x / sum and exp(log x - logsum) agree to ~1e-15: far inside the band
   return ok;
 }
 
@@ -231,11 +282,20 @@ __global__ void __launch_bounds__(512, EXACT ? 1 : 2) k_frontend(FrontCfg c, con
       bool ok;
       double p[3];
       if (codes) {
-        ok = posterior_from_code(code[q], p);
+        if (code[q] == NGSD_BLANK_SITE_CODE) {                     // empty text line: (0,0,0) after exp (read_data.cpp:58-59)
+          p[0] = p[1] = p[2] = 0.0;
+          ok = true;
+          if (i == 0) { atomicOr((unsigned long long *) &c.blank[(site0 + sl) >> 6], 1ull << ((site0 + sl) & 63)); bad |= 4; }
+        } else {
+          ok = posterior_from_code(code[q], p);
+        }
         if (!ok) bad |= 2;
       } else {
-        ok = EXACT ? posterior(c, A[q][0], A[q][1], A[q][2], p) : posterior_fast(c, A[q][0], A[q][1], A[q][2], p);
+        bool knife;
+        ok = EXACT ? posterior(c, A[q][0], A[q][1], A[q][2], p, &knife) : posterior_fast(c, A[q][0], A[q][1], A[q][2], p, &knife);
         if (!ok) bad |= 1;
+        if (knife) defer_triple(c, site0 + sl, i, A[q][0], A[q][1], A[q][2], err);
+        if (i == 0 && !c.call_geno && is_blank(A[q][0])) { atomicOr((unsigned long long *) &c.blank[(site0 + sl) >> 6], 1ull << ((site0 + sl) & 63)); bad |= 4; }
       }
       present = !miss_data(p);
       if (c.pairwise_del && !present) p[0] = p[1] = p[2] = 0;       // the skip of ngsDist.cpp:335-338, folded into the operands
@@ -299,7 +359,9 @@ __device__ __noinline__ unsigned called_code_exact(int kind, int in_log, double 
   c.kind = kind; c.in_log = in_log; c.call_geno = 1; c.pairwise_del = 0; c.planes = 3; c.int_path = 1;
   c.N_thresh = N_thresh; c.call_thresh = call_thresh;
   double p[3];
-  const bool ok = posterior(c, x0, x1, x2, p);
+  bool knife;
+  c.defer = nullptr; c.defer_n = nullptr; c.defer_cap = 0; c.blank = nullptr;
+  const bool ok = posterior(c, x0, x1, x2, p, &knife);
   const unsigned code = (p[0] == 1.0) ? 0u : (p[1] == 1.0) ? 1u : (p[2] == 1.0) ? 2u : 3u;   // one-hot or the uniform "missing" triple
   return code | (ok ? 0u : 4u);
 }
@@ -380,10 +442,12 @@ __global__ void __launch_bounds__(512, 2) k_frontend_codes(FrontCfg c, const dou
       cbits = (cbits & ~(3u << (2 * q))) | (cg << (2 * q));
     }
   }
-  if (need_exact) {                       // the reference's exact log-space sequence, values re-read (keeps the hot loop lean)
-    for (int q = 0; q < 4; q++) {
+  if (need_exact) {                       // the reference's exact log-space sequence, values re-read (keeps the hot loop lean);
+    for (int q = 0; q < 4; q++) {         // the host's libm has the last word on these triples (resolve_deferred)
       if (!((need_exact >> q) & 1u)) continue;
       const double *x = raw + ((s_local0 + q) * n_ind + i) * 3;
+      if (is_blank(x[0])) continue;       // empty text line under call_geno: max_pp = -1 -> missing (code 3 is already set)
+      defer_triple(c, site0 + s_local0 + q, i, x[0], x[1], x[2], err);
       unsigned cg = called_code_exact(c.kind, c.in_log, c.N_thresh, c.call_thresh, x[0], x[1], x[2]);
       if (cg & 4u) bad |= 1;
       cbits = (cbits & ~(3u << (2 * q))) | ((cg & 3u) << (2 * q));
@@ -416,7 +480,8 @@ __global__ void __launch_bounds__(512, 2) k_frontend_codes(FrontCfg c, const dou
 // block shape and output as k_frontend_codes without any of its floating-point state, so that it is a ~20-register
 // kernel that can share an SM with a persistent contraction CTA (a packed push overlapping another context's contraction).
 __global__ void __launch_bounds__(512, 4) k_codes_from_int8(const int8_t *__restrict__ codes, uint64_t n_ind, uint64_t site0, uint64_t n, uint64_t NW,
-                                                            uint32_t *__restrict__ codes_out, uint64_t *__restrict__ mask, int *__restrict__ err) {
+                                                            uint32_t *__restrict__ codes_out, uint64_t *__restrict__ mask, int *__restrict__ err,
+                                                            uint64_t *__restrict__ blank) {
   __shared__ unsigned cod[16][32];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const uint64_t i = (uint64_t) blockIdx.x * 32 + tx;
@@ -431,6 +496,10 @@ __global__ void __launch_bounds__(512, 4) k_codes_from_int8(const int8_t *__rest
       const int g = (int) codes[sl * n_ind + i];
       unsigned cg = g < 0 ? 3u : (unsigned) g;                       // -1 = missing
       if (g > 2) { bad = 2; cg = 3u; }
+      if (g == NGSD_BLANK_SITE_CODE && i == 0) {                     // empty text line: the site gets weight 0 in the contraction
+        atomicOr((unsigned long long *) &blank[(site0 + sl) >> 6], 1ull << ((site0 + sl) & 63));
+        bad |= 4;
+      }
       cbits = (cbits & ~(3u << (2 * q))) | (cg << (2 * q));
     }
   }
@@ -532,18 +601,96 @@ cudaError_t ngsd_launch_frontend(ngsd_ctx *ctx, const ngsd_frontend_args &a) {
   c.N_thresh = ctx->cfg.N_thresh;
   c.call_thresh = ctx->cfg.call_thresh;
   for (int k = 0; k < 9; k++) c.score[k] = ctx->cfg.score[k];
-  dim3 grid((unsigned) (ctx->n_pad / 32), (unsigned) ((a.n + 63) / 64)), block(32, 16);
-  if (ctx->int_path && a.codes)
-    k_codes_from_int8<<<grid, block, 0, ctx->stream>>>(a.codes, ctx->n_ind, a.site0, a.n, ctx->NW, ctx->codes, ctx->mask, ctx->d_err);
-  else if (ctx->int_path)
-    k_frontend_codes<<<grid, block, 0, ctx->stream>>>(c, a.raw, a.codes, ctx->n_ind, a.site0, a.n, ctx->NW, ctx->codes, ctx->mask,
-                                                      ctx->d_err);
-  else if (c.call_geno)
-    k_frontend<true><<<grid, block, 0, ctx->stream>>>(c, a.raw, a.codes, ctx->n_ind, a.site0, a.n, ctx->NC, ctx->NW, ctx->Apack,
-                                                      ctx->Bpack, ctx->Cplane, ctx->ldc, ctx->mask, ctx->d_err);
-  else
-    k_frontend<false><<<grid, block, 0, ctx->stream>>>(c, a.raw, a.codes, ctx->n_ind, a.site0, a.n, ctx->NC, ctx->NW, ctx->Apack,
-                                                       ctx->Bpack, ctx->Cplane, ctx->ldc, ctx->mask, ctx->d_err);
+  c.defer = ctx->d_defer;
+  c.defer_n = ctx->d_defer_n;
+  c.defer_cap = ctx->defer_cap;
+  c.blank = ctx->d_blank;
+  // grid.y is limited to 65535 blocks of 64 sites: a push of any size goes out as several launches
+  const uint64_t max_sites = (uint64_t) 65535 * 64;
+  for (uint64_t off = 0; off < a.n; off += max_sites) {
+    const uint64_t n = std::min(max_sites, a.n - off), site0 = a.site0 + off;
+    const double *raw = a.raw ? a.raw + off * ctx->n_ind * 3 : nullptr;
+    const int8_t *codes = a.codes ? a.codes + off * ctx->n_ind : nullptr;
+    dim3 grid((unsigned) (ctx->n_pad / 32), (unsigned) ((n + 63) / 64)), block(32, 16);
+    if (ctx->int_path && codes)
+      k_codes_from_int8<<<grid, block, 0, ctx->stream>>>(codes, ctx->n_ind, site0, n, ctx->NW, ctx->codes, ctx->mask, ctx->d_err, ctx->d_blank);
+    else if (ctx->int_path)
+      k_frontend_codes<<<grid, block, 0, ctx->stream>>>(c, raw, codes, ctx->n_ind, site0, n, ctx->NW, ctx->codes, ctx->mask, ctx->d_err);
+    else if (c.call_geno)
+      k_frontend<true><<<grid, block, 0, ctx->stream>>>(c, raw, codes, ctx->n_ind, site0, n, ctx->NC, ctx->NW, ctx->Apack, ctx->Bpack,
+                                                        ctx->Cplane, ctx->ldc, ctx->mask, ctx->d_err);
+    else
+      k_frontend<false><<<grid, block, 0, ctx->stream>>>(c, raw, codes, ctx->n_ind, site0, n, ctx->NC, ctx->NW, ctx->Apack, ctx->Bpack,
+                                                         ctx->Cplane, ctx->ldc, ctx->mask, ctx->d_err);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+  }
+  return cudaSuccess;
+}
+
+namespace {
+
+// Knife-edge triples after the host decided them with its own libm (api.cu resolve_deferred): one thread per entry
+// rewrites the triple's slots in the resident layout -- operand planes (or 2-bit code) and the presence bit.
+// d.x = the normal-space posterior as gen_dist reads it; d.flags bit 0 = miss_data() is true, bits 8..9 = the code.
+__global__ void k_patch(FrontCfg c, const ngsd_deferred *__restrict__ list, unsigned n, uint64_t n_pad, uint64_t NC, uint64_t NW,
+                        double *__restrict__ Apack, double *__restrict__ Bpack, double *__restrict__ Cplane, uint32_t *__restrict__ codes,
+                        uint64_t *__restrict__ mask) {
+  const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const ngsd_deferred d = list[k];
+  const uint64_t i = d.ind, s = d.site, rb = i >> 7, r = i & 127;
+  const bool present = !(d.flags & 1u);
+  unsigned long long *mw = (unsigned long long *) &mask[(rb * NW + (s >> 6)) * 128 + r];
+  if (present) atomicOr(mw, 1ull << (s & 63)); else atomicAnd(mw, ~(1ull << (s & 63)));
+  if (c.int_path) {
+    unsigned *cw = &codes[((rb * NW + (s >> 6)) * 4 + ((s >> 4) & 3)) * 128 + r];
+    const unsigned sh = 2 * (unsigned) (s & 15);
+    atomicAnd(cw, ~(3u << sh));
+    atomicOr(cw, ((d.flags >> 8) & 3u) << sh);
+    return;
+  }
+  double p[3] = {d.x[0], d.x[1], d.x[2]};
+  if (c.pairwise_del && !present) p[0] = p[1] = p[2] = 0;
+  double B[3];
+#pragma unroll
+  for (int g = 0; g < 3; g++) {
+    double b = c.score[3 * g + 0] * p[0];
+    b += c.score[3 * g + 1] * p[1];
+    b += c.score[3 * g + 2] * p[2];
+    B[g] = b;
+  }
+  const uint64_t sgrp = s >> 2, q = s & 3;
+  if (c.planes == 3) {
+    const uint64_t base = (rb * NC + (sgrp >> 1)) * NGSD_TILE_DOUBLES + (r >> 3) * 32 + (r & 7) * 4 + q;
+    for (int g = 0; g < 3; g++) {
+      const uint64_t o = base + (uint64_t) (g * 2 + (sgrp & 1)) * 512;
+      Apack[o] = p[g];
+      Bpack[o] = B[g];
+    }
+  } else {
+    const uint64_t base = (rb * NC + sgrp / 3) * NGSD_TILE_DOUBLES + (r >> 3) * 32 + (r & 7) * 4 + q;
+    for (int g = 0; g < 2; g++) {
+      const uint64_t o = base + (uint64_t) (g * 3 + sgrp % 3) * 512;
+      Apack[o] = p[g];
+      Bpack[o] = B[g] - B[2];
+    }
+    Cplane[((s >> 6) * n_pad + i) * 64 + (s & 63)] = B[2];
+  }
+}
+
+}  // namespace
+
+cudaError_t ngsd_launch_patch(ngsd_ctx *ctx, const ngsd_deferred *list_dev, unsigned n) {
+  if (n == 0) return cudaSuccess;
+  FrontCfg c;
+  memset(&c, 0, sizeof(c));
+  c.pairwise_del = ctx->cfg.pairwise_del;
+  c.planes = ctx->planes;
+  c.int_path = ctx->int_path ? 1 : 0;
+  for (int k = 0; k < 9; k++) c.score[k] = ctx->cfg.score[k];
+  k_patch<<<(n + 127) / 128, 128, 0, ctx->stream>>>(c, list_dev, n, ctx->n_pad, ctx->NC, ctx->NW, ctx->Apack, ctx->Bpack, ctx->Cplane, ctx->codes,
+                                                    ctx->mask);
   return cudaGetLastError();
 }
 

@@ -523,11 +523,15 @@ int main(int argc, char **argv) {
       for (uint64_t k = 0; k < want; k++) {
         const std::string &line = lines[k];
         const std::vector<double> &f = fields[k];
-        if (line.empty()) {                                     // consumes a site (read_data.cpp:58-59)
-          fprintf(stderr, "> Empty line at site %lu: treated as missing data for every individual\n", sl.s0 + s);
+        if (line.empty()) {
+          // consumes a site and leaves the reference's values at their -1e15 fill (read_data.cpp:58-59): (0,0,0) after
+          // exp, plain missing data under --call_geno -- the front end reproduces both from this marker
+          double blank;
+          const uint64_t bits = NGSD_BLANK_SITE_BITS;
+          memcpy(&blank, &bits, sizeof(blank));
           for (uint64_t i = 0; i < p.n_ind; i++) {
-            if (codes_input) sl.codes[s * p.n_ind + i] = -1;
-            else sl.raw[(s * p.n_ind + i) * 3 + 0] = sl.raw[(s * p.n_ind + i) * 3 + 1] = sl.raw[(s * p.n_ind + i) * 3 + 2] = p.in_logscale ? log(1.0 / 3) : 1.0 / 3;
+            if (codes_input) sl.codes[s * p.n_ind + i] = (int8_t) NGSD_BLANK_SITE_CODE;
+            else sl.raw[(s * p.n_ind + i) * 3 + 0] = sl.raw[(s * p.n_ind + i) * 3 + 1] = sl.raw[(s * p.n_ind + i) * 3 + 2] = blank;
           }
           s++;
           continue;

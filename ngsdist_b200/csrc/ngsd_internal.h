@@ -41,6 +41,16 @@ constexpr int NGSD_TILE_ELEMS = NGSD_TILE * NGSD_TILE;           // accumulator 
 
 struct ngsd_tile { uint16_t ti, tj; };
 
+// A triple whose outcome hangs on the last ulp of log / exp (a comparison of the reference within 1e-11 of flipping):
+// the front-end kernels append it here and the host re-evaluates it with its own libm -- the reference's -- before
+// anything is contracted (api.cu resolve_deferred, frontend.cu k_patch).
+struct ngsd_deferred {
+  uint64_t site;
+  uint32_t ind;
+  uint32_t flags;      // after the host pass: bit 0 miss_data(), bits 8..9 genotype code (integer path)
+  double x[3];         // raw values as pushed; after the host pass the normal-space posterior
+};
+
 struct ngsd_ctx {
   ngsd_cfg cfg;
   int device = 0;
@@ -65,7 +75,22 @@ struct ngsd_ctx {
   uint32_t int_lut[4] = {0, 0, 0, 0};
   double int_scale = 1.0;
   int int_max_byte = 0;
-  int *d_err = nullptr;                        // device error flags (bit0 NaN, bit1 bad genotype code)
+  int *d_err = nullptr;                        // device error flags (bit0 NaN, bit1 bad genotype code, bit2 blank site seen, bit3 deferred list full)
+  ngsd_deferred *d_defer = nullptr; unsigned *d_defer_n = nullptr; unsigned defer_cap = 0;   // knife-edge triples for the host
+  uint64_t deferred_total = 0, deferred_changed = 0;   // statistics: triples re-evaluated by the host / whose outcome differed
+  uint64_t *d_blank = nullptr;                 // [NW] sites that were empty text lines (read_data.cpp:58-59)
+  std::vector<uint64_t> h_blank;               // host copy (empty: none), fetched by ngsd_frontend
+  bool any_blank = false;
+  // 2-plane mode rests on p0 + p1 + p2 == 1.  The one triple the reference produces that breaks it (all-zero binary
+  // likelihoods -> exp(-1.125) three times) is kept here with its deficit; ngsd_distances adds
+  // deficit * w_s * B_2(j, s) for the pairs whose row individual holds it (epilogue.cu k_deficit_fix).
+  struct deficit_entry { uint32_t ind; uint64_t site; double delta; };
+  std::vector<deficit_entry> deficit;
+  bool deficit_dirty = false;
+  uint32_t *d_def_rowptr = nullptr, *d_def_rowind = nullptr; uint64_t *d_def_site = nullptr; double *d_def_delta = nullptr;
+  uint32_t def_rows = 0; uint64_t def_cap = 0;
+  double *d_fix = nullptr;                     // [n_ind][n_ind] correction of the current matrix (allocated on first use)
+  bool deferred_nan = false;                   // a host-evaluated triple produced the NaN that is fatal on the binary path
   // push state
   std::vector<uint8_t> pushed;                 // per 64-site word: pushed?
   uint64_t words_pushed = 0;
@@ -101,6 +126,9 @@ struct ngsd_ctx {
   uint32_t *d_cnt = nullptr;                   // [n_pad][n_pad] shared-site counts
   double *d_out = nullptr, *d_num = nullptr; uint64_t *d_cntout = nullptr;   // [n_ind][n_ind]
   void *h_pin = nullptr; uint64_t h_pin_bytes = 0;    // pinned scratch for weights / lists / results
+  void *h_pin2 = nullptr; uint64_t h_pin2_bytes = 0;  // pinned scratch of the tensor-core count pass of the FP64 path
+  uint32_t *d_cs_begin = nullptr; uint32_t cs_cap = 0;          // its K-split boundaries
+  int32_t *d_cnt_part = nullptr; uint64_t cnt_part_ints = 0;    // its partial count tiles
   // ---- multi-GPU (comm.cu) ----
   void *comm = nullptr;                        // ncclComm_t of this context's rank (ngsd_comm_attach, or the group's ncclCommInitAll)
   uint32_t comm_rank = 0, comm_world = 1;
@@ -141,6 +169,7 @@ cudaError_t ngsd_launch_frontend(ngsd_ctx *ctx, const ngsd_frontend_args &a);
 cudaError_t ngsd_launch_unpack(ngsd_ctx *ctx, double *P_dev /*[ind][site][3]*/, uint8_t *miss_dev /*[ind][site]*/);
 cudaError_t ngsd_launch_unpack_2bit(ngsd_ctx *ctx, const uint8_t *packed_dev, uint64_t row_stride, uint32_t code_of_field, uint64_t n,
                                     int8_t *codes_dev);   // packed fields -> [site][ind] int8 codes
+cudaError_t ngsd_launch_patch(ngsd_ctx *ctx, const ngsd_deferred *list_dev, unsigned n);
 cudaError_t ngsd_launch_synth(ngsd_ctx *ctx, double *raw_dev, uint64_t seed, double miss_rate, uint64_t site0, uint64_t n);
 
 struct ngsd_dist_plan {
@@ -166,6 +195,7 @@ uint64_t ngsd_em_ld(const ngsd_ctx *ctx);     // leading dimension of the EM par
 cudaError_t ngsd_launch_dist_em(ngsd_ctx *ctx, uint32_t n_chunks, uint32_t n_splits, bool weighted);
 cudaError_t ngsd_launch_finish(ngsd_ctx *ctx, uint64_t const_cnt = 0);   // const_cnt > 0: cnt is that constant (no --pairwise_del)
 cudaError_t ngsd_launch_cvec(ngsd_ctx *ctx, bool weighted, uint64_t n_eff);
+cudaError_t ngsd_launch_deficit_fix(ngsd_ctx *ctx, bool weighted, uint64_t n_eff);
 cudaError_t ngsd_launch_epilogue_em(ngsd_ctx *ctx, uint32_t n_splits, uint64_t const_cnt, bool use_cnt);
 // K2c: called genotypes on the int8 tensor cores (dist_imma.cu)
 bool ngsd_int_lut(const double *score, bool pairwise_del, uint32_t lut[4], double *scale, int *max_byte);
@@ -173,9 +203,18 @@ cudaError_t ngsd_launch_dist_imma(ngsd_ctx *ctx, uint32_t n_units, int grid, boo
 int ngsd_imma_ctas_per_sm();
 bool ngsd_use_umma();
 cudaError_t ngsd_launch_dist_umma(ngsd_ctx *ctx, uint32_t n_units, int grid, uint32_t pstride, bool count);   // dist_umma.cu (tcgen05)
+struct ngsd_count_umma_args {
+  const uint32_t *split_begin;   // [n_splits + 1] positions in the word list
+  uint32_t n_splits;
+  int32_t *partials;             // [n_splits][n_tiles][128][128]
+  const uint8_t *wsite;          // [layers][NW * 64] per-site weight bytes
+  const uint32_t *word_ids, *word_layer;
+};
+cudaError_t ngsd_launch_count_umma(ngsd_ctx *ctx, const ngsd_count_umma_args &c);   // dist_umma.cu: --pairwise_del counts of the FP64 path
 cudaError_t ngsd_launch_epilogue_int(ngsd_ctx *ctx, uint32_t n_splits, uint64_t const_cnt, bool use_cnt, bool in_kernel_cnt);
 
 // ---- multi-GPU (comm.cu) ----
+extern "C" int ngsd_frontend_resolve(ngsd_ctx *ctx);      // api.cu: knife-edge triples -> host libm -> k_patch
 extern "C" int ngsd_frontend_flags(ngsd_ctx *ctx);        // api.cu: the deferred error flags of the front end, without the completeness check
 extern "C" void ngsd_mark_all_pushed(ngsd_ctx *ctx);      // api.cu: after an all-gather every site is resident
 void ngsd_comm_release(ngsd_ctx *ctx);         // comm.cu: communicator + staging buffers of one context

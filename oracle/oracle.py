@@ -171,11 +171,20 @@ def distances_block(P, r0, r1, c0, c1, score=None, indep=True, pairwise_del=Fals
 
 
 def run_job(raw, *, in_log=False, call_geno=False, N_thresh=0.0, call_thresh=0.0, avg_nuc_dist=False, indep=True,
-            pairwise_del=False, tot_sites=0, evol_model=1, n_boot_rep=0, boot_block_size=1, seed=12345, kind=0):
-    """Whole job the way main() runs it (ngsDist.cpp:156-289): returns the list of 1+n_boot_rep result dicts."""
-    P = frontend(raw, kind=kind, in_log=in_log, call_geno=call_geno, N_thresh=N_thresh, call_thresh=call_thresh)
-    if call_geno:
-        indep = True  # ngsDist.cpp:59-62
+            pairwise_del=False, tot_sites=0, evol_model=1, n_boot_rep=0, boot_block_size=1, seed=12345, kind=0, blank_sites=(),
+            genotypes=False):
+    """Whole job the way main() runs it (ngsDist.cpp:156-289): returns the list of 1+n_boot_rep result dicts.
+    blank_sites: sites that were empty text lines -- read_geno leaves them at the -1e15 fill without normalising
+    (read_data.cpp:58-59), so after ngsDist.cpp:165-174 every individual holds (0,0,0) there, or the missing-data triple
+    exp(log(1/3)) when call_geno ran on the all-equal fill (gen_func.cpp:895-905).  genotypes: raw is [site][ind] codes."""
+    if genotypes:
+        P = frontend_geno(raw)
+    else:
+        P = frontend(raw, kind=kind, in_log=in_log, call_geno=call_geno, N_thresh=N_thresh, call_thresh=call_thresh)
+    for s in blank_sites:
+        P[:, s, :] = np.exp(np.log(1.0 / 3)) if call_geno else 0.0
+    if call_geno or genotypes:
+        indep = True  # ngsDist.cpp:55-62
     n_sites = P.shape[1]
     rng = Taus(seed)
     out = []

@@ -9,7 +9,7 @@ import pytest
 
 import oracle
 from util import load_bin, manifest, parse_flags, read_text_input
-from test_gpu_parity import assert_close, golden_mats, nb, params_from
+from test_gpu_parity import assert_close, golden_mats, nb, params_from, run_text_case
 
 pytestmark = pytest.mark.gpu
 MAN = manifest()
@@ -34,15 +34,21 @@ def test_golden_cases_em(case):
         assert np.allclose(r["dist"][fin], gm[fin], rtol=0, atol=6e-11)
 
 
-def test_text_probs_em_golden():
-    case = [c for c in MAN["text"] if c["name"] == "txt_probs_em"][0]
+@pytest.mark.parametrize("case", [c for c in MAN["text"] if not parse_flags(c["flags"])[0]["indep"]], ids=lambda c: c["name"])
+def test_text_probs_em_goldens(case):
+    """Text posteriors through the per pair-site EM: plain, on the miss_data boundary under --pairwise_del, and with empty
+    lines (every pair NaN without --pairwise_del, the sites skipped with it)."""
     kw, probs = parse_flags(case["flags"])
-    data = read_text_input(case["input"], case["n_ind"], case["n_sites"], probs)
-    with nb().NgsDistB200(params_from(kw, case["n_ind"], case["n_sites"], probs=True, in_text=True)) as g:
-        g.push_sites(data)
-        r = g.run()[0]
-    gm = golden_mats(case["name"], case["n_ind"])[0]
-    assert np.allclose(r["dist"], gm, rtol=0, atol=6e-11)
+    data, blank = read_text_input(case["input"], case["n_ind"], case["n_sites"], probs, want_blank=True)
+    res = run_text_case(kw, case, probs, data, blank)
+    ora = oracle.run_job(data, kind=1, blank_sites=blank, **kw)
+    gold = golden_mats(case["name"], case["n_ind"])
+    for r, gm, o in zip(res, gold, ora):
+        fin = np.isfinite(gm)
+        assert np.allclose(r["dist"][fin], gm[fin], rtol=0, atol=6e-11)
+        assert np.array_equal(np.isnan(r["dist"]), np.isnan(gm))
+        if fin.any():
+            assert np.array_equal(r["cnt"], o["cnt"])
 
 
 @pytest.mark.parametrize("alpha", [0.1, 0.5, 2.0])

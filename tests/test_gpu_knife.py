@@ -1,0 +1,101 @@
+"""Knife edges of the reference's comparisons (VERDICT r1 "what's weak" #1).
+
+miss_data (gen_func.cpp:862-868) compares |p0-p1| and |p1-p2| with EPSILON = 1e-5 on exp(log(x) - logsum(log x)).  On
+6-decimal posteriors (the reference's own text inputs) triples like 0.333340 0.333330 0.333330 sit ON that boundary and
+the outcome hangs on the last bit of libm's log / exp.  The front end hands every triple within 1e-11 of one of the
+reference's comparisons to the host's libm (ngsd_deferred); masks, cnt and calls must then be bit-exact against the
+oracle (same libm) and against .dist files written by the reference binary (tests/golden/grid_*, txt_grid_*)."""
+import numpy as np
+import pytest
+
+import oracle
+from util import load_bin, manifest
+from test_gpu_parity import assert_close, nb
+
+pytestmark = pytest.mark.gpu
+MAN = manifest()
+
+
+def grid():
+    c = [c for c in MAN["binary"] if c["input"] == "grid12x96.bin"][0]
+    return load_bin(c["input"], c["n_ind"], c["n_sites"])
+
+
+@pytest.mark.parametrize("in_text", [False, True])
+def test_masks_on_the_decimal_grid_are_bit_exact(in_text):
+    raw = grid()
+    n_sites, n_ind, _ = raw.shape
+    p = nb().Params(n_ind=n_ind, n_sites=n_sites, in_probs=True, indep_geno=True, pairwise_del=False, keep_planes=True, in_text=in_text)
+    with nb().NgsDistB200(p) as g:
+        g.push_sites(raw)
+        g.frontend()
+        P, miss = g.posteriors()
+        n_host = g.deferred_stats()
+    Po = oracle.frontend(raw, kind=1 if in_text else 0)
+    mo = oracle.miss_mask(Po)
+    assert n_host > 50, "the grid is built to sit on the boundary: the host path must have been taken (%d)" % n_host
+    assert np.array_equal(miss, mo), "%d masks differ" % (miss != mo).sum()
+    assert np.abs(P - Po).max() < 1e-14
+
+
+@pytest.mark.parametrize("mode", ["indep_pdel", "em_pdel", "thresh_pdel", "call_pdel"])
+def test_counts_on_the_decimal_grid_are_bit_exact(mode):
+    raw = grid()
+    n_sites, n_ind, _ = raw.shape
+    kw = {"indep_pdel": dict(indep=True), "em_pdel": dict(indep=False), "thresh_pdel": dict(call_geno=True, N_thresh=0.33334, call_thresh=0.9),
+          "call_pdel": dict(call_geno=True)}[mode]
+    p = nb().Params(n_ind=n_ind, n_sites=n_sites, in_probs=True, indep_geno=kw.get("indep", True), pairwise_del=True, evol_model=0,
+                    call_geno=kw.get("call_geno", False), N_thresh=kw.get("N_thresh", 0.0), call_thresh=kw.get("call_thresh", 0.0),
+                    n_boot_rep=2, boot_block_size=8, seed=12345)
+    with nb().NgsDistB200(p) as g:
+        g.push_sites(raw)
+        res = g.run(want_num=True, want_cnt=True)
+    ora = oracle.run_job(raw, pairwise_del=True, evol_model=0, n_boot_rep=2, boot_block_size=8, seed=12345, **kw)
+    for r, o in zip(res, ora):
+        assert np.array_equal(r["cnt"], o["cnt"]), "%s: %d counts differ" % (mode, (r["cnt"] != o["cnt"]).sum())
+        assert_close(r["num"], o["num"], mode)
+
+
+def test_host_path_is_idle_on_continuous_data():
+    raw = oracle.synth_raw(5, 0.1, 40, 640)
+    p = nb().Params(n_ind=40, n_sites=640, in_probs=True, indep_geno=True, pairwise_del=True)
+    with nb().NgsDistB200(p) as g:
+        g.push_sites(raw)
+        g.frontend()
+        assert g.deferred_stats() == 0
+
+
+@pytest.mark.parametrize("boot", [False, True])
+def test_all_zero_triples_in_two_plane_mode(boot):
+    """an all-zero binary triple becomes exp(-1.125) x 3 (sum 0.974); the 2-plane contraction assumes sum 1."""
+    n_ind, n_sites = 150, 700
+    raw = oracle.synth_raw(21, 0.05, n_ind, n_sites)
+    rng = np.random.RandomState(3)
+    for _ in range(400):
+        raw[rng.randint(n_sites), rng.randint(n_ind)] = 0.0
+    raw[5, :] = 0.0                                  # a whole site
+    raw[:, 7] = 0.0                                  # a whole individual
+    kw = dict(n_boot_rep=2, boot_block_size=10, seed=12345) if boot else {}
+    p = nb().Params(n_ind=n_ind, n_sites=n_sites, in_probs=True, indep_geno=True, pairwise_del=False, evol_model=0, **kw)
+    with nb().NgsDistB200(p) as g:
+        for s0 in (0, 320):                          # two pushes; the second one re-pushed once more
+            g.push_sites(raw[s0:s0 + 320 if s0 == 0 else n_sites], s0)
+        g.push_sites(raw[320:], 320)
+        res = g.run(want_num=True, want_cnt=True)
+    ora = oracle.run_job(raw, indep=True, evol_model=0, **kw)
+    for r, o in zip(res, ora):
+        assert_close(r["num"], o["num"], "zero triples, 2 planes")
+        assert np.array_equal(r["cnt"], o["cnt"])
+
+
+def test_push_larger_than_one_launch_grid():
+    """grid.y = ceil(n / 64) is limited to 65535 -- a push of 4.2M+ sites goes out as several launches."""
+    n_ind, n_sites = 3, 65535 * 64 + 640
+    codes = (np.arange(n_sites * n_ind, dtype=np.int64) % 4 - 1).astype(np.int8).reshape(n_sites, n_ind)
+    p = nb().Params(n_ind=n_ind, n_sites=n_sites, in_probs=False, pairwise_del=True, evol_model=0)
+    with nb().NgsDistB200(p) as g:
+        g.push_genotypes(codes)
+        r = g.run(want_cnt=True)[0]
+    pres = codes >= 0
+    want = (pres[:, 0] & pres[:, 1]).sum()
+    assert r["cnt"][0, 1] == want

@@ -85,18 +85,31 @@ def test_golden_cases_text_inputs(case):
     kw, probs = parse_flags(case["flags"])
     if not kw["indep"]:
         pytest.skip("EM path covered in test_gpu_em.py")
-    data = read_text_input(case["input"], case["n_ind"], case["n_sites"], probs)
-    with nb().NgsDistB200(params_from(kw, case["n_ind"], case["n_sites"], probs=probs, in_text=True)) as g:
-        if probs:
-            g.push_sites(data)
-        else:
-            g.push_genotypes(data)
-        res = g.run()
+    data, blank = read_text_input(case["input"], case["n_ind"], case["n_sites"], probs, want_blank=True)
+    res = run_text_case(kw, case, probs, data, blank)
+    ora = oracle.run_job(data, kind=1, blank_sites=blank, genotypes=not probs, **kw)
     gold = golden_mats(case["name"], case["n_ind"])
-    for r, gm in zip(res, gold):
+    assert len(res) == len(gold) == len(ora)
+    for r, gm, o in zip(res, gold, ora):
         fin = np.isfinite(gm)
         assert np.allclose(r["dist"][fin], gm[fin], rtol=0, atol=6e-11)
         assert np.array_equal(np.isnan(r["dist"]), np.isnan(gm))
+        assert np.array_equal(r["cnt"], o["cnt"]), "cnt must be bit-exact"
+        assert_close(r["num"], o["num"], case["name"] + " num")
+
+
+def run_text_case(kw, case, probs, data, blank):
+    """What the drop-in reader does with a text file: values as parsed; an empty line becomes the blank-site marker."""
+    with nb().NgsDistB200(params_from(kw, case["n_ind"], case["n_sites"], probs=probs, in_text=True)) as g:
+        if probs:
+            data = data.copy()
+            data[blank] = nb().BLANK_SITE
+            g.push_sites(data)
+        else:
+            data = data.astype(np.int8)
+            data[blank] = nb().BLANK_SITE_CODE
+            g.push_genotypes(data)
+        return g.run(want_num=True, want_cnt=True)
 
 
 @pytest.mark.parametrize("call,thr", [(False, (0, 0)), (True, (0, 0)), (True, (0.35, 0.9))])

@@ -59,23 +59,8 @@ def test_oracle_reproduces_reference_binary_input(case):
 @pytest.mark.parametrize("case", MAN["text"], ids=lambda c: c["name"])
 def test_oracle_reproduces_reference_text_input(case):
     kw, probs = parse_flags(case["flags"])
-    data = read_text_input(case["input"], case["n_ind"], case["n_sites"], probs)
-    if probs:
-        res = oracle.run_job(data, kind=1, **kw)
-    else:
-        P = oracle.frontend_geno(data)
-        n_sites = P.shape[1]
-        rng = oracle.Taus(kw["seed"])
-        res = []
-        args = dict(score=oracle.score_matrix(kw["avg_nuc_dist"]), indep=True, pairwise_del=kw["pairwise_del"],
-                    tot_sites=kw["tot_sites"], evol_model=kw["evol_model"])
-        for rep in range(kw["n_boot_rep"] + 1):
-            if rep == 0:
-                res.append(oracle.distances(P, **args))
-            else:
-                n_sites -= n_sites % kw["boot_block_size"]
-                sm = rng.boot_map(n_sites // kw["boot_block_size"], kw["boot_block_size"])
-                res.append(oracle.distances(P, site_map=sm, **args))
+    data, blank = read_text_input(case["input"], case["n_ind"], case["n_sites"], probs, want_blank=True)
+    res = oracle.run_job(data, kind=1, blank_sites=blank, genotypes=not probs, **kw)
     assert format_dist([r["dist"] for r in res]) == golden_text(case["name"])
 
 

@@ -76,14 +76,20 @@ def parse_flags(flags):
     return kw, probs
 
 
-def read_text_input(name, n_ind, n_sites, probs):
+def read_text_input(name, n_ind, n_sites, probs, want_blank=False):
     """The text reader's semantics (read_data.cpp:48-103) for the well-formed golden inputs: header skipped when it has
-    too few numeric fields, last n_ind*n_geno numeric columns used."""
+    too few numeric fields, last n_ind*n_geno numeric columns used; an empty line consumes a site (:58-59) -- its row is a
+    placeholder here and its index is returned in `blank` (the caller applies the reference's outcome for such a site)."""
     n_geno = 3 if probs else 1
-    rows = []
+    rows, blank = [], []
     with gzip.open(os.path.join(GOLDEN, name), "rt") as fh:
         for line in fh:
             line = line.rstrip("\n")
+            if line == "":
+                if len(rows) < n_sites:
+                    blank.append(len(rows))
+                    rows.append([1.0 / 3] * (n_ind * n_geno) if probs else [-1.0] * n_ind)
+                continue
             nums = []
             for tok in line.replace(" ", "\t").split("\t"):
                 if tok == "":
@@ -96,4 +102,5 @@ def read_text_input(name, n_ind, n_sites, probs):
                 continue  # header
             rows.append(nums[-n_ind * n_geno:])
     a = np.array(rows[:n_sites], dtype=np.float64)
-    return a.reshape(n_sites, n_ind, 3) if probs else a.reshape(n_sites, n_ind).astype(np.int32)
+    a = a.reshape(n_sites, n_ind, 3) if probs else a.reshape(n_sites, n_ind).astype(np.int32)
+    return (a, blank) if want_blank else a
