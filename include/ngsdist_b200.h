@@ -133,6 +133,17 @@ NGSD_API const char *ngsd_last_error(const ngsd_ctx *ctx);   /* ctx may be NULL:
  * returns when the copy has been consumed; the device variant reads a device pointer in place. */
 NGSD_API int ngsd_push_sites(ngsd_ctx *ctx, const double *raw_host, uint64_t site0, uint64_t n);
 NGSD_API int ngsd_push_sites_device(ngsd_ctx *ctx, const double *raw_dev, uint64_t site0, uint64_t n);
+/* Transport tiers for likelihoods / posteriors: the same front end fed from narrower host values, for
+ * hosts where the 24 B per individual-site of the binary layout (read_data.cpp:28-31) make PCIe the bottleneck.  The
+ * values are widened to double on the device and then take exactly the path of ngsd_push_sites.
+ *   NGSD_XFER_F32   [site][ind][3] float:   12 B.  Rounds every input to 24 bits; measured effect on distances in DESIGN §4.
+ *   NGSD_XFER_U32   [site][ind][3] uint32:  12 B.  value = q / denom (IEEE division): EXACTLY the double strtod gives a decimal
+ *                                           with <= 9 significant digits when denom is the matching power of ten.
+ *   NGSD_XFER_U20X3 [site][ind] uint64:      8 B.  q0 | q1 << 20 | q2 << 40, value = q / denom: exact for the 6-decimal
+ *                                           posteriors the reference's text inputs hold (ANGSD -doGeno 8), denom = 1e6.
+ * denom is ignored for NGSD_XFER_F32.  Normal-scale and log-scale contexts alike (fixed point: normal scale only). */
+typedef enum { NGSD_XFER_F32 = 1, NGSD_XFER_U32 = 2, NGSD_XFER_U20X3 = 3 } ngsd_xfer_format;
+NGSD_API int ngsd_push_sites_packed(ngsd_ctx *ctx, const void *host, int32_t format, double denom, uint64_t site0, uint64_t n);
 /* Genotype input (no --probs): codes [site][ind] in {-1,0,1,2}; NGSD_ERR_GENO for anything > 2. */
 NGSD_API int ngsd_push_genotypes(ngsd_ctx *ctx, const int8_t *codes_host, uint64_t site0, uint64_t n);
 /* The same genotype input, four individuals per byte (the 1 B -- or as text 2-3 B -- per individual-site

@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "ngsd_boot_block_counts", "ngsd_get_posteriors", "ngsd_synth_raw_device", "ngsd_get_timing", "ngsd_stream",
     "ngsd_probe_fp64_tflops", "ngsd_probe_int8_tmacs", "ngsd_probe_umma_tmacs", "ngsd_host_alloc", "ngsd_host_free", "ngsd_set_tile_shard", "ngsd_device_results", "ngsd_finish",
     "ngsd_distances_batch", "ngsd_comm_unique_id", "ngsd_comm_attach", "ngsd_comm_allgather_operands", "ngsd_comm_reduce_sites", "ngsd_comm_reduce_tiles",
-    "ngsd_comm_barrier", "ngsd_comm_stats", "ngsd_bind_host_to_device", "ngsd_deferred_stats",
+    "ngsd_comm_barrier", "ngsd_comm_stats", "ngsd_bind_host_to_device", "ngsd_deferred_stats", "ngsd_push_sites_packed",
 ]
 ABI_VERSION = 2
 COMM_ID_BYTES = 128
@@ -122,11 +122,12 @@ def lib():
     L.ngsd_comm_stats.argtypes = [vp, C.POINTER(u64), C.POINTER(C.c_float)]
     L.ngsd_bind_host_to_device.argtypes = [i32]
     L.ngsd_deferred_stats.argtypes = [vp, C.POINTER(u64)]
+    L.ngsd_push_sites_packed.argtypes = [vp, vp, i32, dbl, u64, u64]
     for name in ("ngsd_create", "ngsd_destroy", "ngsd_push_sites", "ngsd_push_sites_device", "ngsd_push_genotypes", "ngsd_push_packed_genotypes", "ngsd_frontend",
                  "ngsd_distances", "ngsd_get_posteriors", "ngsd_synth_raw_device", "ngsd_get_timing", "ngsd_probe_fp64_tflops", "ngsd_probe_int8_tmacs", "ngsd_probe_umma_tmacs",
                  "ngsd_set_tile_shard", "ngsd_device_results", "ngsd_finish", "ngsd_distances_batch", "ngsd_comm_unique_id", "ngsd_comm_attach",
                  "ngsd_comm_allgather_operands", "ngsd_comm_reduce_sites", "ngsd_comm_reduce_tiles", "ngsd_comm_barrier", "ngsd_comm_stats",
-                 "ngsd_bind_host_to_device", "ngsd_deferred_stats"):
+                 "ngsd_bind_host_to_device", "ngsd_deferred_stats", "ngsd_push_sites_packed"):
         getattr(L, name).restype = i32
     _lib = L
     return L
@@ -223,6 +224,16 @@ def bind_host_to_device(device):
     return lib().ngsd_bind_host_to_device(device)
 
 
+XFER_F32, XFER_U32, XFER_U20X3 = 1, 2, 3
+
+
+def pack_u20x3(q):
+    """[n][n_ind][3] integers < 2^20 -> [n][n_ind] uint64 (q0 | q1 << 20 | q2 << 40), the NGSD_XFER_U20X3 layout."""
+    q = np.asarray(q).astype(np.uint64)
+    assert (q < (1 << 20)).all()
+    return np.ascontiguousarray(q[..., 0] | (q[..., 1] << np.uint64(20)) | (q[..., 2] << np.uint64(40)))
+
+
 BLANK_SITE = np.array([0x7FF84E4753444231], dtype=np.uint64).view(np.float64)[0]   # NGSD_BLANK_SITE_BITS: an empty text line
 BLANK_SITE_CODE = -128
 
@@ -310,6 +321,28 @@ class NgsDistB200:
 
     def push_sites_device(self, dev_ptr, site0, n):
         self._check(lib().ngsd_push_sites_device(self._h, _ptr(dev_ptr), site0, n))
+
+    def push_sites_f32(self, raw32, site0=0):
+        """Transport tier NGSD_XFER_F32: [n][n_ind][3] float32."""
+        raw32 = np.ascontiguousarray(raw32, dtype=np.float32)
+        assert raw32.shape[1:] == (self.p.n_ind, 3)
+        self._check(lib().ngsd_push_sites_packed(self._h, _ptr(raw32), XFER_F32, 0.0, site0, raw32.shape[0]))
+
+    def push_sites_fixed(self, q, denom, site0=0):
+        """Fixed-point transport: q uint32 [n][n_ind][3] (NGSD_XFER_U32) or uint64 [n][n_ind] holding three 20-bit fields
+        (NGSD_XFER_U20X3, see pack_u20x3); value = q / denom."""
+        q = np.ascontiguousarray(q)
+        if q.dtype == np.uint64:
+            assert q.shape[1:] == (self.p.n_ind,)
+            fmt = XFER_U20X3
+        else:
+            q = np.ascontiguousarray(q, dtype=np.uint32)
+            assert q.shape[1:] == (self.p.n_ind, 3)
+            fmt = XFER_U32
+        self._check(lib().ngsd_push_sites_packed(self._h, _ptr(q), fmt, float(denom), site0, q.shape[0]))
+
+    def push_sites_packed_ptr(self, host_ptr, fmt, denom, site0, n):
+        self._check(lib().ngsd_push_sites_packed(self._h, _ptr(host_ptr), fmt, float(denom), site0, n))
 
     def push_genotypes(self, codes, site0=0):
         codes = np.ascontiguousarray(codes, dtype=np.int8)

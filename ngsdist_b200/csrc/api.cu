@@ -383,6 +383,57 @@ int ngsd_push_sites(ngsd_ctx *ctx, const double *raw_host, uint64_t site0, uint6
   return NGSD_OK;
 }
 
+int ngsd_push_sites_packed(ngsd_ctx *ctx, const void *host, int32_t format, double denom, uint64_t site0, uint64_t n) {
+  if (ctx && !ctx->kids.empty()) {
+    const uint64_t b = format == NGSD_XFER_U20X3 ? ctx->n_ind * 8 : ctx->n_ind * 12;
+    return ngsd_group_push(ctx, 10 + format, host, b, 0, reinterpret_cast<const int8_t *>(&denom), site0, n);
+  }
+  int rc = check_push(ctx, site0, n);
+  if (rc) return rc;
+  if (!host) { ngsd_set_error(ctx, "null input pointer"); return NGSD_ERR_ARG; }
+  if (ctx->cfg.input_kind == NGSD_INPUT_GENOTYPES) { ngsd_set_error(ctx, "context expects genotype codes"); return NGSD_ERR_ARG; }
+  if (format < NGSD_XFER_F32 || format > NGSD_XFER_U20X3) { ngsd_set_error(ctx, "unknown transport format %d", format); return NGSD_ERR_ARG; }
+  if (format != NGSD_XFER_F32 && (!(denom > 0) || ctx->cfg.input_is_log)) {
+    ngsd_set_error(ctx, "fixed-point transport needs denom > 0 and normal-scale input");
+    return NGSD_ERR_ARG;
+  }
+  NGSD_CUDA(ctx, cudaSetDevice(ctx->device));
+  // one staging slot = the chunk's narrow values followed by the doubles they widen to
+  const uint64_t in_bps = format == NGSD_XFER_U20X3 ? ctx->n_ind * 8 : ctx->n_ind * 12, raw_bps = ctx->n_ind * 24, bps = in_bps + raw_bps;
+  if (ctx->stage_dev[0] && ctx->stage_bps != bps) {
+    NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    for (int b = 0; b < 2; b++) { cudaFree(ctx->stage_dev[b]); ctx->stage_dev[b] = nullptr; }
+  }
+  rc = ensure_staging(ctx, bps);
+  if (rc) return rc;
+  ctx->stage_bps = bps;
+  ctx->timing = ngsd_timing();
+  tick(ctx, 0);
+  int launches = 0;
+  for (uint64_t off = 0; off < n; off += ctx->stage_sites) {
+    const uint64_t m = std::min(ctx->stage_sites, n - off);
+    const int b = ctx->stage_next;
+    ctx->stage_next ^= 1;
+    double *d_raw = ctx->stage_dev[b];                                               // 32-byte aligned: first
+    char *d_in = reinterpret_cast<char *>(ctx->stage_dev[b]) + ctx->stage_sites * raw_bps;
+    NGSD_CUDA(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->stage_free[b], 0));
+    NGSD_CUDA(ctx, cudaMemcpyAsync(d_in, reinterpret_cast<const char *>(host) + off * in_bps, m * in_bps, cudaMemcpyHostToDevice, ctx->copy_stream));
+    NGSD_CUDA(ctx, cudaEventRecord(ctx->stage_ready[b], ctx->copy_stream));
+    NGSD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->stage_ready[b], 0));
+    NGSD_CUDA(ctx, ngsd_launch_widen(ctx, d_in, format, denom, m, d_raw));
+    ngsd_frontend_args a{d_raw, nullptr, site0 + off, m};
+    NGSD_CUDA(ctx, ngsd_launch_frontend(ctx, a));
+    NGSD_CUDA(ctx, cudaEventRecord(ctx->stage_free[b], ctx->stream));
+    launches += 2;
+  }
+  tick(ctx, 1);
+  ctx->timing.launches = launches;
+  ctx->timing.total_ms = -1.f;
+  NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));   // the caller may now reuse `host`
+  mark_pushed(ctx, site0, n);
+  return NGSD_OK;
+}
+
 int ngsd_push_genotypes(ngsd_ctx *ctx, const int8_t *codes_host, uint64_t site0, uint64_t n) {
   if (ctx && !ctx->kids.empty()) return ngsd_group_push(ctx, 1, codes_host, ctx->n_ind, 0, nullptr, site0, n);
   int rc = check_push(ctx, site0, n);

@@ -476,6 +476,12 @@ int ngsd_group_push(ngsd_ctx *parent, int what, const void *ptr, uint64_t bytes_
       case 0: rc[q] = ngsd_push_sites(pc.k, (const double *) src, local0, pc.n); break;
       case 1: rc[q] = ngsd_push_genotypes(pc.k, (const int8_t *) src, local0, pc.n); break;
       case 2: rc[q] = ngsd_push_packed_genotypes(pc.k, (const uint8_t *) src, row_stride, code_of_field, local0, pc.n); break;
+      case 10 + NGSD_XFER_F32: case 10 + NGSD_XFER_U32: case 10 + NGSD_XFER_U20X3: {   // transport tiers: code_of_field carries &denom
+        double denom;
+        memcpy(&denom, code_of_field, sizeof(denom));
+        rc[q] = ngsd_push_sites_packed(pc.k, src, what - 10, denom, local0, pc.n);
+        break;
+      }
       default: {
         cudaPointerAttributes at;
         if (cudaPointerGetAttributes(&at, src) != cudaSuccess || at.type != cudaMemoryTypeDevice || at.device != pc.k->device) {

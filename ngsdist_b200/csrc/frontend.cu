@@ -694,6 +694,32 @@ cudaError_t ngsd_launch_patch(ngsd_ctx *ctx, const ngsd_deferred *list_dev, unsi
   return cudaGetLastError();
 }
 
+namespace {
+// transport tiers (ngsd_push_sites_packed): narrow host values -> the doubles the front end reads
+__global__ void k_widen(const void *__restrict__ src, int format, double denom, uint64_t n_triples, double *__restrict__ raw) {
+  const uint64_t k = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_triples) return;
+  double x0, x1, x2;
+  if (format == NGSD_XFER_F32) {
+    const float *f = reinterpret_cast<const float *>(src) + k * 3;
+    x0 = (double) f[0]; x1 = (double) f[1]; x2 = (double) f[2];
+  } else if (format == NGSD_XFER_U32) {
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(src) + k * 3;
+    x0 = (double) q[0] / denom; x1 = (double) q[1] / denom; x2 = (double) q[2] / denom;
+  } else {
+    const uint64_t q = reinterpret_cast<const uint64_t *>(src)[k];
+    x0 = (double) (q & 0xFFFFFu) / denom; x1 = (double) ((q >> 20) & 0xFFFFFu) / denom; x2 = (double) ((q >> 40) & 0xFFFFFu) / denom;
+  }
+  raw[k * 3 + 0] = x0; raw[k * 3 + 1] = x1; raw[k * 3 + 2] = x2;
+}
+}  // namespace
+
+cudaError_t ngsd_launch_widen(ngsd_ctx *ctx, const void *src_dev, int format, double denom, uint64_t n, double *raw_dev) {
+  const uint64_t tot = n * ctx->n_ind;
+  k_widen<<<(unsigned) ((tot + 255) / 256), 256, 0, ctx->stream>>>(src_dev, format, denom, tot, raw_dev);
+  return cudaGetLastError();
+}
+
 cudaError_t ngsd_launch_unpack_2bit(ngsd_ctx *ctx, const uint8_t *packed_dev, uint64_t row_stride, uint32_t code_of_field, uint64_t n,
                                     int8_t *codes_dev) {
   const uint64_t tot = n * ctx->n_ind;

@@ -455,13 +455,19 @@ int main(int argc, char **argv) {
   const uint64_t n_geno = p.in_probs ? 3 : 1;
   struct Slot {
     double *raw = nullptr;
+    uint64_t *packed = nullptr;   // text posteriors that are k / 10^6 with k < 2^20 travel as 3 x 20 bits (NGSD_XFER_U20X3)
+    bool packable = false;
     std::vector<int8_t> codes;
     uint64_t s0 = 0, n = 0;
     bool full = false;
   } slots[2];
+  // 6-decimal text posteriors (what ANGSD -doGeno 8 writes and the reference's test inputs hold) are exactly k / 10^6:
+  // 8 bytes per individual-site over PCIe instead of 24, and the device's (double) k / 1e6 is the very double strtod gave
+  const bool try_pack = !p.in_bin && p.in_probs && !p.in_logscale && !getenv("NGSD_CLI_NO_PACK");
   for (auto &sl : slots) {
     if (codes_input) sl.codes.resize(chunk * p.n_ind);
     else if (!(sl.raw = (double *) ngsd_host_alloc(chunk * per_site * sizeof(double)))) die("main", "cannot allocate pinned host buffer");
+    if (try_pack && !(sl.packed = (uint64_t *) ngsd_host_alloc(chunk * p.n_ind * sizeof(uint64_t)))) die("main", "cannot allocate pinned host buffer");
   }
   std::mutex mu;
   std::condition_variable cv;
@@ -500,6 +506,7 @@ int main(int argc, char **argv) {
   std::vector<std::vector<double>> fields;
   auto fill_text = [&](Slot &sl) {
     uint64_t s = 0;
+    sl.packable = try_pack;
     while (s < sl.n) {
       // (1) sequential: the next batch of lines, at most one per site still missing
       const uint64_t want = sl.n - s;
@@ -526,6 +533,7 @@ int main(int argc, char **argv) {
         if (line.empty()) {
           // consumes a site and leaves the reference's values at their -1e15 fill (read_data.cpp:58-59): (0,0,0) after
           // exp, plain missing data under --call_geno -- the front end reproduces both from this marker
+          sl.packable = false;                                  // the marker is a NaN: this chunk travels as doubles
           double blank;
           const uint64_t bits = NGSD_BLANK_SITE_BITS;
           memcpy(&blank, &bits, sizeof(blank));
@@ -551,6 +559,16 @@ int main(int argc, char **argv) {
           }
         } else {
           memcpy(sl.raw + s * per_site, ptr, per_site * sizeof(double));
+          for (uint64_t i = 0; i < p.n_ind && sl.packable; i++) {
+            uint64_t w = 0;
+            for (int g = 0; g < 3; g++) {
+              const double v = ptr[i * 3 + g];
+              const double qd = nearbyint(v * 1e6);
+              if (!(v >= 0) || signbit(v) || !(qd < 1048576.0) || qd / 1e6 != v) { sl.packable = false; break; }
+              w |= (uint64_t) qd << (20 * g);
+            }
+            sl.packed[s * p.n_ind + i] = w;
+          }
         }
         s++;
       }
@@ -582,7 +600,9 @@ int main(int argc, char **argv) {
         std::unique_lock<std::mutex> lk(mu);
         cv.wait(lk, [&] { return sl.full; });
       }
-      int rc = codes_input ? ngsd_push_genotypes(ctx, sl.codes.data(), sl.s0, sl.n) : ngsd_push_sites(ctx, sl.raw, sl.s0, sl.n);
+      int rc = codes_input    ? ngsd_push_genotypes(ctx, sl.codes.data(), sl.s0, sl.n)
+               : sl.packable ? ngsd_push_sites_packed(ctx, sl.packed, NGSD_XFER_U20X3, 1e6, sl.s0, sl.n)
+                             : ngsd_push_sites(ctx, sl.raw, sl.s0, sl.n);
       if (rc) die("read_geno", ngsd_last_error(ctx));
       {
         std::lock_guard<std::mutex> lk(mu);
@@ -603,8 +623,10 @@ int main(int argc, char **argv) {
     }
   }
   gzclose(fh);
-  for (auto &sl : slots)
+  for (auto &sl : slots) {
     if (sl.raw) ngsd_host_free(sl.raw);
+    if (sl.packed) ngsd_host_free(sl.packed);
+  }
   }   // !in_bed
   if (ngsd_frontend(ctx)) die("read_geno", ngsd_last_error(ctx));
   stamp("input read + front end");
@@ -631,7 +653,7 @@ int main(int argc, char **argv) {
     if (rep > 0 && round > 1) {
       n_sites -= n_sites % p.boot_block_size;                         // persistent truncation (ngsDist.cpp:236)
       const uint64_t n_blocks = n_sites / p.boot_block_size, k = std::min<uint64_t>(round, p.n_boot_rep - rep + 1);
-      counts.resize(n_blocks * k);
+      counts.resize(std::max<uint64_t>(1, n_blocks * k));             // (n_blocks == 0: --boot_block_size > n_sites, still a non-NULL pointer)
       for (uint64_t q = 0; q < k; q++) ngsd_boot_block_counts(rng, n_blocks, counts.data() + q * n_blocks);
       if (p.verbose >= 1)
         for (uint64_t q = 0; q < k; q++) fprintf(stderr, "==> Bootstrap replicate # %lu ...\n", rep + q);
@@ -654,7 +676,7 @@ int main(int argc, char **argv) {
     } else {
       n_sites -= n_sites % p.boot_block_size;                         // persistent truncation (ngsDist.cpp:236)
       const uint64_t n_blocks = n_sites / p.boot_block_size;
-      counts.resize(n_blocks);
+      counts.resize(std::max<uint64_t>(1, n_blocks));                 // non-NULL even for zero blocks: NULL means replicate 0
       ngsd_boot_block_counts(rng, n_blocks, counts.data());           // the draws of rnd_map_data (ngsDist.cpp:421-423)
       rc = ngsd_distances(ctx, counts.data(), n_blocks, p.boot_block_size, dist.data(), num.empty() ? nullptr : num.data(),
                           cnt.empty() ? nullptr : cnt.data());

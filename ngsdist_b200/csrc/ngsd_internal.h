@@ -169,6 +169,7 @@ cudaError_t ngsd_launch_frontend(ngsd_ctx *ctx, const ngsd_frontend_args &a);
 cudaError_t ngsd_launch_unpack(ngsd_ctx *ctx, double *P_dev /*[ind][site][3]*/, uint8_t *miss_dev /*[ind][site]*/);
 cudaError_t ngsd_launch_unpack_2bit(ngsd_ctx *ctx, const uint8_t *packed_dev, uint64_t row_stride, uint32_t code_of_field, uint64_t n,
                                     int8_t *codes_dev);   // packed fields -> [site][ind] int8 codes
+cudaError_t ngsd_launch_widen(ngsd_ctx *ctx, const void *src_dev, int format, double denom, uint64_t n, double *raw_dev);
 cudaError_t ngsd_launch_patch(ngsd_ctx *ctx, const ngsd_deferred *list_dev, unsigned n);
 cudaError_t ngsd_launch_synth(ngsd_ctx *ctx, double *raw_dev, uint64_t seed, double miss_rate, uint64_t site0, uint64_t n);
 
