@@ -553,7 +553,7 @@ def multi_gpu_extras(nb, torch, np, dist, multi, rank, world, local, share_id, b
     rb, rms = gc.comm_stats()
     fe_max = max_over_ranks(fe_ms)
     tot = fe_max + ag_ms + statistics.median(ms)
-    out["c4_tiles"] = {"workload": "C4: called genotypes 5000 ind x 5M sites, 5 % missing, --call_geno --pairwise_del (int8 tcgen05 path, bit-exact), "
+    out["c4_tiles"] = {"workload": "C4: called genotypes 5000 ind x 5M sites, 5 %% missing, --call_geno --pairwise_del (int8 tcgen05 path, bit-exact), "
                                    "site-sharded front end + NCCL all-gather of the 2-bit codes, output-triangle tiles dealt to %d ranks, NCCL assembly on rank 0" % world,
                        "frontend_ms_max_rank": fe_max, "allgather_ms": ag_ms, "allgather_bytes_per_rank": ag_bytes,
                        "matrix_ms": statistics.median(ms), "contraction_ms_max_rank": k_ms, "assembly_bytes": rb, "assembly_ms_rank0": rms,

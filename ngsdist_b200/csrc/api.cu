@@ -235,6 +235,13 @@ int ngsd_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
   CREATE_CUDA(dev_alloc(&ctx->Apack, plane));
   CREATE_CUDA(dev_alloc(&ctx->Bpack, plane));
   CREATE_CUDA(dev_alloc(&ctx->mask, ctx->RB * ctx->NW * 128));
+  // Padding must read as zero: in two-plane mode the last 12-site chunk can hold a k4-group beyond the last 64-site word
+  // (NW * 16 groups are written, NC * 3 are contracted), and cudaMalloc hands back whatever an earlier context left there.
+  if (plane) {
+    CREATE_CUDA(cudaMemsetAsync(ctx->Apack, 0, plane * sizeof(double), ctx->stream));
+    CREATE_CUDA(cudaMemsetAsync(ctx->Bpack, 0, plane * sizeof(double), ctx->stream));
+  }
+  CREATE_CUDA(cudaMemsetAsync(ctx->mask, 0, ctx->RB * ctx->NW * 128 * sizeof(uint64_t), ctx->stream));
   if (ctx->planes == 2) {
     ctx->ldc = ctx->n_pad;   // Cplane is [NW][n_pad][64]: the sites of a 64-site word are contiguous per individual
     CREATE_CUDA(dev_alloc(&ctx->Cplane, ctx->NW * ctx->n_pad * 64));

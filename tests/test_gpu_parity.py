@@ -77,7 +77,7 @@ def test_golden_cases_indep(case):
         assert np.allclose(r["dist"][fin], gm[fin], rtol=0, atol=6e-11)
         assert np.array_equal(np.isnan(r["dist"]), np.isnan(gm))
         assert (np.diag(r["dist"]) == 0).all()
-        assert np.array_equal(r["dist"], r["dist"].T)
+        assert np.array_equal(r["dist"], r["dist"].T, equal_nan=True)
 
 
 @pytest.mark.parametrize("case", [c for c in MAN["text"]], ids=lambda c: c["name"])
