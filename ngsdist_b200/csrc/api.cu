@@ -81,6 +81,17 @@ std::vector<uint32_t> plan_splits(uint32_t n_chunks, uint32_t n_tiles, double co
 
 void tick(ngsd_ctx *ctx, int k) { cudaEventRecord(ctx->ev[k], ctx->stream); }
 
+// Small host <-> device copies of bookkeeping arrays.  NOT cudaMemcpy: that runs on the legacy default stream, which the
+// context's non-blocking streams do not wait for, and a host-to-device copy from pageable memory may return while its
+// DMA is still in flight -- a kernel launched next on ctx->stream could read the old contents (seen: k_patch reading the
+// deferred list before the host's answers had landed).  Stream-ordered copy + synchronise instead.
+cudaError_t copy_sync(ngsd_ctx *ctx, void *dst, const void *src, size_t bytes, cudaMemcpyKind kind) {
+  if (bytes == 0) return cudaSuccess;
+  cudaError_t e = cudaMemcpyAsync(dst, src, bytes, kind, ctx->stream);
+  if (e != cudaSuccess) return e;
+  return cudaStreamSynchronize(ctx->stream);
+}
+
 // development aid: NGSD_SYNC=1 synchronises after every launch of ngsd_distances and names the one that failed
 cudaError_t dbg_sync(ngsd_ctx *ctx, const char *what) {
   static const bool on = getenv("NGSD_SYNC") != nullptr;
@@ -98,7 +109,7 @@ cudaError_t upload_tile_index(ngsd_ctx *ctx, const std::vector<ngsd_tile> &tiles
     cudaError_t e = cudaMalloc((void **) &ctx->d_tile_index, idx.size() * sizeof(uint32_t));
     if (e != cudaSuccess) return e;
   }
-  cudaError_t e = cudaMemcpy(ctx->d_tile_index, idx.data(), idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  cudaError_t e = copy_sync(ctx, ctx->d_tile_index, idx.data(), idx.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
   if (e != cudaSuccess) return e;
   // tiles of one row block share their A operand: dist_umma.cu contracts them two at a time (one 128 x 256 MMA)
   std::vector<uint32_t> pairs;
@@ -117,7 +128,7 @@ cudaError_t upload_tile_index(ngsd_ctx *ctx, const std::vector<ngsd_tile> &tiles
     if (e != cudaSuccess) return e;
   }
   if (pairs.empty()) return cudaSuccess;
-  return cudaMemcpy(ctx->d_pairs, pairs.data(), pairs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
+  return copy_sync(ctx, ctx->d_pairs, pairs.data(), pairs.size() * sizeof(uint32_t), cudaMemcpyHostToDevice);
 }
 
 }  // namespace
@@ -260,7 +271,7 @@ int ngsd_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
   ctx->n_tiles = (uint32_t) tiles.size();
   ctx->n_diag_tiles = (uint32_t) ctx->RB;
   CREATE_CUDA(dev_alloc(&ctx->d_tiles, tiles.size()));
-  CREATE_CUDA(cudaMemcpy(ctx->d_tiles, tiles.data(), tiles.size() * sizeof(ngsd_tile), cudaMemcpyHostToDevice));
+  CREATE_CUDA(copy_sync(ctx, ctx->d_tiles, tiles.data(), tiles.size() * sizeof(ngsd_tile), cudaMemcpyHostToDevice));
   CREATE_CUDA(upload_tile_index(ctx, tiles));
 #undef CREATE_CUDA
   *out = ctx;
@@ -606,7 +617,7 @@ extern "C" int ngsd_frontend_resolve(ngsd_ctx *ctx) {
   if (n == 0) return NGSD_OK;
   n = std::min(n, ctx->defer_cap);
   std::vector<ngsd_deferred> list(n);
-  NGSD_CUDA(ctx, cudaMemcpy(list.data(), ctx->d_defer, (size_t) n * sizeof(ngsd_deferred), cudaMemcpyDeviceToHost));
+  NGSD_CUDA(ctx, copy_sync(ctx, list.data(), ctx->d_defer, (size_t) n * sizeof(ngsd_deferred), cudaMemcpyDeviceToHost));
   bool nan_found = false;
   for (ngsd_deferred &d : list) {
     double p[3];
@@ -620,7 +631,7 @@ extern "C" int ngsd_frontend_resolve(ngsd_ctx *ctx) {
       if (fabs(delta) > 1e-9) { ctx->deficit.push_back({d.ind, d.site, delta}); ctx->deficit_dirty = true; }
     }
   }
-  NGSD_CUDA(ctx, cudaMemcpy(ctx->d_defer, list.data(), (size_t) n * sizeof(ngsd_deferred), cudaMemcpyHostToDevice));
+  NGSD_CUDA(ctx, copy_sync(ctx, ctx->d_defer, list.data(), (size_t) n * sizeof(ngsd_deferred), cudaMemcpyHostToDevice));
   NGSD_CUDA(ctx, ngsd_launch_patch(ctx, ctx->d_defer, n));
   NGSD_CUDA(ctx, cudaMemsetAsync(ctx->d_defer_n, 0, sizeof(unsigned), ctx->stream));
   if (nan_found) ctx->deferred_nan = true;
@@ -647,7 +658,7 @@ int ngsd_frontend_flags(ngsd_ctx *ctx) {
   ctx->any_blank = (flags & 4) != 0;
   if (ctx->any_blank) {        // sites that were empty text lines: the integer path gives them weight 0 (distances_int)
     ctx->h_blank.resize(ctx->NW);
-    NGSD_CUDA(ctx, cudaMemcpy(ctx->h_blank.data(), ctx->d_blank, ctx->NW * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    NGSD_CUDA(ctx, copy_sync(ctx, ctx->h_blank.data(), ctx->d_blank, ctx->NW * sizeof(uint64_t), cudaMemcpyDeviceToHost));
   }
   return NGSD_OK;
 }
@@ -739,10 +750,10 @@ static int upload_deficit(ngsd_ctx *ctx) {
     ctx->def_cap = cap;
   }
   if (!ctx->d_fix) NGSD_CUDA(ctx, dev_alloc(&ctx->d_fix, ctx->n_ind * ctx->n_ind));
-  NGSD_CUDA(ctx, cudaMemcpy(ctx->d_def_rowptr, rowptr.data(), rowptr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-  NGSD_CUDA(ctx, cudaMemcpy(ctx->d_def_rowind, rowind.data(), rowind.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
-  NGSD_CUDA(ctx, cudaMemcpy(ctx->d_def_site, site.data(), site.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
-  NGSD_CUDA(ctx, cudaMemcpy(ctx->d_def_delta, delta.data(), delta.size() * sizeof(double), cudaMemcpyHostToDevice));
+  NGSD_CUDA(ctx, copy_sync(ctx, ctx->d_def_rowptr, rowptr.data(), rowptr.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  NGSD_CUDA(ctx, copy_sync(ctx, ctx->d_def_rowind, rowind.data(), rowind.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  NGSD_CUDA(ctx, copy_sync(ctx, ctx->d_def_site, site.data(), site.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+  NGSD_CUDA(ctx, copy_sync(ctx, ctx->d_def_delta, delta.data(), delta.size() * sizeof(double), cudaMemcpyHostToDevice));
   ctx->def_rows = (uint32_t) rowind.size();
   ctx->deficit_dirty = false;
   return NGSD_OK;
@@ -1529,7 +1540,7 @@ int ngsd_set_tile_shard(ngsd_ctx *ctx, uint32_t rank, uint32_t world) {
   ctx->n_tiles = (uint32_t) mine.size();
   ctx->n_diag_tiles = 0;
   for (auto &t : mine) ctx->n_diag_tiles += (t.ti == t.tj);
-  if (!mine.empty()) NGSD_CUDA(ctx, cudaMemcpy(ctx->d_tiles, mine.data(), mine.size() * sizeof(ngsd_tile), cudaMemcpyHostToDevice));
+  if (!mine.empty()) NGSD_CUDA(ctx, copy_sync(ctx, ctx->d_tiles, mine.data(), mine.size() * sizeof(ngsd_tile), cudaMemcpyHostToDevice));
   NGSD_CUDA(ctx, upload_tile_index(ctx, mine));
   ctx->shard_rank = rank;
   ctx->shard_world = world;

@@ -250,9 +250,11 @@ int allgather_impl(ngsd_ctx *err_to, const std::vector<ngsd_ctx *> &cs, const ui
     if (rc) return rc;
     if (any_deficit) {                        // one process per GPU: the lists are host state of other processes -> refuse on every rank
       int f = 0;
-      NGSD_CUDA(err_to, cudaMemcpy(&f, c->d_err, sizeof(int), cudaMemcpyDeviceToHost));
+      NGSD_CUDA(err_to, cudaMemcpyAsync(&f, c->d_err, sizeof(int), cudaMemcpyDeviceToHost, c->stream));   // stream-ordered: see copy_sync in api.cu
+      NGSD_CUDA(err_to, cudaStreamSynchronize(c->stream));
       f |= 16;
-      NGSD_CUDA(err_to, cudaMemcpy(c->d_err, &f, sizeof(int), cudaMemcpyHostToDevice));
+      NGSD_CUDA(err_to, cudaMemcpyAsync(c->d_err, &f, sizeof(int), cudaMemcpyHostToDevice, c->stream));
+      NGSD_CUDA(err_to, cudaStreamSynchronize(c->stream));
     }
     NGSD_CUDA(err_to, cudaEventRecord(c->ev_comm[0], c->stream));
   }

@@ -390,38 +390,35 @@ __device__ __forceinline__ void pair_group26(const double *tb, const int *meta, 
   const double *rho_row = tb + kW_RhoRow, *rho_col = tb + kW_RhoCol, *fac_row = tb + kW_FacRow, *fac_col = tb + kW_FacCol;
   const int *ts = meta, *lo = meta + 128, *hi = meta + 256, *valid = meta + 384;
   int pos[4], cap[4], tfix[4];
-  const double *pr[4], *pc[4];
   bool ok[4];
+  int wide = 0;                                         // widest search interval of this thread's pairs
 #pragma unroll
   for (int e = 0; e < 4; e++) {
     const int h = e & 1, r = r0 + 16 * (e >> 1), cc = h * 32 + lane;
     ok[e] = (!diag || cc > r) && vcol[h] && valid[r] != 0;
     const int tm = min(max(ts[r], tcol[h]), L), lop = max(lo[r], locol[h]);
     cap[e] = ok[e] ? min(max(hi[r], hicol[h]), L + 1) : 0;              // the pair has stopped by cap (L + 1: not known to)
-    pos[e] = ok[e] ? max(tm + 1, lop) : 0;                               // ... and not before pos, once the prefix is scanned
+    pos[e] = ok[e] ? min(max(tm + 1, lop), L + 1) : 0;                   // ... and not before pos, once the prefix is scanned
     tfix[e] = 0;
     if (ok[e] && tm >= lop) {                           // rare: scan the non-monotone prefix
       for (int t = max(lop, 1); t <= tm; t++)
         if (rho_row[r * kWLd + t] * rho_col[t * kEdge + cc] < kExpTol) { tfix[e] = t; pos[e] = cap[e] = 0; break; }
     }
-    pos[e] = min(pos[e], L + 1);
-    pr[e] = rho_row + r * kWLd + pos[e];
-    pc[e] = rho_col + pos[e] * kEdge + cc;
+    wide = max(wide, cap[e] - pos[e]);
   }
-  // first t in [pos, cap] whose rho product is below e^0.001 -- cap itself needs no test (every t < pos is known to be above)
+  // first t in [pos, cap] whose rho product is below e^0.001 -- cap itself needs no test (every t < pos is known to be
+  // above).  Rounds wider than the widest interval in the warp cannot move anybody and are skipped (warp-uniform); the
+  // state is one int per pair, addresses are formed at the loads.
+  wide = __reduce_max_sync(0xFFFFFFFFu, wide);
 #pragma unroll
   for (int s = 16; s >= 1; s >>= 1) {
-    bool any = false;
-#pragma unroll
-    for (int e = 0; e < 4; e++) any |= pos[e] + s <= cap[e];
-    if (!__any_sync(0xFFFFFFFFu, any)) continue;
+    if (s > wide) continue;
 #pragma unroll
     for (int e = 0; e < 4; e++) {
-      const double prod = pr[e][s - 1] * pc[e][(s - 1) * kEdge];
-      const bool adv = (pos[e] + s <= cap[e]) && !(prod < kExpTol);
-      pos[e] += adv ? s : 0;
-      pr[e] += adv ? s : 0;
-      pc[e] += adv ? s * kEdge : 0;
+      const int h = e & 1, r = r0 + 16 * (e >> 1), cc = h * 32 + lane;
+      const int qn = pos[e] + s;                                        // probe t = qn - 1
+      const double prod = rho_row[r * kWLd + qn - 1] * rho_col[(qn - 1) * kEdge + cc];
+      if (qn <= cap[e] && !(prod < kExpTol)) pos[e] = qn;
     }
   }
   unsigned tailmask = 0;
