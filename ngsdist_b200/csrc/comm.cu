@@ -407,16 +407,22 @@ int ngsd_group_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
     const uint64_t bs = std::max<uint64_t>(1, cfg->boot_block_size);
     align = 64 / gcd64(64, bs) * bs;                            // whole bootstrap blocks and whole 64-site words
   }
-  parent->site_begin.assign(N + 1, 0);
-  for (int g = 1; g < N; g++) parent->site_begin[g] = (cfg->n_sites / align * (uint64_t) g / (uint64_t) N) * align;
-  parent->site_begin[N] = cfg->n_sites;
-  for (int g = 0; g < N; g++)
-    if (parent->site_begin[g + 1] <= parent->site_begin[g]) {
-      if (first) ngsd_destroy(first);
-      ngsd_set_error(nullptr, "%llu sites cannot be split over %d GPUs in units of %llu sites", (unsigned long long) cfg->n_sites, N, (unsigned long long) align);
-      return fail(NGSD_ERR_ARG);
+  // a data set too small to give every GPU a whole unit of sites runs on fewer of them (one: an ordinary context)
+  const int N_use = (int) std::max<uint64_t>(1, std::min<uint64_t>((uint64_t) N, cfg->n_sites / align));
+  if (N_use == 1) {
+    if (!first) {
+      kc.device = cfg->device;
+      int rc = ngsd_create(&kc, &first);
+      if (rc) return fail(rc);
     }
-  for (int g = 0; g < N; g++) {
+    delete parent;
+    *out = first;
+    return NGSD_OK;
+  }
+  parent->site_begin.assign(N_use + 1, 0);
+  for (int g = 1; g < N_use; g++) parent->site_begin[g] = (cfg->n_sites / align * (uint64_t) g / (uint64_t) N_use) * align;
+  parent->site_begin[N_use] = cfg->n_sites;
+  for (int g = 0; g < N_use; g++) {
     ngsd_ctx *k = nullptr;
     if (g == 0 && first) {
       k = first;
@@ -428,18 +434,18 @@ int ngsd_group_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
     }
     k->parent = parent;
     k->comm_rank = (uint32_t) g;
-    k->comm_world = (uint32_t) N;
+    k->comm_world = (uint32_t) N_use;
     parent->kids.push_back(k);
   }
-  std::vector<ncclComm_t> comms(N);
-  std::vector<int> devs(N);
-  for (int g = 0; g < N; g++) devs[g] = cfg->device + g;
-  ncclResult_t r = ncclCommInitAll(comms.data(), N, devs.data());
+  std::vector<ncclComm_t> comms(N_use);
+  std::vector<int> devs(N_use);
+  for (int g = 0; g < N_use; g++) devs[g] = cfg->device + g;
+  ncclResult_t r = ncclCommInitAll(comms.data(), N_use, devs.data());
   if (r != ncclSuccess) {
-    ngsd_set_error(nullptr, "NCCL error: %s (ncclCommInitAll over %d devices)", ncclGetErrorString(r), N);
+    ngsd_set_error(nullptr, "NCCL error: %s (ncclCommInitAll over %d devices)", ncclGetErrorString(r), N_use);
     return fail(NGSD_ERR_COMM);
   }
-  for (int g = 0; g < N; g++) parent->kids[g]->comm = comms[g];
+  for (int g = 0; g < N_use; g++) parent->kids[g]->comm = comms[g];
   *out = parent;
   return NGSD_OK;
 }

@@ -39,3 +39,20 @@ def test_group_context_rejects_more_gpus_than_visible():
     p = nb.Params(n_ind=10, n_sites=640, indep_geno=True)
     with pytest.raises(nb.NgsDistError):
         nb.NgsDistB200(p, n_gpus=_n_gpus() + 1)
+
+
+@pytest.mark.parametrize("shard", ["replicated", "sites"])
+@pytest.mark.parametrize("name", ["c1_indep_boot", "c1_thresh_boot_pdel", "c1_call_boot", "c1_em"])
+def test_cli_n_gpus_writes_the_reference_file(name, shard, tmp_path):
+    """The drop-in command line with --n_gpus 2: same bytes as the reference's .dist (goldens written by oracle/_ref/ngsDist)."""
+    if _n_gpus() < 2:
+        pytest.skip("needs 2 GPUs")
+    from util import GOLDEN, golden_text, manifest
+    case = [c for c in manifest()["binary"] if c["name"] == name][0]
+    out = str(tmp_path / "o.dist")
+    cli = os.path.join(ROOT, "ngsdist_b200", "bin", "ngsDist")
+    args = [cli, "--geno", os.path.join(GOLDEN, case["input"]), "--n_ind", str(case["n_ind"]), "--n_sites", str(case["n_sites"]), "--out", out,
+            "--n_threads", "4", "--verbose", "0", "--n_gpus", "2", "--shard", shard] + case["flags"]
+    r = subprocess.run(args, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert open(out).read() == golden_text(name)
