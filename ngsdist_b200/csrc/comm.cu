@@ -446,6 +446,20 @@ int ngsd_group_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
     return fail(NGSD_ERR_COMM);
   }
   for (int g = 0; g < N_use; g++) parent->kids[g]->comm = comms[g];
+  for (ngsd_ctx *k : parent->kids) {                       // connect every pair now (NCCL sets channels up lazily), see ngsd_comm_attach
+    cudaSetDevice(k->device);
+    if (ensure_tri(k, 2 * (uint64_t) N_use)) return fail(NGSD_ERR_CUDA);
+  }
+  bool okc = ncclGroupStart() == ncclSuccess;
+  for (ngsd_ctx *k : parent->kids)
+    for (int p = 0; p < N_use && okc; p++) {
+      if ((uint32_t) p == k->comm_rank) continue;
+      okc = okc && ncclSend(k->d_tri + k->comm_rank, 1, ncclDouble, p, comm_of(k), k->stream) == ncclSuccess;
+      okc = okc && ncclRecv(k->d_tri + N_use + p, 1, ncclDouble, p, comm_of(k), k->stream) == ncclSuccess;
+    }
+  okc = (ncclGroupEnd() == ncclSuccess) && okc;
+  for (ngsd_ctx *k : parent->kids) { cudaSetDevice(k->device); okc = okc && cudaStreamSynchronize(k->stream) == cudaSuccess; }
+  if (!okc) { ngsd_set_error(nullptr, "NCCL error while connecting the GPUs of the group"); return fail(NGSD_ERR_COMM); }
   *out = parent;
   return NGSD_OK;
 }
@@ -733,6 +747,19 @@ int ngsd_comm_attach(ngsd_ctx *ctx, const uint8_t id[NGSD_COMM_ID_BYTES], uint32
   ctx->comm = comm;
   ctx->comm_rank = rank;
   ctx->comm_world = world;
+  // NCCL connects lazily: the first collective and the first send / recv between two ranks pay for the channel set-up
+  // (seconds on a fresh communicator).  Do both here, so that "attached" means "connected" and no data-path call does.
+  int rc = ensure_tri(ctx, 2 * (uint64_t) world);
+  if (rc) return rc;
+  NGSD_NCCL(ctx, ncclAllReduce(ctx->d_tri, ctx->d_tri, 1, ncclDouble, ncclSum, comm, ctx->stream));
+  NGSD_NCCL(ctx, ncclGroupStart());
+  for (uint32_t p = 0; p < world; p++) {
+    if (p == rank) continue;
+    NGSD_NCCL(ctx, ncclSend(ctx->d_tri + rank, 1, ncclDouble, (int) p, comm, ctx->stream));
+    NGSD_NCCL(ctx, ncclRecv(ctx->d_tri + world + p, 1, ncclDouble, (int) p, comm, ctx->stream));
+  }
+  NGSD_NCCL(ctx, ncclGroupEnd());
+  NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return NGSD_OK;
 }
 

@@ -15,7 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--n-ind", type=int, default=20000)
 ap.add_argument("--n-sites", type=int, default=10_000_000)
 ap.add_argument("--chunk", type=int, default=2048)
-ap.add_argument("--slab", type=int, default=160_000, help="sites contracted per ngsd_distances call (operands of a slab stay resident)")
+ap.add_argument("--slab", type=int, default=98_304, help="sites contracted per ngsd_distances call (operands of a slab stay resident)")
 ap.add_argument("--check", action="store_true")
 args = ap.parse_args()
 rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
