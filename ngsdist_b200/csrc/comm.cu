@@ -448,14 +448,15 @@ int ngsd_group_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
   for (int g = 0; g < N_use; g++) parent->kids[g]->comm = comms[g];
   for (ngsd_ctx *k : parent->kids) {                       // connect every pair now (NCCL sets channels up lazily), see ngsd_comm_attach
     cudaSetDevice(k->device);
-    if (ensure_tri(k, 2 * (uint64_t) N_use)) return fail(NGSD_ERR_CUDA);
+    if (ensure_tri(k, 2 * ((uint64_t) 1 << 19) * N_use)) return fail(NGSD_ERR_CUDA);
   }
+  const uint64_t kWarm = (uint64_t) 1 << 19;
   bool okc = ncclGroupStart() == ncclSuccess;
   for (ngsd_ctx *k : parent->kids)
     for (int p = 0; p < N_use && okc; p++) {
       if ((uint32_t) p == k->comm_rank) continue;
-      okc = okc && ncclSend(k->d_tri + k->comm_rank, 1, ncclDouble, p, comm_of(k), k->stream) == ncclSuccess;
-      okc = okc && ncclRecv(k->d_tri + N_use + p, 1, ncclDouble, p, comm_of(k), k->stream) == ncclSuccess;
+      okc = okc && ncclSend(k->d_tri + (uint64_t) p * kWarm, kWarm, ncclDouble, p, comm_of(k), k->stream) == ncclSuccess;
+      okc = okc && ncclRecv(k->d_tri + (uint64_t) (N_use + p) * kWarm, kWarm, ncclDouble, p, comm_of(k), k->stream) == ncclSuccess;
     }
   okc = (ncclGroupEnd() == ncclSuccess) && okc;
   for (ngsd_ctx *k : parent->kids) { cudaSetDevice(k->device); okc = okc && cudaStreamSynchronize(k->stream) == cudaSuccess; }
@@ -749,14 +750,16 @@ int ngsd_comm_attach(ngsd_ctx *ctx, const uint8_t id[NGSD_COMM_ID_BYTES], uint32
   ctx->comm_world = world;
   // NCCL connects lazily: the first collective and the first send / recv between two ranks pay for the channel set-up
   // (seconds on a fresh communicator).  Do both here, so that "attached" means "connected" and no data-path call does.
-  int rc = ensure_tri(ctx, 2 * (uint64_t) world);
+  // (with messages large enough for the bulk protocol: its buffers are set up on first use as well)
+  const uint64_t kWarm = (uint64_t) 1 << 19;                             // 4 MiB per peer and direction
+  int rc = ensure_tri(ctx, 2 * kWarm * world);
   if (rc) return rc;
-  NGSD_NCCL(ctx, ncclAllReduce(ctx->d_tri, ctx->d_tri, 1, ncclDouble, ncclSum, comm, ctx->stream));
+  NGSD_NCCL(ctx, ncclAllReduce(ctx->d_tri, ctx->d_tri, kWarm, ncclDouble, ncclSum, comm, ctx->stream));
   NGSD_NCCL(ctx, ncclGroupStart());
   for (uint32_t p = 0; p < world; p++) {
     if (p == rank) continue;
-    NGSD_NCCL(ctx, ncclSend(ctx->d_tri + rank, 1, ncclDouble, (int) p, comm, ctx->stream));
-    NGSD_NCCL(ctx, ncclRecv(ctx->d_tri + world + p, 1, ncclDouble, (int) p, comm, ctx->stream));
+    NGSD_NCCL(ctx, ncclSend(ctx->d_tri + (uint64_t) p * kWarm, kWarm, ncclDouble, (int) p, comm, ctx->stream));
+    NGSD_NCCL(ctx, ncclRecv(ctx->d_tri + (uint64_t) (world + p) * kWarm, kWarm, ncclDouble, (int) p, comm, ctx->stream));
   }
   NGSD_NCCL(ctx, ncclGroupEnd());
   NGSD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
