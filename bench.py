@@ -537,7 +537,8 @@ def multi_gpu_extras(nb, torch, np, dist, multi, rank, world, local, share_id, b
         gc.push_sites_device(buf.data_ptr(), s0, m)
         fe_ms += gc.timing().frontend_ms
     del buf
-    ag_ms = span(st, lambda: gc.comm_allgather_operands(sb))
+    ag_first_ms = span(st, lambda: gc.comm_allgather_operands(sb))      # first exchange on this communicator
+    ag_ms = span(st, lambda: gc.comm_allgather_operands(sb))            # steady state (same bytes again)
     ag_bytes = gc.comm_stats()[0]
     gc.set_tile_shard(rank, world)
     oc = torch.empty((cn, cn), dtype=torch.float64).pin_memory() if rank == 0 else None
@@ -555,7 +556,7 @@ def multi_gpu_extras(nb, torch, np, dist, multi, rank, world, local, share_id, b
     tot = fe_max + ag_ms + statistics.median(ms)
     out["c4_tiles"] = {"workload": "C4: called genotypes 5000 ind x 5M sites, 5 %% missing, --call_geno --pairwise_del (int8 tcgen05 path, bit-exact), "
                                    "site-sharded front end + NCCL all-gather of the 2-bit codes, output-triangle tiles dealt to %d ranks, NCCL assembly on rank 0" % world,
-                       "frontend_ms_max_rank": fe_max, "allgather_ms": ag_ms, "allgather_bytes_per_rank": ag_bytes,
+                       "frontend_ms_max_rank": fe_max, "allgather_ms": ag_ms, "allgather_first_call_ms": ag_first_ms, "allgather_bytes_per_rank": ag_bytes,
                        "matrix_ms": statistics.median(ms), "contraction_ms_max_rank": k_ms, "assembly_bytes": rb, "assembly_ms_rank0": rms,
                        "total_ms": tot, "value": pairs(cn) * cs / (tot * 1e-3), "value_matrix_only": pairs(cn) * cs / (statistics.median(ms) * 1e-3), "unit": UNIT}
     gc.close()
