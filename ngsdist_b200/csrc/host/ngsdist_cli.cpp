@@ -66,6 +66,11 @@ struct Pars {
 
 static const char *kModels[] = {"Raw p-distance", "Log transf. p-distance", "JC69", "K80", "F81", "HKY85/F84", "TN93"};
 
+static bool is_vcf_name(const char *name) {
+  const size_t len = name ? strlen(name) : 0;
+  return (len > 7 && strcmp(name + len - 7, ".vcf.gz") == 0) || (len > 4 && strcmp(name + len - 4, ".vcf") == 0);
+}
+
 static void parse_args(Pars *p, int argc, char **argv) {
   static struct option lopts[] = {
       {"geno", required_argument, nullptr, 'g'},       {"probs", no_argument, nullptr, 'p'},
@@ -120,6 +125,7 @@ static void parse_args(Pars *p, int argc, char **argv) {
       default: exit(-1);
     }
   }
+  if (is_vcf_name(p->in_geno)) p->in_probs = p->in_logscale = true;   // a VCF holds log-scale likelihoods whatever the flags say
   if (p->verbose >= 1) {
     fprintf(stderr, "==> Input Arguments:\n");
     fprintf(stderr,
@@ -352,6 +358,7 @@ int main(int argc, char **argv) {
   if (argc >= 2 && strcmp(argv[1], "--selftest_io") == 0) return selftest_io(argc >= 3 ? (uint64_t) atol(argv[2]) : 1000000);
   Pars p;
   parse_args(&p, argc, argv);
+  const bool in_vcf = is_vcf_name(p.in_geno);
   const uint64_t n_comb = (uint64_t) ((pow((double) p.n_ind, 2) - p.n_ind) / 2);
   if (p.verbose >= 1) fprintf(stderr, "==> Analysis will be run in %lu combinations\n", n_comb);
   // forcing rules of ngsDist.cpp:55-65
@@ -366,7 +373,14 @@ int main(int argc, char **argv) {
   }
   // input kind (ngsDist.cpp:73-95)
   bool in_bed = false;
-  if (strcmp(p.in_geno, "-") == 0) {
+  if (in_vcf) {
+    // Extension: genotype likelihoods straight from a VCF -- FORMAT/GL (log10) or FORMAT/PL (phred) of
+    // biallelic records, one site per record, samples in column order.  They enter the front end as natural-log
+    // likelihoods through the text reader's --log_scale path (read_data.cpp:83-87,98), i.e. exactly as if the same
+    // numbers had been written to a .gz text file and read with --probs --log_scale.
+    if (p.verbose >= 1) fprintf(stderr, "==> VCF input file (FORMAT/GL or FORMAT/PL genotype likelihoods)\n");
+    p.in_bin = false;
+  } else if (strcmp(p.in_geno, "-") == 0) {
     if (p.verbose >= 1) fprintf(stderr, "==> Reading from STDIN (BINARY)\n");
     p.in_bin = true;
   } else {
@@ -574,6 +588,77 @@ int main(int argc, char **argv) {
       }
     }
   };
+  // VCF records -> natural-log likelihood triples (see in_vcf above)
+  auto parse_vcf_record = [&](const std::string &line, double *dst) {
+    std::vector<const char *> col;
+    col.reserve(p.n_ind + 9);
+    const char *b = line.c_str();
+    col.push_back(b);
+    for (const char *c = b; *c; c++)
+      if (*c == '\t') col.push_back(c + 1);
+    if (col.size() != p.n_ind + 9) die("read_geno", "wrong VCF file format. Number of sample columns differs from --n_ind!");
+    auto field_end = [](const char *c) { while (*c && *c != '\t') c++; return c; };
+    for (const char *c = col[4]; c < field_end(col[4]); c++)
+      if (*c == ',') die("read_geno", "wrong VCF file format. Only biallelic records are supported!");
+    // position of GL / PL inside FORMAT
+    int idx = -1, k = 0;
+    bool phred = false;
+    for (const char *c = col[8], *e = field_end(col[8]); c < e; k++) {
+      const char *q = c;
+      while (q < e && *q != ':') q++;
+      if (q - c == 2 && c[0] == 'G' && c[1] == 'L') { idx = k; phred = false; break; }
+      if (q - c == 2 && c[0] == 'P' && c[1] == 'L' && idx < 0) { idx = k; phred = true; }
+      c = q + 1;
+    }
+    if (idx < 0) die("read_geno", "wrong VCF file format. FORMAT holds neither GL nor PL!");
+    const double ln10 = 2.302585092994046;
+    for (uint64_t i = 0; i < p.n_ind; i++) {
+      const char *c = col[9 + i], *e = field_end(c);
+      for (int f = 0; f < idx && c < e; f++) { while (c < e && *c != ':') c++; if (c < e) c++; }
+      const char *fe = c;
+      while (fe < e && *fe != ':') fe++;
+      double v[3];
+      int got = 0;
+      while (c < fe && got < 3) {
+        const char *q = c;
+        while (q < fe && *q != ',') q++;
+        if (!fastio::parse_number(c, q, &v[got])) break;
+        got++;
+        c = q + 1;
+      }
+      for (int g = 0; g < 3; g++) {
+        if (got < 3) dst[i * 3 + g] = log(1.0 / 3);                      // "." = no data: equal likelihoods -> missing
+        else dst[i * 3 + g] = phred ? -v[g] / 10 * ln10 : v[g] * ln10;
+      }
+    }
+  };
+  auto fill_vcf = [&](Slot &sl) {
+    uint64_t s = 0;
+    sl.packable = false;
+    while (s < sl.n) {
+      const uint64_t want = sl.n - s;
+      if (lines.size() < want) lines.resize(want);
+      uint64_t have = 0;
+      while (have < want) {
+        if (!read_line(fh, lines[have])) {
+          if (gzeof(fh)) die("read_geno", "GENO file at premature EOF. Check GENO file and number of sites!");
+          die("read_geno", "cannot read GZip GENO file. Check GENO file and number of sites!");
+        }
+        if (lines[have].empty() || lines[have][0] == '#') continue;       // meta lines and the #CHROM header
+        have++;
+      }
+      const unsigned T = (unsigned) std::max<uint64_t>(1, std::min<uint64_t>(p.n_threads, want / 8 + 1));
+      auto range = [&](uint64_t k0, uint64_t k1) { for (uint64_t k = k0; k < k1; k++) parse_vcf_record(lines[k], sl.raw + (s + k) * per_site); };
+      if (T == 1) {
+        range(0, want);
+      } else {
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < T; t++) th.emplace_back(range, want * t / T, want * (t + 1) / T);
+        for (auto &x : th) x.join();
+      }
+      s += want;
+    }
+  };
   std::thread reader([&]() {
     int w = 0;
     for (uint64_t s0 = 0; s0 < p.n_sites; s0 += chunk, w ^= 1) {
@@ -584,7 +669,7 @@ int main(int argc, char **argv) {
       }
       sl.s0 = s0;
       sl.n = (p.n_sites - s0 < chunk) ? p.n_sites - s0 : chunk;
-      if (p.in_bin) fill_binary(sl); else fill_text(sl);
+      if (p.in_bin) fill_binary(sl); else if (in_vcf) fill_vcf(sl); else fill_text(sl);
       {
         std::lock_guard<std::mutex> lk(mu);
         sl.full = true;

@@ -3,6 +3,7 @@
 CPU part: argument validation reproduces parse_args.cpp:203-220 (message + exit status 255) before any CUDA call.
 GPU part: every golden case is run through the binary and compared with the reference's own .dist text.
 """
+import gzip
 import os
 import subprocess
 
@@ -258,3 +259,65 @@ def test_cli_plink_bed_input_matches_genotype_text(tmp_path):
     assert r.returncode != 0 and "variant-major" in r.stderr
     r = run_cli(["--geno", bed, "--out", str(tmp_path / "x"), "--n_ind", str(n_ind), "--n_sites", str(n_sites + 1), "--verbose", "0"])
     assert r.returncode != 0 and "invalid/corrupt genotype input file!" in r.stderr
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fmt", ["GL", "PL"])
+@pytest.mark.parametrize("flags", [["--indep_geno", "--pairwise_del"], [], ["--call_geno"]], ids=["indep_pdel", "em", "call"])
+def test_cli_vcf_likelihoods_are_the_log_scale_text_input(fmt, flags, tmp_path):
+    """Extension: FORMAT/GL (log10) or FORMAT/PL (phred) of a VCF enter the front end as natural-log
+    likelihoods -- byte-identical output to the same numbers written as a .gz text file and read with --probs --log_scale
+    (the reference's own text path, read_data.cpp:83-87,98)."""
+    import math
+    n_ind, n_sites = 9, 70
+    raw = oracle.synth_raw(41, 0.1, n_ind, n_sites)
+    rng = np.random.RandomState(1)
+    vcf = tmp_path / "in.vcf.gz"
+    txt = tmp_path / "in.txt.gz"
+    with gzip.open(vcf, "wt") as fv, gzip.open(txt, "wt") as ft:
+        fv.write("##fileformat=VCFv4.2\n##FORMAT=<ID=GT,Number=1,Type=String,Description=\"g\">\n")
+        fv.write("#CHROM\tPOS\tID\tREF\tALT\tQUAL\tFILTER\tINFO\tFORMAT\t" + "\t".join("S%d" % i for i in range(n_ind)) + "\n")
+        for s in range(n_sites):
+            cols, vals = [], []
+            for i in range(n_ind):
+                if rng.rand() < 0.1:
+                    cols.append("./.:.:3")
+                    vals += [repr(math.log(1.0 / 3))] * 3
+                    continue
+                if fmt == "GL":
+                    f = ["%.4f" % math.log10(max(x, 1e-30)) for x in raw[s, i]]
+                    L = [float(t) * 2.302585092994046 for t in f]
+                else:
+                    f = ["%d" % min(255, int(round(-10 * math.log10(max(x, 1e-30))))) for x in raw[s, i]]
+                    L = [-float(t) / 10 * 2.302585092994046 for t in f]
+                cols.append("0/1:" + ",".join(f) + ":7")
+                vals += [repr(v) for v in L]
+            fv.write("chr1\t%d\t.\tA\tC\t.\tPASS\t.\tGT:%s:DP\t" % (s + 1, fmt) + "\t".join(cols) + "\n")
+            ft.write("\t".join(vals) + "\n")
+    outs = []
+    for path, extra in ((vcf, []), (txt, ["--probs", "--log_scale"])):
+        out = str(tmp_path / (os.path.basename(str(path)) + ".dist"))
+        r = run_cli(["--geno", str(path), "--n_ind", str(n_ind), "--n_sites", str(n_sites), "--out", out, "--n_threads", "3", "--verbose", "0",
+                     "--n_boot_rep", "2", "--boot_block_size", "7", "--seed", "12345"] + extra + flags)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(open(out).read())
+    assert outs[0] == outs[1]
+    if oracle.have_ref():      # ... and that text file through the reference binary: the same bytes
+        _, ref_text = oracle.run_reference(None, ["--probs", "--log_scale", "--n_boot_rep", "2", "--boot_block_size", "7", "--seed", "12345"] + flags,
+                                           geno_path=str(txt), n_ind=n_ind, n_sites=n_sites)
+        assert outs[0] == ref_text
+
+
+@pytest.mark.gpu
+def test_cli_packs_six_decimal_text_posteriors(tmp_path):
+    """6-decimal .gz posteriors travel as 3 x 20 bits (NGSD_XFER_U20X3); NGSD_CLI_NO_PACK=1 sends the doubles: same bytes out."""
+    case = [c for c in MAN["text"] if c["name"] == "txt_grid_pdel"][0]
+    outs = []
+    for env in ({}, {"NGSD_CLI_NO_PACK": "1"}):
+        out = str(tmp_path / ("o%d.dist" % len(outs)))
+        r = subprocess.run([CLI, "--geno", os.path.join(GOLDEN, case["input"]), "--n_ind", str(case["n_ind"]), "--n_sites", str(case["n_sites"]),
+                            "--out", out, "--verbose", "0"] + case["flags"], env=dict(os.environ, **env), stdout=subprocess.PIPE,
+                           stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 0, r.stderr[-2000:]
+        outs.append(open(out).read())
+    assert outs[0] == outs[1] == golden_text(case["name"])
