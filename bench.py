@@ -442,6 +442,40 @@ def single_gpu_extras(nb, torch, np, local, multi):
         if indep:
             res[name]["frontend_gbs_algorithmic_48B"] = n * s * 48 / (statistics.median(fe) * 1e-3) * 1e-9
         gq.close()
+    # ---- transport tiers on C2: the same matrix end to end from host memory, 24 B vs 8 B per individual-site ----
+    try:
+        pz = raw / raw.sum(dim=2, keepdim=True)
+        q = torch.round(pz * 1e6).to(torch.int64)                         # 6-decimal posteriors (what ANGSD -doGeno 8 prints)
+        dec = (q.to(torch.float64) / 1e6)                                 # the doubles a text reader gets from them (IEEE division)
+        packed = (q[..., 0] | (q[..., 1] << 20) | (q[..., 2] << 40)).contiguous()
+        h_dec = torch.empty(dec.shape, dtype=torch.float64).pin_memory(); h_dec.copy_(dec)
+        h_pk = torch.empty(packed.shape, dtype=torch.int64).pin_memory(); h_pk.copy_(packed)
+        del pz, q, dec, packed
+        tiers = {}
+        mats = {}
+        for name in ("f64", "u20x3"):
+            gt = nb.NgsDistB200(nb.Params(n_ind=n, n_sites=s, in_probs=True, indep_geno=True, evol_model=2, in_text=True), device=local)
+            o = torch.empty((n, n), dtype=torch.float64).pin_memory()
+            best = None
+            for it in range(5):
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                if name == "f64":
+                    gt.push_sites_ptr(h_dec.data_ptr(), 0, s)
+                else:
+                    gt.push_sites_packed_ptr(h_pk.data_ptr(), nb.XFER_U20X3, 1e6, 0, s)
+                gt.distances_raw(None, 0, 1, o.data_ptr())
+                dt = time.perf_counter() - t0
+                if it >= 2:
+                    best = dt if best is None else min(best, dt)
+            mats[name] = o.clone()
+            tiers[name] = {"ms": best * 1e3, "h2d_bytes": n * s * (24 if name == "f64" else 8), "value": pairs(n) * s / best, "unit": UNIT}
+            gt.close()
+        tiers["bit_identical"] = bool(torch.equal(mats["f64"], mats["u20x3"]))
+        res["e2e_transport"] = {"workload": "C2 from pinned host memory, 6-decimal posteriors: doubles vs 3 x 20-bit fixed point (ngsd_push_sites_packed)", **tiers}
+        del h_dec, h_pk
+    except Exception as ex:
+        res["e2e_transport"] = {"error": str(ex)[:200]}
     del raw
     out["c2"] = {"workload": "C2: 500 ind x 100k sites, --probs --evol_model 2: with --indep_geno (2-plane DMMA contraction) and the literal default "
                              "(per pair-site EM, emOptim2.cpp em2, kernel k_dist_em); front end + contraction + epilogue, device time", **res}

@@ -13,7 +13,7 @@ from dataclasses import dataclass, field
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "libngsdist_b200.so")
+_LIB = os.environ.get("NGSDIST_B200_LIB") or os.path.join(_HERE, "libngsdist_b200.so")   # (override: A/B builds of the same ABI)
 
 ABI_SYMBOLS = [
     "ngsd_abi_version", "ngsd_default_cfg", "ngsd_create", "ngsd_destroy", "ngsd_last_error", "ngsd_push_sites",

@@ -241,6 +241,7 @@ int ngsd_create(const ngsd_cfg *cfg, ngsd_ctx **out) {
     ctx->sc = NGSD_SC;
     ctx->NC = ctx->NW * 8;
     CREATE_CUDA(dev_alloc(&ctx->codes, ctx->RB * ctx->NW * 512));
+    CREATE_CUDA(dev_alloc(&ctx->codes4, ctx->RB * ctx->NW * 1024));
   }
   const uint64_t plane = ctx->int_path ? 0 : ctx->RB * ctx->NC * NGSD_TILE_DOUBLES;
   CREATE_CUDA(dev_alloc(&ctx->Apack, plane));
@@ -292,7 +293,7 @@ int ngsd_destroy(ngsd_ctx *ctx) {
   cudaFree(ctx->d_ent_word); cudaFree(ctx->d_ent_mask); cudaFree(ctx->d_cnt); cudaFree(ctx->d_split_begin); cudaFree(ctx->d_split_scale); cudaFree(ctx->d_sched);
   cudaFree(ctx->d_out); cudaFree(ctx->d_num); cudaFree(ctx->d_cntout);
   cudaFree(ctx->d_cache); cudaFree(ctx->d_cnt_cache); cudaFree(ctx->d_ent_begin); cudaFree(ctx->d_tile_index); cudaFree(ctx->d_pairs);
-  cudaFree(ctx->codes); cudaFree(ctx->d_wsite); cudaFree(ctx->d_word_layer); cudaFree(ctx->d_word_ids);
+  cudaFree(ctx->codes); cudaFree(ctx->codes4); cudaFree(ctx->d_wsite); cudaFree(ctx->d_word_layer); cudaFree(ctx->d_word_ids);
   cudaFree(ctx->d_defer); cudaFree(ctx->d_defer_n); cudaFree(ctx->d_blank);
   cudaFree(ctx->d_def_rowptr); cudaFree(ctx->d_def_rowind); cudaFree(ctx->d_def_site); cudaFree(ctx->d_def_delta); cudaFree(ctx->d_fix);
   if (ctx->h_pin) cudaFreeHost(ctx->h_pin);

@@ -211,7 +211,10 @@ void site_range_segments(ngsd_ctx *c, uint64_t s0, uint64_t s1, bool last, std::
     if (rb == 0 && w1 > w0) out.push_back({(char *) (c->d_blank + w0), (w1 - w0) * sizeof(uint64_t)});
     if (w1 > w0) {
       out.push_back({(char *) (c->mask + (rb * c->NW + w0) * 128), (w1 - w0) * 128 * sizeof(uint64_t)});
-      if (c->int_path) out.push_back({(char *) (c->codes + (rb * c->NW + w0) * 512), (w1 - w0) * 512 * sizeof(uint32_t)});
+      if (c->int_path) {
+        out.push_back({(char *) (c->codes + (rb * c->NW + w0) * 512), (w1 - w0) * 512 * sizeof(uint32_t)});
+        out.push_back({(char *) (c->codes4 + (rb * c->NW + w0) * 1024), (w1 - w0) * 1024 * sizeof(uint32_t)});
+      }
     }
   }
   if (c->planes == 2 && !c->int_path && w1 > w0) out.push_back({(char *) (c->Cplane + w0 * c->n_pad * 64), (w1 - w0) * c->n_pad * 64 * sizeof(double)});

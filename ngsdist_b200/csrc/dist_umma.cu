@@ -30,11 +30,19 @@
 
 namespace {
 
-constexpr int kRaw = 4;                           // raw (packed codes) stages
-constexpr int kExp = 3;                           // expanded operand stages
+// Stage counts (A/B on 5 000 x 100 000, round 2): 2 raw + 3 expanded stages 3.60 ms, 4 raw + 2 expanded 3.74 ms; the nibble
+// codes doubled the raw stage, so 4 + 3 no longer fits the 227 KiB of shared memory.
+#ifndef NGSD_UMMA_KRAW
+#define NGSD_UMMA_KRAW 2
+#endif
+#ifndef NGSD_UMMA_KEXP
+#define NGSD_UMMA_KEXP 3
+#endif
+constexpr int kRaw = NGSD_UMMA_KRAW;              // raw (packed codes) stages
+constexpr int kExp = NGSD_UMMA_KEXP;              // expanded operand stages
 constexpr int kExpWarps = 16, kEpiWarps = 4;
 constexpr int kThreads = (2 + kExpWarps + kEpiWarps) * 32;
-constexpr int kCodeBytes = 4 * 128 * 4;           // [4 words][128 rows] uint32, one operand of one 64-site stage
+constexpr int kCodeBytes = 8 * 128 * 4;           // [8 words][128 rows] uint32 of selector nibbles (codes4), one operand of one 64-site stage
 constexpr int kMaskBytes = 128 * 8;               // presence bits of one operand of one stage (count pass)
 constexpr int kRawBytes = 3 * kCodeBytes + 128;   // A codes, B codes of the two tiles, 64 site weights; a multiple of 128 so that a warp's 32 code words stay in one bank row
 constexpr int kOpBytes = 16 * 16 * 128;           // expanded A operand: [16 site quads][16 row groups][8 rows][16 B] = 32 KiB
@@ -44,9 +52,12 @@ constexpr int kCntGroup = 4;                      // count pass: word-list entri
 constexpr int kCntEntry = 3 * kMaskBytes;         // count pass raw stage: kCntGroup x {A, B, B' masks} then kCntGroup x 64 weights
 constexpr int kCntRawBytes = kCntGroup * (kCntEntry + 64);
 constexpr int kCntRaw = 2;                        // ... and two of those stages fill the same ring bytes
-static_assert(kCntRaw * kCntRawBytes <= kRaw * kRawBytes && kCntRawBytes % 128 == 0, "count-pass raw ring must fit the code ring");
+static_assert(kCntRawBytes % 128 == 0 && kCntRaw <= kRaw, "count-pass raw stages reuse the code ring's barriers");
+constexpr int kRingBytes = kRaw * kRawBytes > kCntRaw * kCntRawBytes ? kRaw * kRawBytes : kCntRaw * kCntRawBytes;
 constexpr int kNBar = 2 * kRaw + 2 * kExp + 4;
-constexpr size_t kSmemBytes = (size_t) kRaw * kRawBytes + (size_t) kExp * kExpBytes + kNBar * 8 + (kRaw + kExp + 2) * 8 + 16 + 16 + 1024;
+constexpr size_t kSmemBytes = (size_t) kRingBytes + (size_t) kExp * kExpBytes + kNBar * 8 + (kRaw + kExp + 2) * 8 + 16 + 16 + 64 + 1024;
+static_assert(kSmemBytes <= 232448, "k_dist_umma shared memory");
+static_assert(kAccCols + kExp * kACols <= 512, "k_dist_umma tensor memory");
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t) __cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
@@ -120,7 +131,7 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint4 v) {
 }
 
 struct UmmaArgs {
-  const uint32_t *codes;        // [RB][NW][4][128]
+  const uint32_t *codes;        // codes4 [RB][NW][8][128]: selector nibbles, 8 sites per word
   const uint64_t *mask;         // [RB][NW][128] presence bits (count pass)
   const uint32_t *pairs;        // [n_pairs][2] tile positions of a unit (second 0xFFFFFFFF: single tile)
   const uint8_t *wsite;         // [n_layers][NW * 64]
@@ -143,19 +154,19 @@ enum : uint32_t { kFirst = 1u, kLast = 2u, kPair = 4u, kExit = 8u, kUnitW = 16u,
 // 4 selector nibbles, PRMT(T_k, sel) picks byte c_j of T_k for site j:  T_k = 0xFF << 8k gives the one-hot plane k of A
 // (AND the 4 weight bytes; UNITW: all 64 site weights are 1, T_k = 0x01 << 8k and no AND), T_k = row k of the S * f
 // table gives plane k of B.  No table loads.
-__device__ __forceinline__ uint32_t spread_codes(uint32_t word, uint32_t pick) {
-  const uint32_t x = __byte_perm(word, 0u, pick);                   // byte q0 of the code word, zero-extended
-  const uint32_t s = (x | (x << 4)) & 0x0F0Fu;
-  return (s | (s << 2)) & 0x3333u;
-}
+// (round 2: the codes arrive as selector nibbles -- codes4, spread once by the front end -- so the selector of a site quad
+// is one 16-bit half of a word; the shift-and-mask spreading that used to run here for every tile was a third of the
+// expanders' integer work)
+__device__ __forceinline__ uint32_t pick_half(uint32_t word, uint32_t pick) { return __byte_perm(word, 0u, pick); }
 template <bool UNITW>
 __device__ __forceinline__ void expand_codes(const uint32_t *cA, const uint32_t *cB, const uint32_t *cB1, const uint32_t *W32,
                                              unsigned char *eB, uint32_t ta, int q0, bool paired, const uint32_t (&rowk)[4]) {
   constexpr int kBChunk = 4096;
-  const uint32_t pick = 0x4440u + (uint32_t) q0;
+  const uint32_t pick = (q0 & 1) ? 0x4432u : 0x4410u;               // site quad 4 i + q0 = half (q0 & 1) of nibble word 2 i + (q0 >> 1)
+  const int w0 = (q0 >> 1) * 128;
 #pragma unroll
-  for (int i = 0; i < 4; i++) {                                     // code word i: sites 16 i + 4 q0 .. + 3 = site quad 4 i + q0
-    const uint32_t sx = spread_codes(cA[i * 128], pick), sy = spread_codes(cB[i * 128], pick);
+  for (int i = 0; i < 4; i++) {                                     // sites 16 i + 4 q0 .. + 3 = site quad 4 i + q0
+    const uint32_t sx = pick_half(cA[i * 256 + w0], pick), sy = pick_half(cB[i * 256 + w0], pick);
     uint4 va, vb;
     if (UNITW) {
       va.x = __byte_perm(0x00000001u, 0u, sx);
@@ -177,7 +188,7 @@ __device__ __forceinline__ void expand_codes(const uint32_t *cA, const uint32_t 
     tmem_st4(ta + 16u * i, va);                                     // K bytes 16 sq .. 16 sq + 15 of this row = columns 4 sq .. 4 sq + 3
     *reinterpret_cast<uint4 *>(eB + sq * kBChunk) = vb;
     if (paired) {                                                   // second tile's rows: row groups 16..31 of B
-      const uint32_t sz = spread_codes(cB1[i * 128], pick);
+      const uint32_t sz = pick_half(cB1[i * 256 + w0], pick);
       vb.x = __byte_perm(rowk[0], 0u, sz);
       vb.y = __byte_perm(rowk[1], 0u, sz);
       vb.z = __byte_perm(rowk[2], 0u, sz);
@@ -199,8 +210,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
   constexpr int kBChunk = 4096;                       // B: bytes between 16-byte K chunks (32 row groups x 128 B)
   constexpr int kMmas = 8;
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char *raw = smem;                                         // kRaw x kRawBytes
-  unsigned char *exps = smem + (size_t) kRaw * kRawBytes;            // kExp x kExpBytes (16-byte aligned: kRawBytes % 16 == 0)
+  unsigned char *raw = smem;                                         // kRaw x kRawBytes (count pass: kCntRaw x kCntRawBytes)
+  unsigned char *exps = smem + (size_t) kRingBytes;                  // kExp x kExpBytes (16-byte aligned: the ring is a multiple of 128)
   uint64_t *bars = reinterpret_cast<uint64_t *>(exps + (size_t) kExp * kExpBytes);
   uint64_t *raw_full = bars, *raw_empty = raw_full + kRaw, *exp_full = raw_empty + kRaw, *exp_empty = exp_full + kExp;
   uint64_t *acc_full = exp_empty + kExp, *acc_empty = acc_full + 2;
@@ -246,9 +257,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
         const ngsd_tile tl = a.tiles[t0];
         const uint32_t tj1 = paired ? a.tiles[t1].tj : tl.tj;
         const uint32_t c0 = a.split_begin[q], c1 = a.split_begin[q + 1];
-        const uint32_t *Ab = a.codes + (uint64_t) tl.ti * a.NW * 512;
-        const uint32_t *Bb = a.codes + (uint64_t) tl.tj * a.NW * 512;
-        const uint32_t *B1b = a.codes + (uint64_t) tj1 * a.NW * 512;
+        const uint32_t *Ab = a.codes + (uint64_t) tl.ti * a.NW * 1024;     // codes4: 1024 words per (row block, 64-site word)
+        const uint32_t *Bb = a.codes + (uint64_t) tl.tj * a.NW * 1024;
+        const uint32_t *B1b = a.codes + (uint64_t) tj1 * a.NW * 1024;
         if (COUNT) {
           for (uint32_t c = c0; c < c1; c += kCntGroup) {
             const uint32_t ne = min((uint32_t) kCntGroup, c1 - c);
@@ -282,9 +293,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
           raw_meta[rs * 2 + 1] = (c == c0 ? kFirst : 0u) | (c + 1 == c1 ? kLast : 0u) | (paired ? kPair : 0u) | (unitw ? kUnitW : 0u);
           mbar_expect_tx(&raw_full[rs], (paired ? 3 : 2) * kCodeBytes + 64);
           unsigned char *dst = raw + (size_t) rs * kRawStage;
-          bulk_g2s(dst, Ab + word * 512, kCodeBytes, &raw_full[rs]);
-          bulk_g2s(dst + kCodeBytes, Bb + word * 512, kCodeBytes, &raw_full[rs]);
-          if (paired) bulk_g2s(dst + 2 * kCodeBytes, B1b + word * 512, kCodeBytes, &raw_full[rs]);
+          bulk_g2s(dst, Ab + word * 1024, kCodeBytes, &raw_full[rs]);
+          bulk_g2s(dst + kCodeBytes, Bb + word * 1024, kCodeBytes, &raw_full[rs]);
+          if (paired) bulk_g2s(dst + 2 * kCodeBytes, B1b + word * 1024, kCodeBytes, &raw_full[rs]);
           bulk_g2s(dst + kOffW, wsrc, 64, &raw_full[rs]);
           if (++rs == kRawN) { rs = 0; rph ^= 1; }
         }
@@ -539,7 +550,7 @@ cudaError_t ngsd_launch_dist_umma(ngsd_ctx *ctx, uint32_t n_units, int grid, uin
     attr_set[ctx->device & 63] = true;
   }
   UmmaArgs a;
-  a.codes = ctx->codes;
+  a.codes = ctx->codes4;
   a.mask = ctx->mask;
   a.wsite = ctx->d_wsite;
   a.word_ids = ctx->d_word_ids;

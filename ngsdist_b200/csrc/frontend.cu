@@ -230,6 +230,13 @@ __device__ __forceinline__ bool called_code_fast(const FrontCfg &c, double x0, d
   return false;
 }
 
+// 4 codes of 2 bits -> the 4 selector nibbles of a byte permute (PRMT), i.e. the form k_dist_umma consumes them in:
+// storing the codes spread once (codes4, 4 bits per site) saves its expander warps the same shuffle for every tile.
+__device__ __forceinline__ unsigned spread8(unsigned b) {
+  const unsigned s = (b | (b << 4)) & 0x0F0Fu;
+  return (s | (s << 2)) & 0x3333u;
+}
+
 // Genotype-code input (read_data.cpp:88-95,98 followed by ngsDist.cpp:172-173): exact one-hot / uniform triples.
 __device__ __forceinline__ bool posterior_from_code(int g, double p[3]) {
   if (g > 2) { p[0] = p[1] = p[2] = 0; return false; }
@@ -371,8 +378,8 @@ __device__ __noinline__ unsigned called_code_exact(int kind, int in_log, double 
 // padding) and the presence mask.  HBM-bound: 24 B (or 1 B of genotype code) read per individual-site, 0.4 B written.
 __global__ void __launch_bounds__(512, 2) k_frontend_codes(FrontCfg c, const double *__restrict__ raw, const int8_t *__restrict__ codes,
                                                             uint64_t n_ind, uint64_t site0, uint64_t n, uint64_t NW,
-                                                            uint32_t *__restrict__ codes_out, uint64_t *__restrict__ mask,
-                                                            int *__restrict__ err) {
+                                                            uint32_t *__restrict__ codes_out, uint32_t *__restrict__ codes4_out,
+                                                            uint64_t *__restrict__ mask, int *__restrict__ err) {
   __shared__ unsigned cod[16][32];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const uint64_t i = (uint64_t) blockIdx.x * 32 + tx;
@@ -473,6 +480,9 @@ __global__ void __launch_bounds__(512, 2) k_frontend_codes(FrontCfg c, const dou
       mhi |= ((cod[k + 8][tx] >> 8) & 0xFu) << (4 * k);
     }
     mask[(rb * NW + word) * 128 + r] = ((uint64_t) mhi << 32) | mlo;
+  } else if (ty >= 8) {                   // codes4 word ty - 8: sites 8 k .. 8 k + 7 as selector nibbles
+    const int k = ty - 8;
+    codes4_out[((rb * NW + word) * 8 + k) * 128 + r] = spread8(cod[2 * k][tx] & 0xFFu) | (spread8(cod[2 * k + 1][tx] & 0xFFu) << 16);
   }
 }
 
@@ -480,8 +490,8 @@ __global__ void __launch_bounds__(512, 2) k_frontend_codes(FrontCfg c, const dou
 // block shape and output as k_frontend_codes without any of its floating-point state, so that it is a ~20-register
 // kernel that can share an SM with a persistent contraction CTA (a packed push overlapping another context's contraction).
 __global__ void __launch_bounds__(512, 4) k_codes_from_int8(const int8_t *__restrict__ codes, uint64_t n_ind, uint64_t site0, uint64_t n, uint64_t NW,
-                                                            uint32_t *__restrict__ codes_out, uint64_t *__restrict__ mask, int *__restrict__ err,
-                                                            uint64_t *__restrict__ blank) {
+                                                            uint32_t *__restrict__ codes_out, uint32_t *__restrict__ codes4_out,
+                                                            uint64_t *__restrict__ mask, int *__restrict__ err, uint64_t *__restrict__ blank) {
   __shared__ unsigned cod[16][32];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const uint64_t i = (uint64_t) blockIdx.x * 32 + tx;
@@ -522,6 +532,9 @@ __global__ void __launch_bounds__(512, 4) k_codes_from_int8(const int8_t *__rest
       mhi |= ((cod[k + 8][tx] >> 8) & 0xFu) << (4 * k);
     }
     mask[(rb * NW + word) * 128 + r] = ((uint64_t) mhi << 32) | mlo;
+  } else if (ty >= 8) {
+    const int k = ty - 8;
+    codes4_out[((rb * NW + word) * 8 + k) * 128 + r] = spread8(cod[2 * k][tx] & 0xFFu) | (spread8(cod[2 * k + 1][tx] & 0xFFu) << 16);
   }
 }
 
@@ -613,9 +626,9 @@ cudaError_t ngsd_launch_frontend(ngsd_ctx *ctx, const ngsd_frontend_args &a) {
     const int8_t *codes = a.codes ? a.codes + off * ctx->n_ind : nullptr;
     dim3 grid((unsigned) (ctx->n_pad / 32), (unsigned) ((n + 63) / 64)), block(32, 16);
     if (ctx->int_path && codes)
-      k_codes_from_int8<<<grid, block, 0, ctx->stream>>>(codes, ctx->n_ind, site0, n, ctx->NW, ctx->codes, ctx->mask, ctx->d_err, ctx->d_blank);
+      k_codes_from_int8<<<grid, block, 0, ctx->stream>>>(codes, ctx->n_ind, site0, n, ctx->NW, ctx->codes, ctx->codes4, ctx->mask, ctx->d_err, ctx->d_blank);
     else if (ctx->int_path)
-      k_frontend_codes<<<grid, block, 0, ctx->stream>>>(c, raw, codes, ctx->n_ind, site0, n, ctx->NW, ctx->codes, ctx->mask, ctx->d_err);
+      k_frontend_codes<<<grid, block, 0, ctx->stream>>>(c, raw, codes, ctx->n_ind, site0, n, ctx->NW, ctx->codes, ctx->codes4, ctx->mask, ctx->d_err);
     else if (c.call_geno)
       k_frontend<true><<<grid, block, 0, ctx->stream>>>(c, raw, codes, ctx->n_ind, site0, n, ctx->NC, ctx->NW, ctx->Apack, ctx->Bpack,
                                                         ctx->Cplane, ctx->ldc, ctx->mask, ctx->d_err);
@@ -635,7 +648,7 @@ namespace {
 // d.x = the normal-space posterior as gen_dist reads it; d.flags bit 0 = miss_data() is true, bits 8..9 = the code.
 __global__ void k_patch(FrontCfg c, const ngsd_deferred *__restrict__ list, unsigned n, uint64_t n_pad, uint64_t NC, uint64_t NW,
                         double *__restrict__ Apack, double *__restrict__ Bpack, double *__restrict__ Cplane, uint32_t *__restrict__ codes,
-                        uint64_t *__restrict__ mask) {
+                        uint32_t *__restrict__ codes4, uint64_t *__restrict__ mask) {
   const unsigned k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= n) return;
   const ngsd_deferred d = list[k];
@@ -648,6 +661,10 @@ __global__ void k_patch(FrontCfg c, const ngsd_deferred *__restrict__ list, unsi
     const unsigned sh = 2 * (unsigned) (s & 15);
     atomicAnd(cw, ~(3u << sh));
     atomicOr(cw, ((d.flags >> 8) & 3u) << sh);
+    unsigned *cw4 = &codes4[((rb * NW + (s >> 6)) * 8 + ((s >> 3) & 7)) * 128 + r];
+    const unsigned sh4 = 4 * (unsigned) (s & 7);
+    atomicAnd(cw4, ~(15u << sh4));
+    atomicOr(cw4, ((d.flags >> 8) & 3u) << sh4);
     return;
   }
   double p[3] = {d.x[0], d.x[1], d.x[2]};
@@ -690,7 +707,7 @@ cudaError_t ngsd_launch_patch(ngsd_ctx *ctx, const ngsd_deferred *list_dev, unsi
   c.int_path = ctx->int_path ? 1 : 0;
   for (int k = 0; k < 9; k++) c.score[k] = ctx->cfg.score[k];
   k_patch<<<(n + 127) / 128, 128, 0, ctx->stream>>>(c, list_dev, n, ctx->n_pad, ctx->NC, ctx->NW, ctx->Apack, ctx->Bpack, ctx->Cplane, ctx->codes,
-                                                    ctx->mask);
+                                                    ctx->codes4, ctx->mask);
   return cudaGetLastError();
 }
 

@@ -69,6 +69,7 @@ struct ngsd_ctx {
   // called-genotype integer path (dist_imma.cu): 2-bit codes instead of FP64 planes
   bool int_path = false;
   uint32_t *codes = nullptr;                   // [RB][NW][4][128] 16 sites per word, code 3 = missing
+  uint32_t *codes4 = nullptr;                  // [RB][NW][8][128] the same codes as PRMT selector nibbles, 8 sites per word (k_dist_umma)
   uint8_t *d_wsite = nullptr; uint64_t wsite_cap = 0;        // [layers][NW*64] per-site weights
   uint32_t *d_word_layer = nullptr; uint64_t word_cap = 0;   // weight layer of each word-list entry (ids live in d_chunk_ids)
   uint32_t *d_word_ids = nullptr;
