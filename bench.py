@@ -446,7 +446,9 @@ def single_gpu_extras(nb, torch, np, local, multi):
     try:
         pz = raw / raw.sum(dim=2, keepdim=True)
         q = torch.round(pz * 1e6).to(torch.int64)                         # 6-decimal posteriors (what ANGSD -doGeno 8 prints)
-        dec = (q.to(torch.float64) / 1e6)                                 # the doubles a text reader gets from them (IEEE division)
+        # the doubles a text reader gets from them: the IEEE quotient (a 0-dim CUDA divisor -- torch turns a division by a
+        # Python scalar into a multiplication by its reciprocal, which is not the same double)
+        dec = q.to(torch.float64) / torch.tensor(1e6, dtype=torch.float64, device="cuda")
         packed = (q[..., 0] | (q[..., 1] << 20) | (q[..., 2] << 40)).contiguous()
         h_dec = torch.empty(dec.shape, dtype=torch.float64).pin_memory(); h_dec.copy_(dec)
         h_pk = torch.empty(packed.shape, dtype=torch.int64).pin_memory(); h_pk.copy_(packed)
