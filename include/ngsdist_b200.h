@@ -223,6 +223,17 @@ NGSD_API int ngsd_comm_stats(const ngsd_ctx *ctx, uint64_t *bytes, float *ms);
  * it touches afterwards -- call before ngsd_host_alloc.  Returns the NUMA node, -1 when the platform exposes none. */
 NGSD_API int ngsd_bind_host_to_device(int device);
 
+/* Downstream of the matrices (the workflow of README.md:83-98 hands the .dist file to FastME for one tree
+ * per matrix): a neighbour-joining tree (Saitou & Nei 1987 / Studier & Keppler 1988; ties: smallest i, then j) computed on
+ * the device.  dist_host == NULL: from the matrix the last ngsd_distances / ngsd_finish left on the device (as transformed
+ * by cfg.evol_model); otherwise from the given n_ind x n_ind host matrix (e.g. after the host's own -log / JC69 tail).
+ * labels: n_ind C strings or NULL ("Ind_<i>", ngsDist.cpp:118-124).  Writes Newick with "%.10f" branch lengths and a
+ * trifurcating root into `newick` (NUL-terminated) and its length into *newick_len; NGSD_ERR_ARG with the needed size in
+ * *newick_len when newick_cap is too small, or when the matrix holds non-finite values.  The reference has no
+ * counterpart: parity is against a CPU restatement of the same rules (oracle/nj_oracle.py). */
+NGSD_API int ngsd_nj_tree(ngsd_ctx *ctx, const double *dist_host, const char *const *labels, char *newick, uint64_t newick_cap,
+                          uint64_t *newick_len);
+
 /* Host-side helper with the reference's RNG semantics (gsl_rng_taus; ngsDist.cpp:179-180, gen_func.cpp:117-119):
  * state[3] is seeded by ngsd_taus_seed and advanced by n_blocks draws per call of ngsd_boot_block_counts, which
  * fills counts[n_blocks] for one replicate exactly as rnd_map_data would have re-pointed the blocks. */

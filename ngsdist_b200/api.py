@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "ngsd_boot_block_counts", "ngsd_get_posteriors", "ngsd_synth_raw_device", "ngsd_get_timing", "ngsd_stream",
     "ngsd_probe_fp64_tflops", "ngsd_probe_int8_tmacs", "ngsd_probe_umma_tmacs", "ngsd_host_alloc", "ngsd_host_free", "ngsd_set_tile_shard", "ngsd_device_results", "ngsd_finish",
     "ngsd_distances_batch", "ngsd_comm_unique_id", "ngsd_comm_attach", "ngsd_comm_allgather_operands", "ngsd_comm_reduce_sites", "ngsd_comm_reduce_tiles",
-    "ngsd_comm_barrier", "ngsd_comm_stats", "ngsd_bind_host_to_device", "ngsd_deferred_stats", "ngsd_push_sites_packed",
+    "ngsd_comm_barrier", "ngsd_comm_stats", "ngsd_bind_host_to_device", "ngsd_deferred_stats", "ngsd_push_sites_packed", "ngsd_nj_tree",
 ]
 ABI_VERSION = 2
 COMM_ID_BYTES = 128
@@ -123,11 +123,12 @@ def lib():
     L.ngsd_bind_host_to_device.argtypes = [i32]
     L.ngsd_deferred_stats.argtypes = [vp, C.POINTER(u64)]
     L.ngsd_push_sites_packed.argtypes = [vp, vp, i32, dbl, u64, u64]
+    L.ngsd_nj_tree.argtypes = [vp, vp, vp, vp, u64, C.POINTER(u64)]
     for name in ("ngsd_create", "ngsd_destroy", "ngsd_push_sites", "ngsd_push_sites_device", "ngsd_push_genotypes", "ngsd_push_packed_genotypes", "ngsd_frontend",
                  "ngsd_distances", "ngsd_get_posteriors", "ngsd_synth_raw_device", "ngsd_get_timing", "ngsd_probe_fp64_tflops", "ngsd_probe_int8_tmacs", "ngsd_probe_umma_tmacs",
                  "ngsd_set_tile_shard", "ngsd_device_results", "ngsd_finish", "ngsd_distances_batch", "ngsd_comm_unique_id", "ngsd_comm_attach",
                  "ngsd_comm_allgather_operands", "ngsd_comm_reduce_sites", "ngsd_comm_reduce_tiles", "ngsd_comm_barrier", "ngsd_comm_stats",
-                 "ngsd_bind_host_to_device", "ngsd_deferred_stats", "ngsd_push_sites_packed"):
+                 "ngsd_bind_host_to_device", "ngsd_deferred_stats", "ngsd_push_sites_packed", "ngsd_nj_tree"):
         getattr(L, name).restype = i32
     _lib = L
     return L
@@ -516,6 +517,25 @@ class NgsDistB200:
 
     def stream(self):
         return lib().ngsd_stream(self._h)
+
+    def nj_tree(self, dist=None, labels=None):
+        """Neighbour-joining tree (Newick) of the last matrix on the device, or of `dist` (n x n host array)."""
+        d = None if dist is None else np.ascontiguousarray(dist, dtype=np.float64)
+        lab = None
+        if labels is not None:
+            lab = (C.c_char_p * len(labels))(*[str(x).encode() for x in labels])
+        need = C.c_uint64(0)
+        cap = 64 * self.p.n_ind + 1024
+        for _ in range(2):
+            buf = C.create_string_buffer(cap)
+            rc = lib().ngsd_nj_tree(self._h, _ptr(d), lab, buf, cap, C.byref(need))
+            if rc == 0:
+                return buf.value.decode()
+            if need.value + 1 > cap:
+                cap = need.value + 1
+                continue
+            self._check(rc)
+        self._check(rc)
 
     def deferred_stats(self):
         """Individual-sites the host's libm decided (knife edges of the reference's comparisons)."""

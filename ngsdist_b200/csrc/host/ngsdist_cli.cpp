@@ -10,7 +10,8 @@
 //
 // Differences on purpose (documented in DESIGN.md): text lines may be longer than the reference's 500 000-character
 // buffer; input is streamed in chunks (the whole data set is never held on the host); --verbose >= 5 per-site dumps are
-// not produced; additive flags: --device N (first GPU), --n_gpus N and --shard auto|replicated|sites (multi-GPU inside
+// not produced; additive flags: --device N (first GPU), --tree FILE (a neighbour-joining tree per matrix), --n_gpus N and
+// --shard auto|replicated|sites (multi-GPU inside
 // the library).  The tail of gen_dist (ngsDist.cpp:372-386: division, -log(1-d), JC69) runs HERE with the
 // host's libm on the raw distance the device returns, so that the written values are the reference's to the last digit.
 #include <fcntl.h>
@@ -53,6 +54,7 @@ struct Pars {
   const char *out = nullptr;
   unsigned n_threads = 1, verbose = 1, seed = 0;
   int device = 0, n_gpus = 1, shard = 0;
+  const char *tree = nullptr;   // --tree FILE: one neighbour-joining tree (Newick) per matrix
 };
 
 // error(): same shape as the reference's (shared/gen_func.cpp:12-18): banner on stderr, perror, exit(-1)
@@ -86,6 +88,7 @@ static void parse_args(Pars *p, int argc, char **argv) {
       {"n_threads", required_argument, nullptr, 'x'},  {"verbose", required_argument, nullptr, 'V'},
       {"seed", required_argument, nullptr, 'r'},       {"device", required_argument, nullptr, 1000},
       {"n_gpus", required_argument, nullptr, 1001},    {"shard", required_argument, nullptr, 1002},
+      {"tree", required_argument, nullptr, 1003},
       {nullptr, 0, nullptr, 0}};
   p->seed = (unsigned) time(nullptr);
   int c;
@@ -116,6 +119,7 @@ static void parse_args(Pars *p, int argc, char **argv) {
       case 'r': p->seed = (unsigned) atoi(optarg); break;
       case 1000: p->device = atoi(optarg); break;
       case 1001: p->n_gpus = atoi(optarg); break;
+      case 1003: p->tree = optarg; break;
       case 1002:
         if (strcmp(optarg, "auto") == 0) p->shard = NGSD_SHARD_AUTO;
         else if (strcmp(optarg, "replicated") == 0) p->shard = NGSD_SHARD_REPLICATED;
@@ -340,6 +344,27 @@ static int selftest_io(uint64_t n) {
     if (fastio::parse_number(t, t + strlen(t), &w)) { fprintf(stderr, "parsed a non-number: '%s'\n", t); bad++; }
   fprintf(stderr, "selftest_io: %lu values, %lu mismatches\n", n, bad);
   return bad ? 1 : 0;
+}
+
+// --tree: the step the reference's workflow (README.md:83-98) runs FastME for -- one neighbour-joining tree per matrix,
+// computed on the device from the matrix that was just written (after the host's -log / JC69 tail)
+static void write_tree(FILE *fh, ngsd_ctx *ctx, const double *d, const std::vector<std::string> &lab) {
+  std::vector<const char *> names;
+  for (auto &l : lab) names.push_back(l.c_str());
+  uint64_t need = 0;
+  std::vector<char> buf(64 * lab.size() + 1024);
+  int rc = ngsd_nj_tree(ctx, d, names.data(), buf.data(), buf.size(), &need);
+  if (rc && need + 1 > buf.size()) {
+    buf.resize(need + 1);
+    rc = ngsd_nj_tree(ctx, d, names.data(), buf.data(), buf.size(), &need);
+  }
+  if (rc) {
+    fprintf(stderr, "> no tree for this matrix: %s\n", ngsd_last_error(ctx));
+    fprintf(fh, "NA\n");
+    return;
+  }
+  fwrite(buf.data(), 1, need, fh);
+  fputc('\n', fh);
 }
 
 // NGSD_CLI_TIMING=1: wall-clock stamps of the phases on stderr (development aid)
@@ -722,6 +747,8 @@ int main(int argc, char **argv) {
 
   FILE *out_fh = fopen(p.out, "w");
   if (!out_fh) die("main", "cannot open output file!");
+  FILE *tree_fh = p.tree ? fopen(p.tree, "w") : nullptr;
+  if (p.tree && !tree_fh) die("main", "cannot open tree output file!");
   static char obuf[1 << 22];
   setvbuf(out_fh, obuf, _IOFBF, sizeof(obuf));
 
@@ -747,6 +774,7 @@ int main(int argc, char **argv) {
         if (host_model) apply_model(dist.data() + q * n2, p.n_ind, p.evol_model, p.n_threads);
         if (p.verbose >= 2) fprintf(stderr, "> Printing distance matrix\n");
         write_matrix(out_fh, labels, dist.data() + q * n2, p.n_ind, p.n_threads);
+        if (tree_fh) write_tree(tree_fh, ctx, dist.data() + q * n2, labels);
       }
       rep += k - 1;
       continue;
@@ -777,8 +805,10 @@ int main(int argc, char **argv) {
     if (host_model) apply_model(dist.data(), p.n_ind, p.evol_model, p.n_threads);
     if (p.verbose >= 2) fprintf(stderr, "> Printing distance matrix\n");
     write_matrix(out_fh, labels, dist.data(), p.n_ind, p.n_threads);
+    if (tree_fh) write_tree(tree_fh, ctx, dist.data(), labels);
   }
   fclose(out_fh);
+  if (tree_fh) fclose(tree_fh);
   stamp("all matrices written");
   if (p.verbose >= 1) fprintf(stderr, "==> Freeing memory...\n");
   ngsd_destroy(ctx);

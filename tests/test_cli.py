@@ -321,3 +321,21 @@ def test_cli_packs_six_decimal_text_posteriors(tmp_path):
         assert r.returncode == 0, r.stderr[-2000:]
         outs.append(open(out).read())
     assert outs[0] == outs[1] == golden_text(case["name"])
+
+
+@pytest.mark.gpu
+def test_cli_tree_flag_writes_one_newick_per_matrix(tmp_path):
+    from oracle import nj_oracle
+    case = [c for c in MAN["binary"] if c["name"] == "c1_indep_boot"][0]
+    out, tree = str(tmp_path / "o.dist"), str(tmp_path / "o.nwk")
+    r = run_cli(["--geno", os.path.join(GOLDEN, case["input"]), "--n_ind", str(case["n_ind"]), "--n_sites", str(case["n_sites"]), "--out", out,
+                 "--tree", tree, "--verbose", "0"] + case["flags"])
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert open(out).read() == golden_text(case["name"])
+    trees = open(tree).read().strip().split("\n")
+    mats = [m for _, m in oracle.parse_dist(out, case["n_ind"])]
+    assert len(trees) == len(mats) == 6
+    for t, m in zip(trees, mats):                       # the matrices as written (10 decimals) -> the same topology from the CPU restatement
+        want = nj_oracle.nj(m)[0]
+        assert nj_oracle.newick_lengths(t)[0] == nj_oracle.newick_lengths(want)[0]
+        assert np.allclose(nj_oracle.newick_lengths(t)[1], nj_oracle.newick_lengths(want)[1], atol=1e-8)
