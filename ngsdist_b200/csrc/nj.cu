@@ -9,7 +9,8 @@
 //     limb_i = d(i,j) / 2 + (r_i - r_j) / (2 (m - 2)),  limb_j = d(i,j) - limb_i
 //     d(u,k) = (d(i,k) + d(j,k) - d(i,j)) / 2                              the new node u takes slot i, slot j retires
 // until three nodes are left, which are joined in a trifurcation -- and is checked against a CPU restatement of the same
-// rules (oracle/nj_oracle.py; ties: smallest i, then smallest j).
+// rules (oracle/nj_oracle.py; ties: smallest i, then smallest j; the exact tie between complementary pairs when four nodes
+// are left is settled by looking only at the pairs of the smallest active index).
 //
 // Per join two launches and no host round trip: k_nj_rowmin (one block per row: the row's best partner) and k_nj_join
 // (one block: best row, limb lengths, the O(n) update of row / column u and of the row sums, the join record).  The host
@@ -50,10 +51,20 @@ __global__ void __launch_bounds__(256) k_nj_rowmin(const double *__restrict__ D,
   __shared__ double sq[256];
   __shared__ uint32_t sj[256];
   const uint64_t i = blockIdx.x;
-  const double mm2 = (double) (*m_ptr - 2);
+  const uint32_t m = *m_ptr;
+  const double mm2 = (double) (m - 2);
   double best = INFINITY;
   uint32_t bj = 0xFFFFFFFFu;
-  if (active[i]) {
+  // With four nodes left Q(i,j) equals Q of the complementary pair exactly (both choices give the same unrooted tree, but
+  // rounding would pick the Newick rooting at random): each of the three pairings is represented once, by the pair that
+  // holds the smallest active index -- only that row takes part.
+  bool skip_row = false;
+  if (m == 4) {
+    int f = 0;
+    for (uint64_t k = threadIdx.x; k < i; k += 256) f |= active[k];
+    skip_row = __syncthreads_or(f) != 0;
+  }
+  if (active[i] && !skip_row) {
     const double ri = r[i];
     for (uint64_t j = i + 1 + threadIdx.x; j < n; j += 256) {
       if (!active[j]) continue;

@@ -25,6 +25,8 @@ def nj(dist, labels=None):
         sub_d = D[np.ix_(idx, idx)]
         Q = (m - 2) * sub_d - r[idx][:, None] - r[idx][None, :]
         Q[np.tril_indices(len(idx))] = np.inf                    # pairs i < j only
+        if m == 4:                                               # Q of a pair equals Q of the complementary pair exactly: every
+            Q[1:, :] = np.inf                                    # pairing is represented once, by the pair of the smallest index
         a, b = np.unravel_index(np.argmin(Q), Q.shape)           # first minimum in row-major order = smallest i, then j
         i, j = int(idx[a]), int(idx[b])
         dij = D[i, j]
@@ -53,3 +55,34 @@ def newick_lengths(s):
     import re
     lens = [float(x) for x in re.findall(r":(-?[0-9.]+(?:e-?[0-9]+)?|-?nan|-?inf)", s)]
     return re.sub(r":-?[0-9.a-z]+(?:e-?[0-9]+)?", "", s), lens
+
+
+def splits(newick):
+    """The unrooted topology as a set of leaf bipartitions (each the frozenset of the side without the first leaf)."""
+    import re
+    tokens = re.findall(r"[(),;]|[^(),;:]+|:[^(),;]+", newick)
+    stack, out, leaves = [], set(), []
+    cur = None
+    for t in tokens:
+        if t == "(":
+            stack.append(set())
+        elif t == ")":
+            done = stack.pop()
+            out.add(frozenset(done))
+            if stack:
+                stack[-1] |= done
+            cur = done
+        elif t in (",", ";") or t.startswith(":"):
+            continue
+        else:
+            leaves.append(t)
+            if stack:
+                stack[-1].add(t)
+    allv = frozenset(leaves)
+    first = leaves[0]
+    norm = set()
+    for sp in out:
+        side = sp if first not in sp else allv - sp
+        if 1 < len(side) < len(allv) - 1:
+            norm.add(frozenset(side))
+    return norm

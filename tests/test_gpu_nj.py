@@ -51,14 +51,17 @@ def test_nj_recovers_an_additive_tree_and_runs_on_the_resident_matrix():
     with nb().NgsDistB200(p) as g:
         t = g.nj_tree(D)
         want, _, _ = nj_oracle.nj(D)
-        assert nj_oracle.newick_lengths(t)[0] == nj_oracle.newick_lengths(want)[0]
+        # on an additive matrix every cherry has the same Q exactly, so rounding picks the join order (and the Newick text);
+        # the unrooted tree -- its set of bipartitions -- is what neighbour joining guarantees
+        assert nj_oracle.splits(t) == nj_oracle.splits(want)
+        assert len(nj_oracle.splits(t)) > 0
         # ... and straight from the matrix ngsd_distances left on the device
         g.push_sites(oracle.synth_raw(8, 0.0, n, 640))
         d = g.run()[0]["dist"]
         t_dev = g.nj_tree()
         t_host = g.nj_tree(d)
         assert t_dev == t_host
-        assert nj_oracle.newick_lengths(t_dev)[0] == nj_oracle.newick_lengths(nj_oracle.nj(d)[0])[0]
+        assert nj_oracle.splits(t_dev) == nj_oracle.splits(nj_oracle.nj(d)[0])
 
 
 def test_nj_refuses_non_finite_matrices():
