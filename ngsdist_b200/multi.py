@@ -1,19 +1,22 @@
-"""Multi-GPU orchestration of the hot path: one process per GPU, `torch.distributed` for the plumbing.
+"""Shard plans of the multi-GPU hot path, and their CPU-testable mirror.
 
-The reference has exactly one parallel strategy (a task per pair through a pthread pool, ngsDist.cpp:197-269).  On a
-box of B200s the path shards three ways; none of the first two needs a data-path collective:
+The multi-GPU orchestration itself lives below the C ABI (csrc/comm.cu: `ngsd_cfg.n_gpus`, `ngsd_comm_attach`,
+`ngsd_distances_batch`, `ngsd_comm_reduce_sites`, `ngsd_comm_reduce_tiles`, `ngsd_comm_allgather_operands`, NCCL linked
+into the library).  The reference has exactly one parallel strategy (a task per pair through a pthread pool,
+ngsDist.cpp:197-269); on a box of B200s the path shards three ways:
 
-  replicates : every rank holds the whole data set and computes the matrices r = rank, rank + world, ... of the
-               1 + n_boot_rep the run produces; all ranks advance the SAME host RNG stream (gsl_rng_taus) so the
-               block draws are identical to a single-process run.  Results are gathered to rank 0 for writing.
-  tiles      : every rank holds the whole data set and computes the 128 x 128 upper-triangle tiles dealt to it
-               (ngsd_set_tile_shard); entries it does not own are 0, so one SUM assembles the matrix exactly.
-  sites      : rank g owns a contiguous block-aligned site range; raw sums num (FP64) and cnt (int64) are
-               all-reduced (NCCL over NVLink on the library's own device buffers) and the non-linear tail of
-               gen_dist (ngsDist.cpp:372-401) runs after the reduction (ngsd_finish).
+  replicates : replicate r on rank r % world; every rank advances the SAME host RNG stream (gsl_rng_taus), so the block
+               draws are those of a single-process run.
+  tiles      : the 128 x 128 upper-triangle tiles dealt to the ranks (ngsd_set_tile_shard); entries a rank does not own
+               are 0, so one SUM assembles the matrix exactly.
+  sites      : rank g owns a contiguous block-aligned site range; raw sums num (FP64) and cnt (int64) are reduced and the
+               non-linear tail of gen_dist (ngsDist.cpp:372-401) runs after the reduction.
 
-The collective wiring is written against callbacks so that it is exercised by world_size-2 `gloo` tests on CPU
-(tests/test_multi_cpu.py) with a stand-in compute function; on GPUs the callbacks are NgsDistB200 methods.
+This module holds what a HOST needs around those calls -- the plans (`site_shards`, `slice_block_counts`,
+`replicate_shard`, `tile_owner_mask`, `BootStream`) used by bench.py and tools/ -- and a torch.distributed restatement of
+the three collectives' wiring (`run_replicates`, `run_tiles`, `reduce_site_partials`) against compute callbacks, so that
+the plans and the assembly rules are exercised by world_size-2 `gloo` tests on CPU (tests/test_multi_cpu.py) where
+neither CUDA nor NCCL exists.  On GPUs the product path is the C ABI (tools/multi_gpu_check.py, tools/group_check.py).
 """
 import numpy as np
 
@@ -176,17 +179,3 @@ def reduce_site_partials(num, cnt, group=None):
     dist.all_reduce(num, op=dist.ReduceOp.SUM, group=group)
     dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
     return num, cnt
-
-
-def run_sites_gpu(ctx, counts_local, block_size, group=None):
-    """Site-sharded matrix on GPUs: `ctx` holds this rank's sites.  Returns the finished n x n matrix (all ranks)."""
-    import torch
-    ctx.partial_sums(counts_local, block_size)
-    _, num_ptr, cnt_ptr = ctx.device_results()
-    n = ctx.p.n_ind
-    num = device_tensor(num_ptr, (n, n), "<f8")
-    cnt = device_tensor(cnt_ptr, (n, n), "<i8")
-    torch.cuda.synchronize()
-    reduce_site_partials(num, cnt, group)
-    torch.cuda.synchronize()
-    return ctx.finish()
