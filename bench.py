@@ -238,7 +238,7 @@ def main():
     GEN = 65536
     for s0 in range(0, n_sites, GEN):
         g.synth_raw_device(raw_dev[s0:].data_ptr(), SEED, MISS, s0, min(GEN, n_sites - s0))
-    out_pin = torch.empty((R, n_ind, n_ind), dtype=torch.float64).pin_memory() if rank == 0 else None
+    out_pin = torch.empty((R, n_ind, n_ind), dtype=torch.float64, pin_memory=True) if rank == 0 else None
     out_ptr = out_pin.data_ptr() if rank == 0 else None
     boot = multi.BootStream(n_sites, BLOCK, BOOT_SEED)       # host RNG: identical on every rank
 
@@ -296,7 +296,7 @@ def main():
         align = 64
         sb = [n_sites // align * r // world * align for r in range(world)] + [n_sites]
         my0, my1 = sb[rank], sb[rank + 1]
-        raw_pin = torch.empty((my1 - my0, n_ind, 3), dtype=torch.float64).pin_memory()
+        raw_pin = torch.empty((my1 - my0, n_ind, 3), dtype=torch.float64, pin_memory=True)
         raw_pin.copy_(raw_dev[my0:my1])
         del raw_dev
         torch.cuda.empty_cache()
@@ -428,7 +428,7 @@ def single_gpu_extras(nb, torch, np, local, multi):
         gq = nb.NgsDistB200(nb.Params(n_ind=n, n_sites=s, in_probs=True, indep_geno=indep, evol_model=2), device=local)
         if name == "indep_geno":
             gq.synth_raw_device(raw.data_ptr(), SEED, 0.0, 0, s)
-        o = torch.empty((n, n), dtype=torch.float64).pin_memory()
+        o = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
         ms, kms, fe = [], [], []
         for it in range(5):
             gq.push_sites_device(raw.data_ptr(), 0, s)
@@ -450,14 +450,14 @@ def single_gpu_extras(nb, torch, np, local, multi):
         # Python scalar into a multiplication by its reciprocal, which is not the same double)
         dec = q.to(torch.float64) / torch.tensor(1e6, dtype=torch.float64, device="cuda")
         packed = (q[..., 0] | (q[..., 1] << 20) | (q[..., 2] << 40)).contiguous()
-        h_dec = torch.empty(dec.shape, dtype=torch.float64).pin_memory(); h_dec.copy_(dec)
-        h_pk = torch.empty(packed.shape, dtype=torch.int64).pin_memory(); h_pk.copy_(packed)
+        h_dec = torch.empty(dec.shape, dtype=torch.float64, pin_memory=True); h_dec.copy_(dec)
+        h_pk = torch.empty(packed.shape, dtype=torch.int64, pin_memory=True); h_pk.copy_(packed)
         del pz, q, dec, packed
         tiers = {}
         mats = {}
         for name in ("f64", "u20x3"):
             gt = nb.NgsDistB200(nb.Params(n_ind=n, n_sites=s, in_probs=True, indep_geno=True, evol_model=2, in_text=True), device=local)
-            o = torch.empty((n, n), dtype=torch.float64).pin_memory()
+            o = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
             best = None
             for it in range(5):
                 torch.cuda.synchronize()
@@ -496,7 +496,7 @@ def single_gpu_extras(nb, torch, np, local, multi):
             fe_ms += gc.timing().frontend_ms
         del buf
         gc.frontend()
-        oc = torch.empty((cn, cn), dtype=torch.float64).pin_memory()
+        oc = torch.empty((cn, cn), dtype=torch.float64, pin_memory=True)
         gc.distances_raw(None, 0, 1, oc.data_ptr())
         c_ms = []
         for _ in range(3):
@@ -526,7 +526,7 @@ def single_gpu_extras(nb, torch, np, local, multi):
         gb.push_sites_device(buf.data_ptr(), s0, m)
     del buf
     gb.frontend()
-    ob = torch.empty((bn, bn), dtype=torch.float64).pin_memory()
+    ob = torch.empty((bn, bn), dtype=torch.float64, pin_memory=True)
     ms = []
     for rep in range(4):
         counts, bs_ = gb.next_boot_counts()
@@ -577,7 +577,7 @@ def multi_gpu_extras(nb, torch, np, dist, multi, rank, world, local, share_id, b
     ag_ms = span(st, lambda: gc.comm_allgather_operands(sb))            # steady state (same bytes again)
     ag_bytes = gc.comm_stats()[0]
     gc.set_tile_shard(rank, world)
-    oc = torch.empty((cn, cn), dtype=torch.float64).pin_memory() if rank == 0 else None
+    oc = torch.empty((cn, cn), dtype=torch.float64, pin_memory=True) if rank == 0 else None
     optr = oc.data_ptr() if rank == 0 else None
 
     def c4_matrix():
@@ -615,7 +615,7 @@ def multi_gpu_extras(nb, torch, np, dist, multi, rank, world, local, share_id, b
         g5.push_sites_device(buf.data_ptr(), s0 - l0, m)
         fe_ms += g5.timing().frontend_ms
     del buf
-    o5 = torch.empty((n5, n5), dtype=torch.float64).pin_memory() if rank == 0 else None
+    o5 = torch.empty((n5, n5), dtype=torch.float64, pin_memory=True) if rank == 0 else None
     o5p = o5.data_ptr() if rank == 0 else None
     parts = {"dist": 0.0}
 

@@ -42,8 +42,8 @@ g.frontend()
 setup_s = time.time() - t0
 boot = multi.BootStream(S, B, 12345)
 counts = np.stack([boot.next_counts() for _ in range(R)])
-out = torch.empty((R, n, n), dtype=torch.float64).pin_memory() if rank == 0 else None
-first = torch.empty((n, n), dtype=torch.float64).pin_memory()
+out = torch.empty((R, n, n), dtype=torch.float64, pin_memory=True) if rank == 0 else None
+first = torch.empty((n, n), dtype=torch.float64, pin_memory=True)
 # untimed warm-up: one replicate per rank through the same call (first-use allocations of the library and of NCCL)
 g._check(nb.lib().ngsd_distances_batch(g._h, counts.ctypes.data, world, counts.shape[1], B, out.data_ptr() if rank == 0 else None))
 if world > 1:

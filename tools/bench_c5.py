@@ -80,7 +80,7 @@ t_local = time.time() - t0 - t_attach
 _, num_ptr, _ = g.device_results()
 multi.device_tensor(num_ptr, (n, n), "<f8").copy_(acc)
 torch.cuda.synchronize()
-out = torch.empty((n, n), dtype=torch.float64).pin_memory() if rank == 0 else None
+out = torch.empty((n, n), dtype=torch.float64, pin_memory=True) if rank == 0 else None
 t1 = time.time()
 g._check(nb.lib().ngsd_comm_reduce_sites(g._h, 0, S, out.data_ptr() if rank == 0 else None)) if world > 1 else g.finish(out.numpy())
 t_red = time.time() - t1

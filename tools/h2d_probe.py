@@ -15,7 +15,7 @@ if "--bind" in sys.argv:
 if world > 1:
     dist.init_process_group("gloo")
 n = 1 << 30
-h = torch.empty(n, dtype=torch.uint8).pin_memory()
+h = torch.empty(n, dtype=torch.uint8, pin_memory=True)
 h.fill_(1)
 d = torch.empty(n, dtype=torch.uint8, device="cuda")
 d.copy_(h, non_blocking=True)
