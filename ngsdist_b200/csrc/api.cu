@@ -796,7 +796,8 @@ static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n
     }
   }
   if (use_cache) maxw = 1;                                     // the contraction (if any) runs unweighted, K splits = blocks
-  const uint32_t layers = (maxw + 126) / 127;                  // site weights are int8 operand bytes: <= 127 per layer
+  const uint32_t wcap = ngsd_int_weight_cap(ctx);              // site weights are int8 operand bytes: <= 127 (42) per layer
+  const uint32_t layers = (maxw + wcap - 1) / wcap;
   const uint64_t ent_max = 0;   // the counts are a second int8 GEMM inside K2c: no K3 entry list
   const uint64_t bytes_w = (uint64_t) layers * nsp, bytes_ids = (uint64_t) layers * NW * sizeof(uint32_t);
   int rc = ensure_pinned(ctx, bytes_w + 2 * bytes_ids + ent_max * (sizeof(uint32_t) + sizeof(uint64_t)) + 256);
@@ -822,7 +823,7 @@ static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n
       uint32_t left = block_counts[b];
       if (left) active_sites += block_size;
       for (uint32_t l = 0; l < layers && left; l++) {
-        const uint32_t w = std::min<uint32_t>(left, 127);
+        const uint32_t w = std::min<uint32_t>(left, wcap);
         memset(h_w + (uint64_t) l * nsp + b * block_size, (int) w, block_size);
         left -= w;
       }
@@ -886,7 +887,7 @@ static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n
     splits = plan_splits((uint32_t) n_words, ctx->n_tiles, (double) ctx->n_tiles, grid);
   }
   if (!use_cache) {
-    const uint64_t per_word = (uint64_t) std::max(ctx->int_max_byte, 1) * std::min<uint32_t>(maxw, 127) * 64;
+    const uint64_t per_word = (uint64_t) std::max(ctx->int_max_byte, 1) * std::min<uint32_t>(maxw, wcap) * 64;
     const uint32_t cap = (uint32_t) std::max<uint64_t>(1, 2147483647ull / per_word);
     std::vector<uint32_t> cut;
     cut.push_back(0);
@@ -965,7 +966,7 @@ static int distances_int(ngsd_ctx *ctx, const uint32_t *block_counts, uint64_t n
   cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[5]); ctx->timing.total_ms = ms;
   ctx->timing.launches = launches;
   ctx->timing.dist_ctas = grid;
-  ctx->timing.dist_imma = run_kernel ? (uint64_t) n_words * (do_count ? 10 : 8) * ctx->n_tiles * 128ull : 0;   // 8 (+2 count) k-steps per word, 8 warps x 16 IMMA per k-step
+  ctx->timing.dist_imma = run_kernel ? (uint64_t) n_words * ((ngsd_use_umma() ? 6 : 8) + (do_count ? 2 : 0)) * ctx->n_tiles * 128ull : 0;   // 8 (6 in three-plane form; +2 count) k-steps of 32 K bytes per word, 8 warps x 16 IMMA-equivalents per k-step
   ctx->timing.active_sites = active_sites;
   ctx->timing.block_cache = use_cache ? (build_cache ? 1 : 2) : 0;
   if (use_cache) {

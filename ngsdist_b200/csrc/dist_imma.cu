@@ -388,6 +388,7 @@ bool ngsd_int_lut(const double *score, bool pairwise_del, uint32_t lut[4], doubl
     for (int k = 0; k < 4; k++) {
       const double v = f[k][c] * S, r = nearbyint(v);
       if (fabs(v - r) > 1e-9 || r < 0 || r > 127) return false;
+      if (!pairwise_del && k < 3 && ((int) r) % 3) return false;   // dist_umma.cu's three-plane form carries S / 3 on the B side
       wv |= (uint32_t) (int) r << (8 * k);
       if ((int) r > mx) mx = (int) r;
     }

@@ -1,26 +1,28 @@
 // K2c' dist_umma: the called-genotype contraction of dist_imma.cu on the 5th-generation tensor cores:
 // tcgen05.mma kind::i8 (SASS UTCIMMA), A operand and int32 accumulators in tensor memory, B operand in shared memory.
 //
-// Same arithmetic as dist_imma.cu (A_i[s][k] = w_s [c_i(s) == k], B_j[s][k] = S f(k, c_j(s)), K = 4 bytes per site,
-// exact int32 accumulation), the same K splits, partial buffers and epilogue.  UMMA runs the int8 GEMM 3.7x faster than
-// mma.sync (tools/probe_utcimma.cu: 2.1e15 vs 5.7e14 MAC/s) but cannot take operands from registers, so the 16x
-// expansion of the 2-bit codes is written out every stage.  A CTA is a four-role pipeline connected by mbarrier rings:
+// The arithmetic.  With codes c in {0, 1, 2, 3 = missing}, f(c_i, c_j) = the site term of ngsDist.cpp:351-353 for two called
+// genotypes, and S = 2 (--pairwise_del) or 18: acc(i,j) = S sum_s w_s f(c_i(s), c_j(s)) as an int8 GEMM with exact int32
+// accumulation and THREE K bytes per site (round 2; dist_imma.cu keeps the four-byte form):
+//     A_i[s][k] = w_s (m [c_i = k] + [c_i = 3] t),     B_j[s][k] = (S / m) f(k, c_j),     k = 0, 1, 2
+// with (m, t) = (1, 0) with --pairwise_del (row and column 3 of f are zero) and (3, 1) without (a missing genotype is the
+// uniform triple, gen_func.cpp:895-899, so its row of f is the mean of the other three) -- the same S f(c_i, c_j) exactly,
+// a quarter fewer operand bytes, MMAs and expansion instructions than one K byte per code value.  UMMA runs the int8 GEMM
+// 4x faster than mma.sync (probe: 2.3e15 vs 5.7e14 MAC/s) but cannot take operands from registers, so the expansion of the
+// 2-bit codes is written out every stage.  A CTA is a four-role pipeline connected by mbarrier rings:
 //
-//   warp 0      producer   cp.async.bulk of the packed codes (3 x 2 KiB + 64 weight bytes per 64-site stage)
-//   warps 2-17  expanders  codes -> int8 operands.  B (64 KiB per stage) goes to shared memory in the K-major, no-swizzle
-//                          UMMA layout (8-row x 16-byte core matrices; one STS.128 = 4 sites of one row, fence.proxy.async);
-//                          A (128 rows x 256 bytes per stage) goes to TENSOR MEMORY with tcgen05.st (row = lane, 4 K bytes
+//   warp 0      producer   cp.async.bulk of the packed codes (3 x 4 KiB of selector nibbles + 64 weight bytes per 64-site stage)
+//   warps 2-17  expanders  codes -> int8 operands.  B (48 KiB per stage) goes to shared memory in the K-major, no-swizzle
+//                          UMMA layout (8-row x 16-byte core matrices; one STS.128 = 16 K bytes of one row, fence.proxy.async);
+//                          A (128 rows x 192 bytes per stage) goes to TENSOR MEMORY with tcgen05.st (row = lane, 4 K bytes
 //                          per 32-bit column) -- the MMA reads it from there, which takes a third of the operand traffic
-//                          off the shared-memory pipe
-//   warp 1      MMA        one lane issues 8 x tcgen05.mma (128 x 256 x 32, A from TMEM) per stage, tcgen05.commit frees the stage
+//                          off the shared-memory pipe.  The warps work in kGroups groups on alternate stages (below)
+//   warp 1      MMA        one lane issues 6 x tcgen05.mma (128 x 256 x 32, A from TMEM) per stage, tcgen05.commit frees the stage
 //   warps 18-21 epilogue   tcgen05.ld of a finished unit's 128 x 256 accumulator, int32 partial tiles written row-major
-//                          (TMEM: 256 accumulator columns + 3 x 64 A columns; the expanders run up to 3 stages ahead
-//                          while the accumulator drains)
+//                          (TMEM: 256 accumulator columns + kExp x 64 A columns)
 //
 // A unit is a PAIR of output tiles of one row block (api.cu: d_pairs): they share the A operand, so one stage expands
 // 3 x 128 rows for 128 x 256 pairs instead of 2 x 128 rows for 128 x 128 (the odd tile of a row runs alone, N = 128).
-// The expanders' instruction stream is the limit (ncu: 85 % of their samples in arithmetic; tensor pipe 66 %, LSU
-// wavefronts 67 %, integer ALU 62 %); the expansion is ~9 integer ops and one 16-byte store per 16 operand bytes.
 #include <math.h>
 #include <stdlib.h>
 
@@ -30,32 +32,50 @@
 
 namespace {
 
-// Stage counts (A/B on 5 000 x 100 000, round 2): 2 raw + 3 expanded stages 3.60 ms, 4 raw + 2 expanded 3.74 ms; the nibble
-// codes doubled the raw stage, so 4 + 3 no longer fits the 227 KiB of shared memory.
 #ifndef NGSD_UMMA_KRAW
-#define NGSD_UMMA_KRAW 2
+#define NGSD_UMMA_KRAW 4
 #endif
 #ifndef NGSD_UMMA_KEXP
 #define NGSD_UMMA_KEXP 3
 #endif
+// The expander warps work in kGroups groups on ALTERNATE stages.  A stage costs a warp a fixed chain of latencies (barrier
+// wake-up, LDS, tcgen05.wait::st, fence.proxy.async, arrive) that does not shrink with the work: with every warp in every
+// stage the stage rate was one warp's latency, whatever the instruction count.  Measured at 5 000 x 100 000 (groups, raw
+// stages, expanded stages): (1, 4, 3) 3.08 ms, (2, 4, 3) 2.77 ms, (2, 2, 4) 2.75 ms, (2, 6, 3) 2.76 ms; with --pairwise_del
+// 4.74 / 4.45 / 4.55 / 4.44 ms.  What bounds a stage now is the shared-memory pipe: 48 KiB of B written + 48 KiB read back
+// by the tensor core + 12 KiB of codes written by the bulk copies + 12 KiB read = 120 KiB at 128 B/clk = 940 cycles
+// (measured 1 250; the 6 MMAs need 770).  A group is kExpWarps / kGroups warps (a multiple of 4: a warp reaches only the TMEM lanes of quadrant warp % 4)
+// and a thread expands kGroups site quads of each code word of its row.
+#ifndef NGSD_UMMA_GROUPS
+#define NGSD_UMMA_GROUPS 2
+#endif
 constexpr int kRaw = NGSD_UMMA_KRAW;              // raw (packed codes) stages
 constexpr int kExp = NGSD_UMMA_KEXP;              // expanded operand stages
+constexpr int kGroups = NGSD_UMMA_GROUPS;
 constexpr int kExpWarps = 16, kEpiWarps = 4;
+constexpr int kGroupWarps = kExpWarps / kGroups;
+static_assert(kGroups == 1 || kGroups == 2 || kGroups == 4, "expander groups");
+// mbarrier waits tell phases apart by parity only.  A raw slot must always belong to the same group (else a group could wait
+// for phase k of a slot whose phase k - 1, another group's, has not landed yet -- bulk copies complete out of order), and a
+// group runs at most kGroups + kExp stages ahead of the MMA, which must stay below two phases of an expanded slot
+// (kGroups = 4 with kExp = 3 hung on the GPU for exactly that reason).
+static_assert(kRaw % kGroups == 0 && kGroups <= kExp, "expander groups vs ring depths");
 constexpr int kThreads = (2 + kExpWarps + kEpiWarps) * 32;
 constexpr int kCodeBytes = 8 * 128 * 4;           // [8 words][128 rows] uint32 of selector nibbles (codes4), one operand of one 64-site stage
-constexpr int kMaskBytes = 128 * 8;               // presence bits of one operand of one stage (count pass)
-constexpr int kRawBytes = 3 * kCodeBytes + 128;   // A codes, B codes of the two tiles, 64 site weights; a multiple of 128 so that a warp's 32 code words stay in one bank row
-constexpr int kOpBytes = 16 * 16 * 128;           // expanded A operand: [16 site quads][16 row groups][8 rows][16 B] = 32 KiB
-constexpr int kExpBytes = 2 * kOpBytes;           // B = [16 site quads][32 row groups][8 rows][16 B] (count pass: one byte per site, a quarter of it)
-constexpr uint32_t kAccCols = 256, kACols = 64;   // TMEM columns: accumulator, one stage of A
-constexpr int kCntGroup = 4;                      // count pass: word-list entries (64 sites, one byte each) per stage
+constexpr int kMaskBytes = 128 * 8;               // presence bits of one operand of one 64-site word (count pass)
+constexpr int kRawBytes = 3 * kCodeBytes + 128;   // A codes, B codes of the two tiles, 64 site weights; a multiple of 128
+constexpr int kBChunk = 4096;                     // B: bytes between 16-byte K chunks (32 row groups x 8 rows x 16 B)
+constexpr int kChunks = 12;                       // 16-byte K chunks per stage: 64 sites x 3 planes (count pass: 192 sites x 1 byte)
+constexpr int kMmas = kChunks / 2;                // K = 32 bytes per tcgen05.mma
+constexpr int kExpBytes = kChunks * kBChunk;      // expanded B of one stage: 48 KiB
+constexpr uint32_t kAccCols = 256, kACols = 64;   // TMEM columns: accumulator, one stage of A (48 in use)
+constexpr int kCntGroup = 3;                      // count pass: word-list entries (64 sites, one byte each) per stage
 constexpr int kCntEntry = 3 * kMaskBytes;         // count pass raw stage: kCntGroup x {A, B, B' masks} then kCntGroup x 64 weights
-constexpr int kCntRawBytes = kCntGroup * (kCntEntry + 64);
-constexpr int kCntRaw = 2;                        // ... and two of those stages fill the same ring bytes
-static_assert(kCntRawBytes % 128 == 0 && kCntRaw <= kRaw, "count-pass raw stages reuse the code ring's barriers");
-constexpr int kRingBytes = kRaw * kRawBytes > kCntRaw * kCntRawBytes ? kRaw * kRawBytes : kCntRaw * kCntRawBytes;
+constexpr int kCntRawBytes = (kCntGroup * (kCntEntry + 64) + 127) / 128 * 128;
+static_assert(kCntRawBytes <= kRawBytes, "count-pass raw stages live in the code ring");
+constexpr int kRingBytes = kRaw * kRawBytes;
 constexpr int kNBar = 2 * kRaw + 2 * kExp + 4;
-constexpr size_t kSmemBytes = (size_t) kRingBytes + (size_t) kExp * kExpBytes + kNBar * 8 + (kRaw + kExp + 2) * 8 + 16 + 16 + 64 + 1024;
+constexpr size_t kSmemBytes = (size_t) kRingBytes + (size_t) kExp * kExpBytes + kNBar * 8 + (kRaw + kExp + 2) * 8 + 16 + 64 + 1024;
 static_assert(kSmemBytes <= 232448, "k_dist_umma shared memory");
 static_assert(kAccCols + kExp * kACols <= 512, "k_dist_umma tensor memory");
 
@@ -130,6 +150,8 @@ __device__ __forceinline__ void tmem_st4(uint32_t taddr, uint4 v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
+__device__ __forceinline__ uint32_t pick_half(uint32_t word, uint32_t pick) { return __byte_perm(word, 0u, pick); }
+
 struct UmmaArgs {
   const uint32_t *codes;        // codes4 [RB][NW][8][128]: selector nibbles, 8 sites per word
   const uint64_t *mask;         // [RB][NW][128] presence bits (count pass)
@@ -143,74 +165,96 @@ struct UmmaArgs {
   uint64_t NW;
   uint32_t n_tiles, n_pairs, n_units, pstride;   // n_units = splits x n_pairs
   uint32_t cnt_off;             // count pass: offset of the count tile inside a unit's slot (ints)
-  uint32_t lut[4];
+  uint32_t rowk[3];             // B table: byte c of rowk[k] = (S / m) f(k, c)
+  uint32_t tA[3];               // A table for unit weights: byte c of tA[k] = m [c = k] + t [c = 3]
+  uint32_t t3, amul;            // weighted A: selector table of the missing code (0xFF000000 or 0), m
 };
 
 enum : uint32_t { kFirst = 1u, kLast = 2u, kPair = 4u, kExit = 8u, kUnitW = 16u, kEntriesShift = 8u };   // count pass: entries of the stage in bits 8..10
 
-// Expansion of one 64-site stage by thread (row r, byte q0 of each of the 4 code words): A row -> tensor memory, B rows ->
-// shared memory.  The K order inside a 16-byte unit is free as long as both operands use it: PLANE-major here (word k =
-// plane k of the unit's 4 sites), because then one byte-permute builds a whole word.  With sel = the 4 codes spread to the
-// 4 selector nibbles, PRMT(T_k, sel) picks byte c_j of T_k for site j:  T_k = 0xFF << 8k gives the one-hot plane k of A
-// (AND the 4 weight bytes; UNITW: all 64 site weights are 1, T_k = 0x01 << 8k and no AND), T_k = row k of the S * f
-// table gives plane k of B.  No table loads.
-// (round 2: the codes arrive as selector nibbles -- codes4, spread once by the front end -- so the selector of a site quad
-// is one 16-bit half of a word; the shift-and-mask spreading that used to run here for every tile was a third of the
-// expanders' integer work)
-__device__ __forceinline__ uint32_t pick_half(uint32_t word, uint32_t pick) { return __byte_perm(word, 0u, pick); }
+// Expansion of one 64-site stage of the sum pass by thread (row r, site quads qb .. qb + kGroups - 1 of each of the 4 code
+// words): A row -> tensor memory, B rows -> shared memory.  The K order inside a stage is free as long as both operands use
+// it: the 4 codes of a site quad arrive as the 4 selector nibbles of one 16-bit half word (codes4, spread once by the front
+// end), and PRMT(T_k, sel) picks byte c_j of the table T_k for site j -- one instruction builds plane k of 4 sites, no table
+// loads.  Word n = 3 i + k of site quad q0 (sites 16 i + 4 q0 .. + 3, plane k) is K word 12 q0 + n of the row in BOTH
+// operands.  The code words are read into registers first and the raw stage is handed back to the producer BEFORE the wait
+// for a free expanded stage, so the next codes travel while this stage is built.
 template <bool UNITW>
-__device__ __forceinline__ void expand_codes(const uint32_t *cA, const uint32_t *cB, const uint32_t *cB1, const uint32_t *W32,
-                                             unsigned char *eB, uint32_t ta, int q0, bool paired, const uint32_t (&rowk)[4]) {
-  constexpr int kBChunk = 4096;
-  const uint32_t pick = (q0 & 1) ? 0x4432u : 0x4410u;               // site quad 4 i + q0 = half (q0 & 1) of nibble word 2 i + (q0 >> 1)
-  const int w0 = (q0 >> 1) * 128;
+__device__ __forceinline__ void expand_stage(const unsigned char *rawS, int r, int qb, int lane, bool paired, unsigned char *eB, uint32_t ta,
+                                             const UmmaArgs &a, uint64_t *raw_empty_bar, uint64_t *exp_empty_bar, uint32_t exp_parity) {
+  constexpr int kWG = kGroups >= 2 ? kGroups / 2 : 1;               // nibble words per 16 sites this thread reads (two site quads each)
+  const uint32_t *cw = reinterpret_cast<const uint32_t *>(rawS) + r;
+  uint32_t wa[kWG][4], wb[kWG][4], wc[kWG][4], wt[kGroups][4];
 #pragma unroll
-  for (int i = 0; i < 4; i++) {                                     // sites 16 i + 4 q0 .. + 3 = site quad 4 i + q0
-    const uint32_t sx = pick_half(cA[i * 256 + w0], pick), sy = pick_half(cB[i * 256 + w0], pick);
-    uint4 va, vb;
-    if (UNITW) {
-      va.x = __byte_perm(0x00000001u, 0u, sx);
-      va.y = __byte_perm(0x00000100u, 0u, sx);
-      va.z = __byte_perm(0x00010000u, 0u, sx);
-      va.w = __byte_perm(0x01000000u, 0u, sx);
-    } else {
-      const uint32_t ww = W32[i * 4];
-      va.x = __byte_perm(0x000000FFu, 0u, sx) & ww;
-      va.y = __byte_perm(0x0000FF00u, 0u, sx) & ww;
-      va.z = __byte_perm(0x00FF0000u, 0u, sx) & ww;
-      va.w = __byte_perm(0xFF000000u, 0u, sx) & ww;
+  for (int g = 0; g < kWG; g++) {
+    const int w0 = ((qb >> 1) + g) * 128;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      wa[g][i] = cw[i * 256 + w0];
+      wb[g][i] = cw[kCodeBytes / 4 + i * 256 + w0];
+      wc[g][i] = paired ? cw[2 * (kCodeBytes / 4) + i * 256 + w0] : 0u;
     }
-    vb.x = __byte_perm(rowk[0], 0u, sy);
-    vb.y = __byte_perm(rowk[1], 0u, sy);
-    vb.z = __byte_perm(rowk[2], 0u, sy);
-    vb.w = __byte_perm(rowk[3], 0u, sy);
-    const uint32_t sq = (uint32_t) (4 * i + q0);
-    tmem_st4(ta + 16u * i, va);                                     // K bytes 16 sq .. 16 sq + 15 of this row = columns 4 sq .. 4 sq + 3
-    *reinterpret_cast<uint4 *>(eB + sq * kBChunk) = vb;
+  }
+  if (!UNITW) {
+    const uint32_t *W32 = reinterpret_cast<const uint32_t *>(rawS + 3 * kCodeBytes);
+#pragma unroll
+    for (int q = 0; q < kGroups; q++)
+#pragma unroll
+      for (int i = 0; i < 4; i++) wt[q][i] = W32[4 * i + qb + q];
+  }
+  __syncwarp();
+  if (lane == 0) mbar_arrive(raw_empty_bar);                        // (release: orders the warp's reads above before the arrival)
+  mbar_wait(exp_empty_bar, exp_parity);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+  for (int q = 0; q < kGroups; q++) {
+    const int q0 = qb + q, g = kGroups >= 2 ? q >> 1 : 0;
+    const uint32_t pick = (q0 & 1) ? 0x4432u : 0x4410u;             // site quad 4 i + q0 = half (q0 & 1) of nibble word 2 i + (q0 >> 1)
+    uint32_t va[12], vb[12];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const uint32_t sx = pick_half(wa[g][i], pick), sy = pick_half(wb[g][i], pick);
+      if (UNITW) {
+#pragma unroll
+        for (int k = 0; k < 3; k++) va[3 * i + k] = __byte_perm(a.tA[k], 0u, sx);
+      } else {
+        const uint32_t ww = wt[q][i], wm = ww * a.amul, m3 = __byte_perm(a.t3, 0u, sx) & ww;   // weight bytes <= 42 when amul = 3
+#pragma unroll
+        for (int k = 0; k < 3; k++) va[3 * i + k] = (__byte_perm(0xFFu << (8 * k), 0u, sx) & wm) | m3;
+      }
+#pragma unroll
+      for (int k = 0; k < 3; k++) vb[3 * i + k] = __byte_perm(a.rowk[k], 0u, sy);
+    }
+    unsigned char *eq = eB + (uint32_t) (3 * q0) * kBChunk;
+#pragma unroll
+    for (int m = 0; m < 3; m++) {
+      tmem_st4(ta + 12u * q0 + 4u * m, make_uint4(va[4 * m], va[4 * m + 1], va[4 * m + 2], va[4 * m + 3]));
+      *reinterpret_cast<uint4 *>(eq + m * kBChunk) = make_uint4(vb[4 * m], vb[4 * m + 1], vb[4 * m + 2], vb[4 * m + 3]);
+    }
     if (paired) {                                                   // second tile's rows: row groups 16..31 of B
-      const uint32_t sz = pick_half(cB1[i * 256 + w0], pick);
-      vb.x = __byte_perm(rowk[0], 0u, sz);
-      vb.y = __byte_perm(rowk[1], 0u, sz);
-      vb.z = __byte_perm(rowk[2], 0u, sz);
-      vb.w = __byte_perm(rowk[3], 0u, sz);
-      *reinterpret_cast<uint4 *>(eB + sq * kBChunk + 2048) = vb;
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        const uint32_t sz = pick_half(wc[g][i], pick);
+#pragma unroll
+        for (int k = 0; k < 3; k++) vb[3 * i + k] = __byte_perm(a.rowk[k], 0u, sz);
+      }
+#pragma unroll
+      for (int m = 0; m < 3; m++)
+        *reinterpret_cast<uint4 *>(eq + m * kBChunk + 2048) = make_uint4(vb[4 * m], vb[4 * m + 1], vb[4 * m + 2], vb[4 * m + 3]);
     }
   }
 }
 
 // COUNT = true: the same pipeline computes the shared-site counts of --pairwise_del, cnt(i,j) = sum_s w_s m_i(s) m_j(s), as an
 // int8 GEMM with ONE byte per site (A' = w_s m_i(s), B' = m_j(s) from the presence masks) and writes them as the second
-// tile of the unit's slot.  A stage then holds up to kCntGroup = 4 word-list entries (256 sites), so that it is the same
-// 256 K bytes, 8 MMAs and operand layout as a stage of the sum pass instead of a quarter-size stage with full-size overheads.
+// tile of the unit's slot.  A stage then holds up to kCntGroup = 3 word-list entries (192 sites), so that it is the same
+// 192 K bytes, 6 MMAs and operand layout as a stage of the sum pass.
 template <bool COUNT>
-__global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
+__global__ void __launch_bounds__(kThreads, 1) k_dist_umma(const __grid_constant__ UmmaArgs a) {
   constexpr int kOffW = 3 * kCodeBytes;                              // sum pass: weights behind the three code tiles
-  constexpr int kRawN = COUNT ? kCntRaw : kRaw;                      // raw ring: stages and bytes per stage
-  constexpr int kRawStage = COUNT ? kCntRawBytes : kRawBytes;
-  constexpr int kBChunk = 4096;                       // B: bytes between 16-byte K chunks (32 row groups x 128 B)
-  constexpr int kMmas = 8;
+  constexpr int kRawStage = COUNT ? kCntRawBytes : kRawBytes;        // (both passes use the kRaw slots of the ring)
   extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char *raw = smem;                                         // kRaw x kRawBytes (count pass: kCntRaw x kCntRawBytes)
+  unsigned char *raw = smem;                                         // kRaw x kRawBytes
   unsigned char *exps = smem + (size_t) kRingBytes;                  // kExp x kExpBytes (16-byte aligned: the ring is a multiple of 128)
   uint64_t *bars = reinterpret_cast<uint64_t *>(exps + (size_t) kExp * kExpBytes);
   uint64_t *raw_full = bars, *raw_empty = raw_full + kRaw, *exp_full = raw_empty + kRaw, *exp_empty = exp_full + kExp;
@@ -218,23 +262,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
   uint32_t *raw_meta = reinterpret_cast<uint32_t *>(bars + kNBar);    // [kRaw][2] = {unit, flags}
   uint32_t *exp_meta = raw_meta + 2 * kRaw;                           // [kExp][2]
   uint32_t *acc_meta = exp_meta + 2 * kExp;                           // {unit, flags} of the finished accumulator (+ 2 spare words)
-  uint32_t *lut = acc_meta + 4;                                       // [4]
-  uint32_t *tmem_slot = lut + 4;
+  uint32_t *tmem_slot = acc_meta + 4;
   uint32_t *lut16 = tmem_slot + 4;                                    // [16] presence nibble -> 0x01 bytes (count pass)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kRaw; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kExpWarps); }
-    for (int s = 0; s < kExp; s++) { mbar_init(&exp_full[s], kExpWarps); mbar_init(&exp_empty[s], 1); }
+    for (int s = 0; s < kRaw; s++) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], kGroupWarps); }
+    for (int s = 0; s < kExp; s++) { mbar_init(&exp_full[s], kGroupWarps); mbar_init(&exp_empty[s], 1); }
     for (int s = 0; s < 2; s++) { mbar_init(&acc_full[s], 2); mbar_init(&acc_empty[s], kEpiWarps); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    lut[0] = a.lut[0]; lut[1] = a.lut[1]; lut[2] = a.lut[2]; lut[3] = a.lut[3];
   }
   if (COUNT && threadIdx.x >= 32 && threadIdx.x < 48) {
     const uint32_t n = threadIdx.x - 32;
     lut16[n] = (n & 1u) | ((n & 2u) << 7) | ((n & 4u) << 14) | ((n & 8u) << 21);
   }
-  if (warp == 1) {                                  // TMEM: accumulator + kExp stages of A (448 of the 512 columns; one CTA per SM)
+  if (warp == 1) {                                  // TMEM: accumulator + kExp stages of A (one CTA per SM)
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
@@ -278,7 +320,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
               if (paired) bulk_g2s(de + 2 * kMaskBytes, a.mask + ((uint64_t) tj1 * a.NW + word) * 128, kMaskBytes, &raw_full[rs]);
               bulk_g2s(dst + kCntGroup * kCntEntry + e * 64, a.wsite + ((uint64_t) (layers[e] & 0x7FFFFFFFu) * a.NW + word) * 64, 64, &raw_full[rs]);
             }
-            if (++rs == kRawN) { rs = 0; rph ^= 1; }
+            if (++rs == kRaw) { rs = 0; rph ^= 1; }
           }
           continue;
         }
@@ -297,12 +339,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
           bulk_g2s(dst + kCodeBytes, Bb + word * 1024, kCodeBytes, &raw_full[rs]);
           if (paired) bulk_g2s(dst + 2 * kCodeBytes, B1b + word * 1024, kCodeBytes, &raw_full[rs]);
           bulk_g2s(dst + kOffW, wsrc, 64, &raw_full[rs]);
-          if (++rs == kRawN) { rs = 0; rph ^= 1; }
+          if (++rs == kRaw) { rs = 0; rph ^= 1; }
         }
       }
-      mbar_wait_sleep(&raw_empty[rs], rph ^ 1);
-      raw_meta[rs * 2 + 1] = kExit;
-      mbar_arrive(&raw_full[rs]);
+      for (int g = 0; g < kGroups; g++) {                             // one exit stage per expander group
+        mbar_wait_sleep(&raw_empty[rs], rph ^ 1);
+        raw_meta[rs * 2 + 1] = kExit;
+        mbar_arrive(&raw_full[rs]);
+        if (++rs == kRaw) { rs = 0; rph ^= 1; }
+      }
     }
   } else if (warp == 1) {
     // ===== MMA issue (one lane) =====
@@ -315,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
       for (;;) {
         mbar_wait(&exp_full[es], eph);
         const uint32_t u = exp_meta[es * 2], fl = exp_meta[es * 2 + 1];
-        if (fl & kExit) {
+        if (fl & kExit) {                                            // (the first exit stage in stage order; the other groups' are never read)
           mbar_wait(&acc_empty[0], aph ^ 1);
           acc_meta[1] = kExit;
           mbar_arrive(&acc_full[0]);
@@ -350,25 +395,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
       }
     }
   } else if (warp < 2 + kExpWarps) {
-    // ===== expanders: 512 threads, thread -> (row r, byte q0 of each of the 4 code words) of both operands =====
+    // ===== expanders: group grp takes stages grp, grp + kGroups, ...; thread -> (row r, site quads qb .. qb + kGroups - 1 of each word) =====
     // (a warp reaches the TMEM lanes of its quadrant warp % 4 only: that fixes which rows it expands)
-    const int r = (warp & 3) * 32 + lane, q0 = (warp - 2) >> 2;
-    const bool lead = warp == 2 && lane == 0;
+    const int r = (warp & 3) * 32 + lane;
+    const int grp = (warp - 2) / kGroupWarps, qb = (((warp - 2) % kGroupWarps) >> 2) * kGroups;
+    const bool lead = (warp - 2) % kGroupWarps == 0 && lane == 0;
     const uint32_t ta_lane = tmem + ((uint32_t) ((warp & 3) * 32) << 16) + kAccCols;
-    uint32_t rowk[4];                                               // row k of the S * f table: byte c = S f(k, c)
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-      rowk[k] = ((a.lut[0] >> (8 * k)) & 0xFFu) | (((a.lut[1] >> (8 * k)) & 0xFFu) << 8) | (((a.lut[2] >> (8 * k)) & 0xFFu) << 16) |
-                (((a.lut[3] >> (8 * k)) & 0xFFu) << 24);
     const uint32_t unit_off = (uint32_t) (r >> 3) * 128 + (uint32_t) (r & 7) * 16;
-    int rs = 0, es = 0;
-    uint32_t rph = 0, eph = 0;
-    for (;;) {
+    for (uint32_t n = (uint32_t) grp;; n += kGroups) {              // stage n: raw slot n % kRaw, expanded slot n % kExp
+      const int rs = (int) (n % kRaw), es = (int) (n % kExp);
+      const uint32_t rph = (n / kRaw) & 1u, eph = (n / kExp) & 1u;
       mbar_wait(&raw_full[rs], rph);
       const uint32_t u = raw_meta[rs * 2], fl = raw_meta[rs * 2 + 1];
-      mbar_wait(&exp_empty[es], eph ^ 1);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       if (fl & kExit) {
+        mbar_wait(&exp_empty[es], eph ^ 1);
         if (lead) exp_meta[es * 2 + 1] = kExit;
         __syncwarp();
         if (lane == 0) mbar_arrive(&exp_full[es]);
@@ -378,8 +418,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
       if (COUNT) {
         // one byte per site: for each word-list entry e of the stage, thread (r, q0) expands the 16 presence bits
         // 16 q0 .. 16 q0 + 15 of its row of each operand into one 16-byte unit (K chunk 4 e + q0); A bytes carry the site weights
+        mbar_wait(&exp_empty[es], eph ^ 1);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t ne = (fl >> kEntriesShift) & 7u;
-        for (uint32_t e = 0; e < ne; e++) {
+        for (uint32_t eq = 0; eq < ne * kGroups; eq++) {
+          const uint32_t e = eq / kGroups;
+          const int q0 = qb + (int) (eq % kGroups);
           const unsigned char *re = rawS + e * kCntEntry;
           const uint32_t ma = reinterpret_cast<const uint32_t *>(re)[r * 2 + (q0 >> 1)] >> (16 * (q0 & 1));
           const uint32_t mb = reinterpret_cast<const uint32_t *>(re + kMaskBytes)[r * 2 + (q0 >> 1)] >> (16 * (q0 & 1));
@@ -417,28 +461,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_dist_umma(UmmaArgs a) {
         if (lead) { exp_meta[es * 2] = u; exp_meta[es * 2 + 1] = fl; }
         __syncwarp();
         if (lane == 0) { mbar_arrive(&exp_full[es]); mbar_arrive(&raw_empty[rs]); }
-        if (++rs == kRawN) { rs = 0; rph ^= 1; }
-        if (++es == kExp) { es = 0; eph ^= 1; }
         continue;
       }
-      const uint32_t *cA = reinterpret_cast<const uint32_t *>(rawS) + r, *cB = reinterpret_cast<const uint32_t *>(rawS + kCodeBytes) + r;
-      const uint32_t *cB1 = reinterpret_cast<const uint32_t *>(rawS + 2 * kCodeBytes) + r;
-      const uint32_t *W32 = reinterpret_cast<const uint32_t *>(rawS + kOffW) + q0;
       unsigned char *eB = exps + (size_t) es * kExpBytes + unit_off;
-      const uint32_t ta = ta_lane + (uint32_t) es * kACols + 4u * q0;
+      const uint32_t ta = ta_lane + (uint32_t) es * kACols;
       const bool paired = (fl & kPair) != 0;
       if (fl & kUnitW)
-        expand_codes<true>(cA, cB, cB1, W32, eB, ta, q0, paired, rowk);
+        expand_stage<true>(rawS, r, qb, lane, paired, eB, ta, a, &raw_empty[rs], &exp_empty[es], eph ^ 1);
       else
-        expand_codes<false>(cA, cB, cB1, W32, eB, ta, q0, paired, rowk);
+        expand_stage<false>(rawS, r, qb, lane, paired, eB, ta, a, &raw_empty[rs], &exp_empty[es], eph ^ 1);
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // A rows are in tensor memory
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to the UMMA (async) proxy
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       if (lead) { exp_meta[es * 2] = u; exp_meta[es * 2 + 1] = fl; }
       __syncwarp();
-      if (lane == 0) { mbar_arrive(&exp_full[es]); mbar_arrive(&raw_empty[rs]); }
-      if (++rs == kRawN) { rs = 0; rph ^= 1; }
-      if (++es == kExp) { es = 0; eph ^= 1; }
+      if (lane == 0) mbar_arrive(&exp_full[es]);
     }
   } else {
     // ===== epilogue: a warp can read the 32 TMEM lanes (= tile rows) of its quadrant warp % 4 =====
@@ -539,6 +576,9 @@ extern "C" int ngsd_probe_umma_tmacs(int device, double *umma_tmacs) {
   return NGSD_OK;
 }
 
+// largest site weight one weight layer may carry: the A bytes are int8 and hold 3 w without --pairwise_del (header)
+uint32_t ngsd_int_weight_cap(const ngsd_ctx *ctx) { return (ngsd_use_umma() && !ctx->cfg.pairwise_del) ? 42u : 127u; }
+
 cudaError_t ngsd_launch_dist_umma(ngsd_ctx *ctx, uint32_t n_units, int grid, uint32_t pstride, bool count) {
   static bool attr_set[64] = {};
   if (!attr_set[ctx->device & 63]) {
@@ -566,7 +606,15 @@ cudaError_t ngsd_launch_dist_umma(ngsd_ctx *ctx, uint32_t n_units, int grid, uin
   a.n_units = ctx->n_tiles ? n_units / ctx->n_tiles * ctx->n_pairs : 0;     // (split, tile) units -> (split, tile pair) units
   a.pstride = pstride;
   a.cnt_off = NGSD_TILE_ELEMS;
-  for (int k = 0; k < 4; k++) a.lut[k] = ctx->int_lut[k];
+  // ctx->int_lut[c] byte k = S f(k, c) (ngsd_int_lut); the three-plane tables of the header
+  const bool third = !ctx->cfg.pairwise_del;                                // missing = the uniform triple
+  a.amul = third ? 3u : 1u;
+  a.t3 = third ? 0xFF000000u : 0u;
+  for (int k = 0; k < 3; k++) {
+    a.tA[k] = (a.amul << (8 * k)) | (third ? 0x01000000u : 0u);
+    a.rowk[k] = 0;
+    for (int c = 0; c < 4; c++) a.rowk[k] |= (((ctx->int_lut[c] >> (8 * k)) & 0xFFu) / a.amul) << (8 * c);
+  }
   cudaError_t e = cudaMemsetAsync(ctx->d_sched, 0, sizeof(uint32_t), ctx->stream);
   if (e != cudaSuccess) return e;
   if (count)
@@ -625,7 +673,9 @@ cudaError_t ngsd_launch_count_umma(ngsd_ctx *ctx, const ngsd_count_umma_args &c)
   a.n_units = c.n_splits * ctx->n_pairs;
   a.pstride = NGSD_TILE_ELEMS;
   a.cnt_off = 0;
-  for (int k = 0; k < 4; k++) a.lut[k] = 0;
+  for (int k = 0; k < 3; k++) a.rowk[k] = a.tA[k] = 0;
+  a.t3 = 0;
+  a.amul = 1;
   cudaError_t e = cudaMemsetAsync(ctx->d_sched, 0, sizeof(uint32_t), ctx->stream);
   if (e != cudaSuccess) return e;
   const int grid = (int) std::min<uint64_t>((uint64_t) ctx->n_sm, std::max<uint32_t>(a.n_units, 1u));

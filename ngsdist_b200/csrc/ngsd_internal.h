@@ -204,6 +204,7 @@ bool ngsd_int_lut(const double *score, bool pairwise_del, uint32_t lut[4], doubl
 cudaError_t ngsd_launch_dist_imma(ngsd_ctx *ctx, uint32_t n_units, int grid, bool count);
 int ngsd_imma_ctas_per_sm();
 bool ngsd_use_umma();
+uint32_t ngsd_int_weight_cap(const ngsd_ctx *ctx);   // dist_umma.cu: largest site weight per weight layer of the integer path
 cudaError_t ngsd_launch_dist_umma(ngsd_ctx *ctx, uint32_t n_units, int grid, uint32_t pstride, bool count);   // dist_umma.cu (tcgen05)
 struct ngsd_count_umma_args {
   const uint32_t *split_begin;   // [n_splits + 1] positions in the word list

@@ -69,16 +69,18 @@ def test_genotype_input_many_tiles_jc69():
             assert_close(r["dist"][r0:r0 + 64, c0:c0 + 64][sub], o["dist"][sub], "dist pdel=%d" % pdel)
 
 
-def test_large_multiplicities_use_weight_layers():
-    """Block multiplicities above 127 (one int8 operand byte) are split into layers; linearity in the weights is exact."""
+@pytest.mark.parametrize("pdel", [True, False])
+def test_large_multiplicities_use_weight_layers(pdel):
+    """Block multiplicities above one int8 operand byte (127; 42 without --pairwise_del, where the byte carries 3 w) are
+    split into layers; linearity in the weights is exact."""
     n_ind, n_sites, bs = 130, 1280, 128
     raw = oracle.synth_raw(3, 0.1, n_ind, n_sites)
-    p = nb().Params(n_ind=n_ind, n_sites=n_sites, in_probs=True, call_geno=True, pairwise_del=True, evol_model=0,
+    p = nb().Params(n_ind=n_ind, n_sites=n_sites, in_probs=True, call_geno=True, pairwise_del=pdel, evol_model=0,
                     no_block_cache=True)     # the direct weighted contraction is what splits weights into layers
     with nb().NgsDistB200(p) as g:
         g.push_sites(raw)
         nbk = n_sites // bs
-        c_big = np.array([300, 0, 1, 127, 128, 0, 5, 0, 2, 254], dtype=np.uint32)
+        c_big = np.array([300, 0, 1, 127, 128, 42, 43, 0, 85, 254], dtype=np.uint32)
         unit = [np.eye(nbk, dtype=np.uint32)[b] for b in range(nbk)]
         big = g.distances(c_big, bs, want_num=True, want_cnt=True)
         num = np.zeros((n_ind, n_ind))
@@ -86,10 +88,14 @@ def test_large_multiplicities_use_weight_layers():
         for b in range(nbk):
             if c_big[b]:
                 r = g.distances(unit[b], bs, want_num=True, want_cnt=True)
-                num += float(c_big[b]) * r["num"]
+                num += float(c_big[b]) * np.rint(r["num"] * 18)
                 cnt += np.uint64(c_big[b]) * r["cnt"]
-    assert np.array_equal(big["cnt"], cnt)
-    assert np.array_equal(big["num"], num)        # multiples of 0.5 far below 2^53: every sum here is exact
+    if pdel:
+        assert np.array_equal(big["cnt"], cnt)
+    else:                                         # without --pairwise_del every pair counts every site of the replicate
+        off = ~np.eye(n_ind, dtype=bool)
+        assert np.all(big["cnt"][off] == n_sites)
+    assert np.array_equal(np.rint(big["num"] * 18), num)        # num is a multiple of 1/18 (1/2 with pairwise_del) far below 2^53
 
 
 def test_soft_thresholds_fall_back_to_fp64_planes():
