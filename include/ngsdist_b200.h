@@ -234,6 +234,16 @@ NGSD_API int ngsd_bind_host_to_device(int device);
 NGSD_API int ngsd_nj_tree(ngsd_ctx *ctx, const double *dist_host, const char *const *labels, char *newick, uint64_t newick_cap,
                           uint64_t *newick_len);
 
+/* Bootstrap support of a tree -- the last step of the reference's workflow (README.md:83-98: `raxmlHPC -f b -t main -z
+ * boots` on FastME's trees).  HOST code only, no context: for every internal edge of `main_newick`, the number of trees among
+ * `rep_newicks[n_reps]` that hold the same bipartition of the leaf labels is written as the node's label
+ * ("(A:0.1,B:0.2)87:0.05"); percent != 0 gives RAxML's integer percentages (int)(0.5 + 100 c / n), else the raw counts.
+ * Replicates given as "NA" (the CLI's marker for a matrix without a tree) are skipped.  Branch lengths are copied as
+ * written.  NGSD_ERR_ARG for malformed Newick, leaf sets that differ, or when out_cap is too small (*out_len = bytes
+ * needed, without the NUL).  No reference code exists for this step: parity is against tests/ restating the definition. */
+NGSD_API int ngsd_tree_support(const char *main_newick, const char *const *rep_newicks, uint64_t n_reps, int percent, char *out,
+                               uint64_t out_cap, uint64_t *out_len);
+
 /* Host-side helper with the reference's RNG semantics (gsl_rng_taus; ngsDist.cpp:179-180, gen_func.cpp:117-119):
  * state[3] is seeded by ngsd_taus_seed and advanced by n_blocks draws per call of ngsd_boot_block_counts, which
  * fills counts[n_blocks] for one replicate exactly as rnd_map_data would have re-pointed the blocks. */

@@ -21,7 +21,7 @@ ABI_SYMBOLS = [
     "ngsd_boot_block_counts", "ngsd_get_posteriors", "ngsd_synth_raw_device", "ngsd_get_timing", "ngsd_stream",
     "ngsd_probe_fp64_tflops", "ngsd_probe_int8_tmacs", "ngsd_probe_umma_tmacs", "ngsd_host_alloc", "ngsd_host_free", "ngsd_set_tile_shard", "ngsd_device_results", "ngsd_finish",
     "ngsd_distances_batch", "ngsd_comm_unique_id", "ngsd_comm_attach", "ngsd_comm_allgather_operands", "ngsd_comm_reduce_sites", "ngsd_comm_reduce_tiles",
-    "ngsd_comm_barrier", "ngsd_comm_stats", "ngsd_bind_host_to_device", "ngsd_deferred_stats", "ngsd_push_sites_packed", "ngsd_nj_tree",
+    "ngsd_comm_barrier", "ngsd_comm_stats", "ngsd_bind_host_to_device", "ngsd_deferred_stats", "ngsd_push_sites_packed", "ngsd_nj_tree", "ngsd_tree_support",
 ]
 ABI_VERSION = 2
 COMM_ID_BYTES = 128
@@ -124,11 +124,12 @@ def lib():
     L.ngsd_deferred_stats.argtypes = [vp, C.POINTER(u64)]
     L.ngsd_push_sites_packed.argtypes = [vp, vp, i32, dbl, u64, u64]
     L.ngsd_nj_tree.argtypes = [vp, vp, vp, vp, u64, C.POINTER(u64)]
+    L.ngsd_tree_support.argtypes = [C.c_char_p, vp, u64, i32, vp, u64, C.POINTER(u64)]
     for name in ("ngsd_create", "ngsd_destroy", "ngsd_push_sites", "ngsd_push_sites_device", "ngsd_push_genotypes", "ngsd_push_packed_genotypes", "ngsd_frontend",
                  "ngsd_distances", "ngsd_get_posteriors", "ngsd_synth_raw_device", "ngsd_get_timing", "ngsd_probe_fp64_tflops", "ngsd_probe_int8_tmacs", "ngsd_probe_umma_tmacs",
                  "ngsd_set_tile_shard", "ngsd_device_results", "ngsd_finish", "ngsd_distances_batch", "ngsd_comm_unique_id", "ngsd_comm_attach",
                  "ngsd_comm_allgather_operands", "ngsd_comm_reduce_sites", "ngsd_comm_reduce_tiles", "ngsd_comm_barrier", "ngsd_comm_stats",
-                 "ngsd_bind_host_to_device", "ngsd_deferred_stats", "ngsd_push_sites_packed", "ngsd_nj_tree"):
+                 "ngsd_bind_host_to_device", "ngsd_deferred_stats", "ngsd_push_sites_packed", "ngsd_nj_tree", "ngsd_tree_support"):
         getattr(L, name).restype = i32
     _lib = L
     return L
@@ -180,6 +181,27 @@ class Params:
         if not p.in_probs or p.call_geno:
             p.indep_geno = True
         return p
+
+
+def tree_support(main_newick, rep_newicks, percent=True):
+    """Bootstrap support of `main_newick` from the replicate trees (host code of the library; no GPU involved):
+    the main tree with the number (or RAxML-style integer percentage) of replicates holding each internal edge's
+    bipartition as node labels."""
+    reps = [r.encode() if isinstance(r, str) else r for r in rep_newicks]
+    arr = (C.c_char_p * max(1, len(reps)))(*reps) if reps else None
+    main = main_newick.encode() if isinstance(main_newick, str) else main_newick
+    need = C.c_uint64(0)
+    cap = 2 * len(main) + 64
+    for _ in range(2):
+        buf = C.create_string_buffer(cap)
+        rc = lib().ngsd_tree_support(main, arr, len(reps), 1 if percent else 0, buf, cap, C.byref(need))
+        if rc == 0:
+            return buf.value.decode()
+        if need.value + 1 > cap:
+            cap = need.value + 1
+            continue
+        break
+    raise ValueError("ngsd_tree_support: malformed Newick or different leaf sets (rc %d)" % rc)
 
 
 def taus_block_counts(state, n_blocks):

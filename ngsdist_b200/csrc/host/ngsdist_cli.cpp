@@ -10,7 +10,7 @@
 //
 // Differences on purpose (documented in DESIGN.md): text lines may be longer than the reference's 500 000-character
 // buffer; input is streamed in chunks (the whole data set is never held on the host); --verbose >= 5 per-site dumps are
-// not produced; additive flags: --device N (first GPU), --tree FILE (a neighbour-joining tree per matrix), --n_gpus N and
+// not produced; additive flags: --device N (first GPU), --tree FILE (a neighbour-joining tree per matrix, and FILE.support with bootstrap support values), --n_gpus N and
 // --shard auto|replicated|sites (multi-GPU inside
 // the library).  The tail of gen_dist (ngsDist.cpp:372-386: division, -log(1-d), JC69) runs HERE with the
 // host's libm on the raw distance the device returns, so that the written values are the reference's to the last digit.
@@ -348,7 +348,7 @@ static int selftest_io(uint64_t n) {
 
 // --tree: the step the reference's workflow (README.md:83-98) runs FastME for -- one neighbour-joining tree per matrix,
 // computed on the device from the matrix that was just written (after the host's -log / JC69 tail)
-static void write_tree(FILE *fh, ngsd_ctx *ctx, const double *d, const std::vector<std::string> &lab) {
+static void write_tree(FILE *fh, ngsd_ctx *ctx, const double *d, const std::vector<std::string> &lab, std::vector<std::string> *keep) {
   std::vector<const char *> names;
   for (auto &l : lab) names.push_back(l.c_str());
   uint64_t need = 0;
@@ -361,10 +361,37 @@ static void write_tree(FILE *fh, ngsd_ctx *ctx, const double *d, const std::vect
   if (rc) {
     fprintf(stderr, "> no tree for this matrix: %s\n", ngsd_last_error(ctx));
     fprintf(fh, "NA\n");
+    keep->push_back("NA");
     return;
   }
   fwrite(buf.data(), 1, need, fh);
   fputc('\n', fh);
+  keep->emplace_back(buf.data(), need);
+}
+
+// FILE.support: the main tree with, on every internal edge, the percentage of bootstrap trees that hold it -- what the
+// reference's workflow gets from `raxmlHPC -f b -t main -z boots` (README.md:83-98)
+static void write_support(const char *tree_path, const std::vector<std::string> &trees) {
+  if (trees.size() < 2 || trees[0] == "NA") return;
+  std::vector<const char *> reps;
+  for (size_t k = 1; k < trees.size(); k++) reps.push_back(trees[k].c_str());
+  uint64_t need = 0;
+  std::vector<char> buf(2 * trees[0].size() + 64);
+  int rc = ngsd_tree_support(trees[0].c_str(), reps.data(), reps.size(), 1, buf.data(), buf.size(), &need);
+  if (rc && need + 1 > buf.size()) {
+    buf.resize(need + 1);
+    rc = ngsd_tree_support(trees[0].c_str(), reps.data(), reps.size(), 1, buf.data(), buf.size(), &need);
+  }
+  if (rc) {
+    fprintf(stderr, "> no support values: the trees do not share one set of labels\n");
+    return;
+  }
+  const std::string path = std::string(tree_path) + ".support";
+  FILE *fh = fopen(path.c_str(), "w");
+  if (!fh) die("main", "cannot open tree support output file!");
+  fwrite(buf.data(), 1, need, fh);
+  fputc('\n', fh);
+  fclose(fh);
 }
 
 // NGSD_CLI_TIMING=1: wall-clock stamps of the phases on stderr (development aid)
@@ -747,6 +774,7 @@ int main(int argc, char **argv) {
 
   FILE *out_fh = fopen(p.out, "w");
   if (!out_fh) die("main", "cannot open output file!");
+  std::vector<std::string> trees;                                      // --tree: the Newick strings, for FILE.support
   FILE *tree_fh = p.tree ? fopen(p.tree, "w") : nullptr;
   if (p.tree && !tree_fh) die("main", "cannot open tree output file!");
   static char obuf[1 << 22];
@@ -774,7 +802,7 @@ int main(int argc, char **argv) {
         if (host_model) apply_model(dist.data() + q * n2, p.n_ind, p.evol_model, p.n_threads);
         if (p.verbose >= 2) fprintf(stderr, "> Printing distance matrix\n");
         write_matrix(out_fh, labels, dist.data() + q * n2, p.n_ind, p.n_threads);
-        if (tree_fh) write_tree(tree_fh, ctx, dist.data() + q * n2, labels);
+        if (tree_fh) write_tree(tree_fh, ctx, dist.data() + q * n2, labels, &trees);
       }
       rep += k - 1;
       continue;
@@ -805,10 +833,11 @@ int main(int argc, char **argv) {
     if (host_model) apply_model(dist.data(), p.n_ind, p.evol_model, p.n_threads);
     if (p.verbose >= 2) fprintf(stderr, "> Printing distance matrix\n");
     write_matrix(out_fh, labels, dist.data(), p.n_ind, p.n_threads);
-    if (tree_fh) write_tree(tree_fh, ctx, dist.data(), labels);
+    if (tree_fh) write_tree(tree_fh, ctx, dist.data(), labels, &trees);
   }
   fclose(out_fh);
   if (tree_fh) fclose(tree_fh);
+  if (tree_fh && p.n_boot_rep > 0) write_support(p.tree, trees);
   stamp("all matrices written");
   if (p.verbose >= 1) fprintf(stderr, "==> Freeing memory...\n");
   ngsd_destroy(ctx);

@@ -17,8 +17,11 @@
 // replays the n - 3 join records into Newick once at the end.  Sum over joins of the active m^2 entries = n^3 / 3 reads:
 // 21 GB at n = 2 000 (4 ms of HBM time; launch-bound at ~8 us per join), 21 TB at n = 20 000.
 #include <math.h>
+#include <string.h>
 
 #include <string>
+#include <unordered_map>
+#include <vector>
 
 #include "ngsd_internal.h"
 
@@ -234,5 +237,244 @@ extern "C" int ngsd_nj_tree(ngsd_ctx *ctx, const double *dist_host, const char *
   *newick_len = out.size();
   if (!newick || newick_cap < out.size() + 1) { ngsd_set_error(ctx, "newick buffer too small: %llu bytes needed", (unsigned long long) out.size() + 1); return NGSD_ERR_ARG; }
   memcpy(newick, out.c_str(), out.size() + 1);
+  return NGSD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Bootstrap support: the last step of the reference's workflow (README.md:83-98 runs `raxmlHPC -f b -t main -z boots`).
+// Host code only (no context, no device): Newick in, Newick with support labels on the internal nodes out.
+// A bipartition is identified by the XOR of per-leaf 128-bit keys over one side (XOR with the key of all leaves gives the
+// other side; the smaller of the two is the canonical one), so a tree is hashed in one pass and a replicate costs O(n).
+namespace {
+
+struct TsNode {
+  int parent = -1;
+  std::vector<int> kids;
+  std::string label, length;                      // length: the text after ':' as it was written
+  int leaf = -1;                                  // index of the leaf's label in the main tree's leaf order
+  uint64_t h0 = 0, h1 = 0;                        // XOR of the leaf keys below
+  uint32_t n_below = 0;
+};
+
+struct TsTree {
+  std::vector<TsNode> nodes;                      // nodes[0] = root
+  uint32_t n_leaves = 0;
+};
+
+inline uint64_t ts_mix(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+// Newick subset: nested parentheses, unquoted or 'single-quoted' labels, optional ":length", optional labels on internal
+// nodes (ignored), terminated by ';'.  Returns false on malformed input.
+bool ts_parse(const char *s, TsTree *t) {
+  t->nodes.clear();
+  t->nodes.emplace_back();
+  t->n_leaves = 0;
+  int cur = 0;
+  const char *p = s;
+  auto skip_ws = [&]() { while (*p == ' ' || *p == '\t' || *p == '\n' || *p == '\r') p++; };
+  auto read_label = [&](std::string *out) {
+    skip_ws();
+    out->clear();
+    if (*p == '\'') {
+      p++;
+      while (*p && !(*p == '\'' && p[1] != '\'')) { if (*p == '\'') p++; out->push_back(*p++); }
+      if (*p != '\'') return false;
+      p++;
+    } else {
+      while (*p && !strchr("():,; \t\n\r", *p)) out->push_back(*p++);
+    }
+    return true;
+  };
+  auto read_length = [&](std::string *out) {
+    skip_ws();
+    out->clear();
+    if (*p != ':') return;
+    p++;
+    skip_ws();
+    while (*p && !strchr("(),; \t\n\r", *p)) out->push_back(*p++);
+  };
+  skip_ws();
+  if (*p != '(') return false;
+  int depth = 0;
+  bool expect_node = true;                        // after '(' or ',': a subtree or a leaf must follow
+  while (*p) {
+    skip_ws();
+    if (*p == '(') {
+      if (!expect_node) return false;
+      if (depth > 0) {                            // (the first '(' opens the root, node 0)
+        TsNode n;
+        n.parent = cur;
+        t->nodes.push_back(n);
+        const int id = (int) t->nodes.size() - 1;
+        t->nodes[cur].kids.push_back(id);
+        cur = id;
+      }
+      depth++;
+      p++;
+      expect_node = true;
+    } else if (*p == ',') {
+      if (expect_node || depth == 0) return false;
+      p++;
+      expect_node = true;
+    } else if (*p == ')') {
+      if (expect_node || depth == 0) return false;
+      p++;
+      depth--;
+      std::string lab, len;
+      if (!read_label(&lab)) return false;
+      read_length(&len);
+      t->nodes[cur].length = len;                 // (a label on an internal node is dropped: support goes there)
+      if (depth == 0) {
+        skip_ws();
+        if (*p != ';') return false;
+        break;
+      }
+      cur = t->nodes[cur].parent;
+      expect_node = false;
+    } else {
+      if (!expect_node || depth == 0) return false;
+      TsNode n;
+      n.parent = cur;
+      if (!read_label(&n.label) || n.label.empty()) return false;
+      read_length(&n.length);
+      n.leaf = 0;
+      t->nodes.push_back(n);
+      t->nodes[cur].kids.push_back((int) t->nodes.size() - 1);
+      t->n_leaves++;
+      expect_node = false;
+    }
+  }
+  return depth == 0 && *p == ';' && t->n_leaves >= 2;
+}
+
+// leaf indices from `index` (label -> position), subtree hashes bottom-up.  false: unknown or repeated label
+bool ts_hash(TsTree *t, const std::unordered_map<std::string, int> &index) {
+  std::vector<uint8_t> seen(index.size(), 0);
+  for (int v = (int) t->nodes.size() - 1; v >= 0; v--) {          // children always have larger ids than their parent
+    TsNode &n = t->nodes[v];
+    if (n.kids.empty()) {
+      auto it = index.find(n.label);
+      if (it == index.end() || seen[it->second]) return false;
+      seen[it->second] = 1;
+      n.leaf = it->second;
+      n.h0 = ts_mix(2 * (uint64_t) n.leaf + 1);
+      n.h1 = ts_mix(ts_mix(2 * (uint64_t) n.leaf + 2));
+      n.n_below = 1;
+    }
+    if (n.parent >= 0) {
+      TsNode &q = t->nodes[n.parent];
+      q.h0 ^= n.h0;
+      q.h1 ^= n.h1;
+      q.n_below += n.n_below;
+    }
+  }
+  return t->n_leaves == index.size();
+}
+
+struct TsKey {
+  uint64_t a, b;
+  bool operator==(const TsKey &o) const { return a == o.a && b == o.b; }
+};
+struct TsKeyHash {
+  size_t operator()(const TsKey &k) const { return (size_t) (k.a ^ (k.b * 0x9E3779B97F4A7C15ull)); }
+};
+
+// canonical keys of the non-trivial bipartitions of a hashed tree, each once; node -> key index in `of_node` (or -1)
+void ts_splits(const TsTree &t, std::vector<TsKey> *keys, std::vector<int> *of_node) {
+  const TsNode &root = t.nodes[0];
+  const uint64_t all0 = root.h0, all1 = root.h1;
+  keys->clear();
+  if (of_node) of_node->assign(t.nodes.size(), -1);
+  std::unordered_map<TsKey, int, TsKeyHash> once;
+  for (size_t v = 1; v < t.nodes.size(); v++) {
+    const TsNode &n = t.nodes[v];
+    if (n.kids.empty() || n.n_below < 2 || n.n_below + 2 > t.n_leaves) continue;   // trivial: a leaf or all but one leaf
+    // canonical side: the smaller of the two keys (the side below, and everything else)
+    const TsKey k1{n.h0, n.h1}, k2{n.h0 ^ all0, n.h1 ^ all1};
+    const TsKey k = (k1.a < k2.a || (k1.a == k2.a && k1.b <= k2.b)) ? k1 : k2;
+    auto it = once.find(k);
+    int id;
+    if (it == once.end()) {
+      id = (int) keys->size();
+      keys->push_back(k);
+      once.emplace(k, id);
+    } else {
+      id = it->second;
+    }
+    if (of_node) (*of_node)[v] = id;
+  }
+}
+
+void ts_write(const TsTree &t, int v, const std::vector<std::string> &support, std::string *out) {
+  const TsNode &n = t.nodes[v];
+  if (n.kids.empty()) {
+    *out += n.label;
+  } else {
+    out->push_back('(');
+    for (size_t k = 0; k < n.kids.size(); k++) {
+      if (k) out->push_back(',');
+      ts_write(t, n.kids[k], support, out);
+    }
+    out->push_back(')');
+    *out += support[v];
+  }
+  if (!n.length.empty()) {
+    out->push_back(':');
+    *out += n.length;
+  }
+}
+
+}  // namespace
+
+extern "C" int ngsd_tree_support(const char *main_newick, const char *const *rep_newicks, uint64_t n_reps, int percent, char *out,
+                                 uint64_t out_cap, uint64_t *out_len) {
+  if (!main_newick || (n_reps && !rep_newicks) || !out_len) return NGSD_ERR_ARG;
+  TsTree mt;
+  if (!ts_parse(main_newick, &mt)) return NGSD_ERR_ARG;
+  std::unordered_map<std::string, int> index;
+  for (const TsNode &n : mt.nodes)
+    if (n.kids.empty() && n.parent >= 0) {
+      if (!index.emplace(n.label, (int) index.size()).second) return NGSD_ERR_ARG;     // repeated label
+    }
+  if (!ts_hash(&mt, index)) return NGSD_ERR_ARG;
+  std::vector<TsKey> mkeys;
+  std::vector<int> of_node;
+  ts_splits(mt, &mkeys, &of_node);
+  std::unordered_map<TsKey, uint64_t, TsKeyHash> count;
+  for (const TsKey &k : mkeys) count.emplace(k, 0);
+  uint64_t used = 0;
+  TsTree rt;
+  std::vector<TsKey> rkeys;
+  for (uint64_t r = 0; r < n_reps; r++) {
+    if (!rep_newicks[r]) return NGSD_ERR_ARG;
+    if (!strcmp(rep_newicks[r], "NA")) continue;                   // a replicate without a tree (non-finite matrix) is skipped
+    if (!ts_parse(rep_newicks[r], &rt) || !ts_hash(&rt, index)) return NGSD_ERR_ARG;
+    ts_splits(rt, &rkeys, nullptr);
+    for (const TsKey &k : rkeys) {
+      auto it = count.find(k);
+      if (it != count.end()) it->second++;
+    }
+    used++;
+  }
+  std::vector<std::string> support(mt.nodes.size());
+  for (size_t v = 1; v < mt.nodes.size(); v++) {
+    if (of_node[v] < 0) continue;
+    const uint64_t c = count[mkeys[of_node[v]]];
+    char buf[32];
+    if (percent) snprintf(buf, sizeof buf, "%d", used ? (int) (0.5 + 100.0 * (double) c / (double) used) : 0);
+    else snprintf(buf, sizeof buf, "%lu", (unsigned long) c);
+    support[v] = buf;
+  }
+  std::string s;
+  ts_write(mt, 0, support, &s);
+  s.push_back(';');
+  *out_len = s.size();
+  if (!out || s.size() + 1 > out_cap) return NGSD_ERR_ARG;
+  memcpy(out, s.c_str(), s.size() + 1);
   return NGSD_OK;
 }

@@ -339,3 +339,7 @@ def test_cli_tree_flag_writes_one_newick_per_matrix(tmp_path):
         want = nj_oracle.nj(m)[0]
         assert nj_oracle.newick_lengths(t)[0] == nj_oracle.newick_lengths(want)[0]
         assert np.allclose(nj_oracle.newick_lengths(t)[1], nj_oracle.newick_lengths(want)[1], atol=1e-8)
+    # FILE.support: the main tree with the percentage of the 5 bootstrap trees holding each internal edge (README.md:83-98,
+    # the raxmlHPC -f b step); the host code behind it is checked against the definition in tests/test_tree_support.py
+    import ngsdist_b200 as nb
+    assert open(tree + ".support").read() == nb.tree_support(trees[0], trees[1:], percent=True) + "\n"
