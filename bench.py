@@ -510,7 +510,8 @@ def single_gpu_extras(nb, torch, np, local, multi):
             exe = tc.dist_imma * 4096.0 / (k_ms * 1e-3) * 1e-12
             row.update({"frontend_ms": fe_ms, "frontend_gbs_raw": cn * cs * 24 / (fe_ms * 1e-3) * 1e-9,
                         "roofline": {"bound": "tensor", "kernel": "k_dist_umma (tcgen05.mma kind::i8, UTCIMMA)", "achieved": exe, "peak": peak,
-                                     "unit": "TMAC/s", "frac": exe / peak, "peak_source": "live back-to-back tcgen05.mma 128x128x32 issue-rate probe in this run"}})
+                                     "unit": "TMAC/s", "frac": exe / peak, "peak_source": "live back-to-back tcgen05.mma 128x128x32 issue-rate probe in this run",
+                                     "note": "achieved = executed int8 MACs (3 K bytes per site since round 2, 4 before); the kernel is bound by the shared-memory pipe (DESIGN.md section 3)"}})
         called["pairwise_del" if pdel else "no_pairwise_del"] = row
         gc.close()
         del oc
